@@ -1,0 +1,298 @@
+"""ctypes binding of the CPU oracle (oracle/tfhe_ntt_oracle.{h,c}) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  The product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ORACLE_DIR = os.path.join(_ROOT, "oracle")
+
+SOLINAS_P = (1 << 64) - (1 << 32) + 1
+
+# enum tfo_native_kind
+NATIVE32_PLAN32, NATIVE32_PLAN52, NATIVE64_PLAN32, NATIVE64_PLAN52, NATIVE128_PLAN32 = range(5)
+NATIVE_BINARY32_PLAN32, NATIVE_BINARY32_PLAN52, NATIVE_BINARY64_PLAN32 = 5, 6, 7
+NATIVE_BINARY64_PLAN52, NATIVE_BINARY128_PLAN32 = 8, 9
+NATIVE_KIND_NAMES = [
+    "native32::Plan32", "native32::Plan52", "native64::Plan32", "native64::Plan52",
+    "native128::Plan32", "native_binary32::Plan32", "native_binary32::Plan52",
+    "native_binary64::Plan32", "native_binary64::Plan52", "native_binary128::Plan32",
+]
+
+
+def build(native=False):
+    """Compile the oracle with gcc (make); returns the path of the shared object."""
+    target = "native" if native else "all"
+    name = "libtfhe_ntt_oracle_native.so" if native else "libtfhe_ntt_oracle.so"
+    so = os.path.join(_ORACLE_DIR, name)
+    src = [os.path.join(_ORACLE_DIR, f) for f in ("tfhe_ntt_oracle.c", "tfhe_ntt_oracle.h")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src)
+    if stale or native:
+        subprocess.run(["make", "-C", _ORACLE_DIR, target], check=True, capture_output=True)
+    return so
+
+
+class Plan64Struct(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("p", C.c_uint64),
+                ("twid", C.POINTER(C.c_uint64)), ("twid_shoup", C.POINTER(C.c_uint64)),
+                ("inv_twid", C.POINTER(C.c_uint64)), ("inv_twid_shoup", C.POINTER(C.c_uint64)),
+                ("use_ifma", C.c_int), ("can_use_fast_reduction_code", C.c_int),
+                ("p_barrett", C.c_uint64), ("big_q", C.c_uint64),
+                ("n_inv_mod_p", C.c_uint64), ("n_inv_mod_p_shoup", C.c_uint64)]
+
+
+class Plan32Struct(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("p", C.c_uint32),
+                ("twid", C.POINTER(C.c_uint32)), ("twid_shoup", C.POINTER(C.c_uint32)),
+                ("inv_twid", C.POINTER(C.c_uint32)), ("inv_twid_shoup", C.POINTER(C.c_uint32)),
+                ("can_use_fast_reduction_code", C.c_int),
+                ("p_barrett", C.c_uint32), ("big_q", C.c_uint32),
+                ("n_inv_mod_p", C.c_uint32), ("n_inv_mod_p_shoup", C.c_uint32)]
+
+
+def _load(native=False):
+    lib = C.CDLL(build(native))
+    u64, u32, sz, vp, i = C.c_uint64, C.c_uint32, C.c_size_t, C.c_void_p, C.c_int
+    P64, P32 = C.POINTER(Plan64Struct), C.POINTER(Plan32Struct)
+    sig = {
+        "tfo_mul_mod64": (u64, [u64, u64, u64]),
+        "tfo_exp_mod64": (u64, [u64, u64, u64]),
+        "tfo_exp_mod32": (u32, [u32, u32, u32]),
+        "tfo_is_prime64": (i, [u64]),
+        "tfo_largest_prime_in_arithmetic_progression64": (i, [u64, u64, u64, u64, C.POINTER(u64)]),
+        "tfo_find_primitive_root64": (i, [u64, u64, C.POINTER(u64)]),
+        "tfo_find_root_solinas_64": (i, [u64, C.POINTER(u64)]),
+        "tfo_bit_rev": (sz, [u32, sz]),
+        "tfo_plan64_try_new": (P64, [sz, u64]),
+        "tfo_plan64_free": (None, [P64]),
+        "tfo_plan64_fwd": (None, [P64, vp]),
+        "tfo_plan64_inv": (None, [P64, vp]),
+        "tfo_plan64_fwd_generic": (None, [P64, vp]),
+        "tfo_plan64_inv_generic": (None, [P64, vp]),
+        "tfo_plan64_normalize": (None, [P64, vp, sz]),
+        "tfo_plan64_mul_assign_normalize": (None, [P64, vp, vp, sz]),
+        "tfo_plan64_mul_accumulate": (None, [P64, vp, vp, vp, sz]),
+        "tfo_plan32_try_new": (P32, [sz, u32]),
+        "tfo_plan32_free": (None, [P32]),
+        "tfo_plan32_fwd": (None, [P32, vp]),
+        "tfo_plan32_inv": (None, [P32, vp]),
+        "tfo_plan32_fwd_generic": (None, [P32, vp]),
+        "tfo_plan32_inv_generic": (None, [P32, vp]),
+        "tfo_plan32_normalize": (None, [P32, vp, sz]),
+        "tfo_plan32_mul_assign_normalize": (None, [P32, vp, vp, sz]),
+        "tfo_plan32_mul_accumulate": (None, [P32, vp, vp, vp, sz]),
+        "tfo_negacyclic_convolution_mod64": (None, [sz, u64, vp, vp, vp]),
+        "tfo_negacyclic_convolution_mod32": (None, [sz, u32, vp, vp, vp]),
+        "tfo_negacyclic_convolution_wrapping_u32": (None, [sz, vp, vp, vp]),
+        "tfo_negacyclic_convolution_wrapping_u64": (None, [sz, vp, vp, vp]),
+        "tfo_negacyclic_convolution_wrapping_u128": (None, [sz, vp, vp, vp]),
+        "tfo_primes32": (u32, [i]),
+        "tfo_primes52": (u64, [i]),
+        "tfo_native_num_primes": (i, [i]),
+        "tfo_native_residue_bytes": (i, [i]),
+        "tfo_native_value_bytes": (i, [i]),
+        "tfo_native_try_new": (vp, [i, sz]),
+        "tfo_native_free": (None, [vp]),
+        "tfo_native_fwd": (None, [vp, vp, C.POINTER(vp), i]),
+        "tfo_native_inv": (None, [vp, vp, C.POINTER(vp)]),
+        "tfo_native_negacyclic_polymul": (None, [vp, vp, vp, vp]),
+        "tfo_reconstruct_32bit_012": (u32, [u32, u32, u32]),
+        "tfo_reconstruct_32bit_01234_v2": (u64, [u32] * 5),
+        "tfo_reconstruct_32bit_01234": (u64, [u32] * 5),
+        "tfo_reconstruct_52bit_012": (u64, [u64] * 3),
+        "tfo_reconstruct_32bit_01": (u32, [u32, u32]),
+        "tfo_reconstruct_32bit_012_u64": (u64, [u32] * 3),
+        "tfo_reconstruct_52bit_01_u64": (u64, [u64, u64]),
+        "tfo_reconstruct_52bit_01_u32": (u32, [u64, u64]),
+        "tfo_reconstruct_52bit_0_u32": (u32, [u64]),
+        "tfo_plan64_fwd_batch": (None, [P64, vp, sz, i]),
+        "tfo_plan64_inv_batch": (None, [P64, vp, sz, i]),
+        "tfo_plan32_fwd_batch": (None, [P32, vp, sz, i]),
+        "tfo_plan32_inv_batch": (None, [P32, vp, sz, i]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(lib, name)
+        f.restype, f.argtypes = res, args
+    return lib
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = _load()
+    return _LIB
+
+
+def _ptr(a):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OraclePlan:
+    """prime32::Plan / prime64::Plan restated (bits = 32 or 64)."""
+
+    def __init__(self, bits, n, p, _lib=None):
+        self.lib = _lib or lib()
+        self.bits, self.n, self.p = bits, n, p
+        self.dtype = np.uint64 if bits == 64 else np.uint32
+        self._pfx = "tfo_plan%d_" % bits
+        self.h = getattr(self.lib, self._pfx + "try_new")(n, p)
+        if not self.h:
+            raise ValueError("try_new returned None")
+
+    @staticmethod
+    def try_new(bits, n, p):
+        try:
+            return OraclePlan(bits, n, p)
+        except ValueError:
+            return None
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            getattr(self.lib, self._pfx + "free")(self.h)
+            self.h = None
+
+    # struct views
+    @property
+    def s(self):
+        return self.h.contents
+
+    def table(self, name):
+        ptr = getattr(self.s, name)
+        if not ptr:
+            return None
+        return np.ctypeslib.as_array(ptr, shape=(self.n,)).copy()
+
+    def _each(self, fn, buf):
+        buf = np.ascontiguousarray(buf, dtype=self.dtype)
+        flat = buf.reshape(-1, self.n)
+        f = getattr(self.lib, self._pfx + fn)
+        for row in flat:
+            f(self.h, _ptr(row))
+        return buf
+
+    def fwd(self, buf):
+        return self._each("fwd", buf.copy())
+
+    def inv(self, buf):
+        return self._each("inv", buf.copy())
+
+    def fwd_generic(self, buf):
+        return self._each("fwd_generic", buf.copy())
+
+    def inv_generic(self, buf):
+        return self._each("inv_generic", buf.copy())
+
+    def normalize(self, values):
+        v = np.ascontiguousarray(values, dtype=self.dtype).copy()
+        getattr(self.lib, self._pfx + "normalize")(self.h, _ptr(v), v.size)
+        return v
+
+    def mul_assign_normalize(self, lhs, rhs):
+        l = np.ascontiguousarray(lhs, dtype=self.dtype).copy()
+        r = np.ascontiguousarray(rhs, dtype=self.dtype)
+        getattr(self.lib, self._pfx + "mul_assign_normalize")(self.h, _ptr(l), _ptr(r), min(l.size, r.size))
+        return l
+
+    def mul_accumulate(self, acc, lhs, rhs):
+        a = np.ascontiguousarray(acc, dtype=self.dtype).copy()
+        l = np.ascontiguousarray(lhs, dtype=self.dtype)
+        r = np.ascontiguousarray(rhs, dtype=self.dtype)
+        getattr(self.lib, self._pfx + "mul_accumulate")(self.h, _ptr(a), _ptr(l), _ptr(r),
+                                                        min(a.size, l.size, r.size))
+        return a
+
+    def fwd_batch_inplace(self, buf, threads):
+        getattr(self.lib, self._pfx + "fwd_batch")(self.h, _ptr(buf), buf.size // self.n, threads)
+
+    def inv_batch_inplace(self, buf, threads):
+        getattr(self.lib, self._pfx + "inv_batch")(self.h, _ptr(buf), buf.size // self.n, threads)
+
+
+def negacyclic_convolution_mod(bits, p, lhs, rhs):
+    dt = np.uint64 if bits == 64 else np.uint32
+    l = np.ascontiguousarray(lhs, dtype=dt)
+    r = np.ascontiguousarray(rhs, dtype=dt)
+    out = np.zeros_like(l)
+    getattr(lib(), "tfo_negacyclic_convolution_mod%d" % bits)(l.size, p, _ptr(l), _ptr(r), _ptr(out))
+    return out
+
+
+VALUE_DTYPES = {4: np.uint32, 8: np.uint64, 16: np.dtype([("lo", np.uint64), ("hi", np.uint64)])}
+
+
+def negacyclic_convolution_wrapping(value_bytes, lhs, rhs):
+    """lhs/rhs: uint32 / uint64 arrays, or (n,2) uint64 (lo,hi) for u128."""
+    l = np.ascontiguousarray(lhs)
+    r = np.ascontiguousarray(rhs)
+    out = np.zeros_like(l)
+    n = l.shape[0]
+    name = {4: "u32", 8: "u64", 16: "u128"}[value_bytes]
+    getattr(lib(), "tfo_negacyclic_convolution_wrapping_" + name)(n, _ptr(l), _ptr(r), _ptr(out))
+    return out
+
+
+class OracleNativePlan:
+    """native{32,64,128}::Plan{32,52} and native_binary*::Plan{32,52} restated."""
+
+    def __init__(self, kind, n):
+        self.lib = lib()
+        self.kind, self.n = kind, n
+        self.num_primes = self.lib.tfo_native_num_primes(kind)
+        self.residue_bytes = self.lib.tfo_native_residue_bytes(kind)
+        self.value_bytes = self.lib.tfo_native_value_bytes(kind)
+        self.rdtype = np.uint32 if self.residue_bytes == 4 else np.uint64
+        self.h = self.lib.tfo_native_try_new(kind, n)
+        if not self.h:
+            raise ValueError("try_new returned None")
+
+    @staticmethod
+    def try_new(kind, n):
+        try:
+            return OracleNativePlan(kind, n)
+        except ValueError:
+            return None
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.tfo_native_free(self.h)
+            self.h = None
+
+    def value_array(self, count=None):
+        n = self.n if count is None else count
+        if self.value_bytes == 16:
+            return np.zeros((n, 2), dtype=np.uint64)
+        return np.zeros(n, dtype=VALUE_DTYPES[self.value_bytes])
+
+    def _res_ptrs(self, res):
+        arr = (C.c_void_p * self.num_primes)()
+        for k in range(self.num_primes):
+            arr[k] = res[k].ctypes.data
+        return arr
+
+    def fwd(self, value, binary=False):
+        value = np.ascontiguousarray(value)
+        res = [np.zeros(self.n, dtype=self.rdtype) for _ in range(self.num_primes)]
+        self.lib.tfo_native_fwd(self.h, _ptr(value), self._res_ptrs(res), int(binary))
+        return res
+
+    def inv(self, residues):
+        res = [np.ascontiguousarray(r, dtype=self.rdtype).copy() for r in residues]
+        value = self.value_array()
+        self.lib.tfo_native_inv(self.h, _ptr(value), self._res_ptrs(res))
+        return value, res
+
+    def negacyclic_polymul(self, lhs, rhs):
+        lhs = np.ascontiguousarray(lhs)
+        rhs = np.ascontiguousarray(rhs)
+        prod = self.value_array()
+        self.lib.tfo_native_negacyclic_polymul(self.h, _ptr(prod), _ptr(lhs), _ptr(rhs))
+        return prod
