@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Headline benchmark: forward + inverse negacyclic NTTs per second, N=2048, u64 Solinas prime
+(2^64 - 2^32 + 1), batched and device-resident, on N B200s (one process per GPU, no collective:
+the polynomial batch shards trivially).
+
+  python bench.py --gpus 1 --steps K --warmup W          # our arm
+  python bench.py --impl reference ...                   # tfhe-ntt's CPU path (C port) on host cores
+
+One "step" = fwd over the whole per-GPU batch, then inv over it (2 * batch transforms).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+N = 2048
+SOLINAS_P = (1 << 64) - (1 << 32) + 1
+BATCH_PER_GPU = 65536          # 65536 * 16 KiB = 1 GiB per GPU: far beyond the 126 MB L2
+ALG_BYTES_PER_NTT = 2 * N * 8  # one in-place NTT reads and writes each coefficient once
+E2E_BATCH = 16384              # host-buffer leg: 256 MiB in + 256 MiB out per step
+METRIC = "fwd+inv NTTs/sec, N=2048 u64 prime, batched"
+UNIT = "NTT/s"
+WORKLOAD = "prime64 Solinas p=2^64-2^32+1 N=2048, batch %d polynomials per GPU, fwd then inv (in place, HBM-resident)" % BATCH_PER_GPU
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples, self.max_mhz, self.reasons = [], None, set()
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def synth(batch, seed):
+    """i.i.d. uniform coefficients in [0, p) from a fixed seed."""
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, 1 << 64, size=(batch, N), dtype=np.uint64, endpoint=False)
+    x[x >= np.uint64(SOLINAS_P)] -= np.uint64(SOLINAS_P)
+    return x
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (oracle port of tfhe-ntt's scalar path; the one place bench.py may execute oracle/)
+# ---------------------------------------------------------------------------------------------
+def cpu_leg(sample_polys, repeats, threads):
+    import oracle_lib
+    lib = oracle_lib._load(native=True)   # rebuilt with -march=native on this host
+    plan = oracle_lib.OraclePlan(64, N, SOLINAS_P, _lib=lib)
+    buf = synth(sample_polys, 0xC0FFEE03)
+    plan.fwd_batch_inplace(buf, threads)  # warm
+    plan.inv_batch_inplace(buf, threads)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        plan.fwd_batch_inplace(buf, threads)
+        plan.inv_batch_inplace(buf, threads)
+    dt = time.perf_counter() - t0
+    return 2.0 * sample_polys * repeats / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 4096
+    # size the sample so the whole run stays within a couple of minutes
+    rate, dt = cpu_leg(sample, 1, threads)
+    steps, warm = args.steps, args.warmup
+    per_step_polys = int(max(256, min(BATCH_PER_GPU, rate * 1.0 / 2)))  # about 1 s of CPU work per step
+    import oracle_lib
+    lib = oracle_lib._load(native=True)
+    plan = oracle_lib.OraclePlan(64, N, SOLINAS_P, _lib=lib)
+    buf = synth(per_step_polys, 0xC0FFEE03)
+    for _ in range(warm):
+        plan.fwd_batch_inplace(buf, threads)
+        plan.inv_batch_inplace(buf, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        plan.fwd_batch_inplace(buf, threads)
+        plan.inv_batch_inplace(buf, threads)
+    dt = time.perf_counter() - t0
+    value = 2.0 * per_step_polys * steps / dt
+    sample_txt = "%d polynomials per step (fwd then inv), %d threads, static contiguous chunks" % (per_step_polys, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "cpu_sample": sample_txt},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt,
+                         "note": "C restatement of tfhe-ntt's scalar CPU path (oracle/); the Rust crate cannot be built in this image"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import tfhe_ntt_b200 as T
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    T.set_device(local)
+    plan = T.prime64.Plan.try_new(N, SOLINAS_P)
+    assert plan is not None
+    stream = torch.cuda.current_stream()
+
+    batch = BATCH_PER_GPU
+    host = synth(4096, 0xC0FFEE03 + rank)
+    d = torch.from_numpy(host.view(np.int64)).cuda().repeat(batch // 4096, 1).contiguous()
+    # make the replicas distinct so no two polynomials are equal
+    d[:, 0] = torch.arange(batch, device="cuda", dtype=torch.int64)
+    torch.cuda.synchronize()
+
+    def step():
+        plan.fwd_device(d, batch, stream=stream)
+        plan.inv_device(d, batch, stream=stream)
+        plan.normalize_device(d, batch * N, stream=stream) if args.normalize else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # per-kernel timing for the roofline: CUDA events on the launching stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_wall0 = time.perf_counter()
+        ev[0].record(stream)
+        for s in range(args.steps):
+            plan.fwd_device(d, batch, stream=stream)
+            ev[2 * s + 1].record(stream)
+            plan.inv_device(d, batch, stream=stream)
+            ev[2 * s + 2].record(stream)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    fwd_ms = sum(ev[2 * s].elapsed_time(ev[2 * s + 1]) for s in range(args.steps)) / args.steps
+    inv_ms = sum(ev[2 * s + 1].elapsed_time(ev[2 * s + 2]) for s in range(args.steps)) / args.steps
+    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = 2.0 * batch * world * args.steps / (total_ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the public batch API, copies inside the timed region ----
+    eb = E2E_BATCH
+    h_in = torch.from_numpy(synth(eb, 0xE2E + rank).view(np.int64)).pin_memory()
+    h_np = h_in.numpy().view(np.uint64)
+    e2e_steps = max(2, min(args.steps, 5))
+    plan.fwd_batch(h_np)
+    plan.inv_batch(h_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.fwd_batch(h_np)   # H2D + fwd + D2H
+        plan.inv_batch(h_np)   # H2D + inv + D2H
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    te = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = 2.0 * eb * world * e2e_steps / float(te.item())
+    e2e_bytes = 2 * eb * N * 8  # per step: the batch crosses PCIe once per call, two calls
+
+    if rank == 0:
+        peaks, which = measured_peaks()
+        hbm = float(peaks["hbm_gbs"])
+        dom_ms = max(fwd_ms, inv_ms)
+        dom = "fwd" if fwd_ms >= inv_ms else "inv"
+        achieved = batch * ALG_BYTES_PER_NTT / (dom_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "n": N, "modulus": SOLINAS_P,
+                       "l2_policy": "inputs (1 GiB per GPU) far larger than the 126 MB L2",
+                       "parallelism": "batch sharded over %d GPU(s), no collective" % world},
+            "roofline": {"bound": "hbm", "kernel": "ntt %s (N=2048 Solinas)" % dom, "achieved": achieved, "peak": hbm,
+                         "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": which,
+                         "fwd_ms": fwd_ms, "inv_ms": inv_ms,
+                         "algorithmic_bytes_per_launch": batch * ALG_BYTES_PER_NTT},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,
+                    "api": "prime64.Plan.fwd_batch + inv_batch on pinned host buffers, batch %d" % eb},
+            "gpu_launches": 2 * args.steps,
+            "clocks": clocks.summary(),
+            "wall_s": t_wall,
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            try:
+                rate, dt = cpu_leg(2048, 1, threads)
+                reps = int(max(1, min(50, 12.0 / max(dt, 1e-3))))
+                rate, dt = cpu_leg(2048, reps, threads)
+                line["cpu_baseline"] = {
+                    "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": "%d x (fwd+inv over 2048 polynomials), %.1f s of CPU work, %d threads" % (reps, dt, threads)}
+            except Exception as e:  # the GPU numbers stand on their own
+                line["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--normalize", action="store_true", help="also run normalize in warm-up steps")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

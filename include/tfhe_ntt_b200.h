@@ -1,0 +1,228 @@
+/*
+ * tfhe_ntt_b200.h -- C ABI of the B200-native batched NTT engine (libtfhe_ntt_b200.so).
+ *
+ * The reference (`tfhe-ntt`, /root/reference/tfhe-ntt/src) is a plain Rust crate with no FFI
+ * layer of its own; its public Rust API is the drop-in boundary (lib.rs:83-116).  Each entry
+ * point below is what a Rust host crate binds to stand in for one reference method; the
+ * citation names the method it replaces.  INTEGRATION.md shows the Rust `extern "C"` block and
+ * the safe wrappers (`prime64::Plan::fwd` ...) a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Return value: NTT_B200_OK (0) on success,
+ *     NTT_B200_NONE where the reference returns `None`, NTT_B200_ERR_LEN where the reference
+ *     panics on a length assertion, NTT_B200_ERR_CUDA on a CUDA failure (text from
+ *     ntt_b200_last_error()).
+ *   - `*_fwd`, `*_inv`, ... with HOST pointers are the per-polynomial drop-ins.
+ *     `*_batch` take HOST pointers to `batch` contiguous polynomials (new; the reference is
+ *     per-polynomial, prime64.rs:897-898).  `*_device` take DEVICE pointers on the plan's GPU
+ *     and a CUDA stream (`void *`, a cudaStream_t; NULL = default stream) and do not synchronise.
+ *   - A plan lives on the CUDA device that was current when it was created; tables are
+ *     immutable afterwards, all entry points are re-entrant on a shared plan
+ *     (reference: plans are Send + Sync, shared through Arc, tfhe ntt64.rs:26-31).
+ *   - Outputs are bit-identical to the reference for inputs in [0, p) (prime plans) / any
+ *     value (native plans).  Inputs >= p are outside the contract, as in the reference.
+ */
+#ifndef TFHE_NTT_B200_H
+#define TFHE_NTT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTT_B200_OK 0
+#define NTT_B200_NONE 1      /* constructor: the reference returns None */
+#define NTT_B200_ERR_LEN 2   /* the reference's assert_eq!(buf.len(), ntt_size()) would panic */
+#define NTT_B200_ERR_CUDA 3  /* CUDA runtime failure; see ntt_b200_last_error() */
+#define NTT_B200_ERR_ARG 4   /* null pointer / unknown plan kind */
+
+const char *ntt_b200_last_error(void); /* thread-local text of the last NTT_B200_ERR_CUDA */
+int ntt_b200_device_count(void);
+int ntt_b200_set_device(int device);   /* device used by subsequently created plans */
+
+/* ------------------------------------------------------------------------------------------
+ * prime64::Plan   (tfhe-ntt/src/prime64.rs:245-261)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ntt_b200_plan64 ntt_b200_plan64;
+
+/* prime64::Plan::try_new(polynomial_size, modulus) -> Option<Plan>   prime64.rs:764-862
+ * NTT_B200_NONE iff n < 16, n not a power of two, p composite, or 2n does not divide p-1. */
+int ntt_b200_plan64_try_new(size_t n, uint64_t p, ntt_b200_plan64 **out);
+/* impl Clone for Plan                                                prime64.rs:244 */
+int ntt_b200_plan64_clone(const ntt_b200_plan64 *plan, ntt_b200_plan64 **out);
+/* Drop */
+void ntt_b200_plan64_free(ntt_b200_plan64 *plan);
+/* Plan::ntt_size / modulus / use_ifma / can_use_fast_reduction_code  prime64.rs:870-890
+ * use_ifma is always 0 (there is no CPU IFMA path); can_use_fast_reduction_code reproduces
+ * prime64.rs:815-817 with use_ifma = false. */
+size_t ntt_b200_plan64_ntt_size(const ntt_b200_plan64 *plan);
+uint64_t ntt_b200_plan64_modulus(const ntt_b200_plan64 *plan);
+int ntt_b200_plan64_use_ifma(const ntt_b200_plan64 *plan);
+int ntt_b200_plan64_can_use_fast_reduction_code(const ntt_b200_plan64 *plan);
+int ntt_b200_plan64_device(const ntt_b200_plan64 *plan);
+
+/* Plan::fwd(&self, buf: &mut [u64])   prime64.rs:897-968 : natural -> bit-reversed, in [0,p) */
+int ntt_b200_plan64_fwd(const ntt_b200_plan64 *plan, uint64_t *buf, size_t len);
+/* Plan::inv(&self, buf: &mut [u64])   prime64.rs:975-1046: bit-reversed -> natural, times n */
+int ntt_b200_plan64_inv(const ntt_b200_plan64 *plan, uint64_t *buf, size_t len);
+/* Plan::normalize(&self, values)      prime64.rs:1137-1179 */
+int ntt_b200_plan64_normalize(const ntt_b200_plan64 *plan, uint64_t *values, size_t len);
+/* Plan::mul_assign_normalize(lhs, rhs) prime64.rs:1050-1133; like the reference's izip!
+ * (lib.rs:658-688) the shorter of the two slices bounds the work */
+int ntt_b200_plan64_mul_assign_normalize(const ntt_b200_plan64 *plan, uint64_t *lhs,
+                                         size_t lhs_len, const uint64_t *rhs, size_t rhs_len);
+/* Plan::mul_accumulate(acc, lhs, rhs) prime64.rs:1182-1222 */
+int ntt_b200_plan64_mul_accumulate(const ntt_b200_plan64 *plan, uint64_t *acc, size_t acc_len,
+                                   const uint64_t *lhs, size_t lhs_len, const uint64_t *rhs,
+                                   size_t rhs_len);
+
+/* batched, host memory: `batch` polynomials of ntt_size() coefficients each, contiguous */
+int ntt_b200_plan64_fwd_batch(const ntt_b200_plan64 *plan, uint64_t *host, size_t batch);
+int ntt_b200_plan64_inv_batch(const ntt_b200_plan64 *plan, uint64_t *host, size_t batch);
+
+/* device-resident: pointers on the plan's GPU, asynchronous on `stream` */
+int ntt_b200_plan64_fwd_device(const ntt_b200_plan64 *plan, uint64_t *dev, size_t batch,
+                               void *stream);
+int ntt_b200_plan64_inv_device(const ntt_b200_plan64 *plan, uint64_t *dev, size_t batch,
+                               void *stream);
+int ntt_b200_plan64_normalize_device(const ntt_b200_plan64 *plan, uint64_t *dev, size_t len,
+                                     void *stream);
+/* rhs (and lhs for mul_accumulate) may be shorter than the destination: it is then reused
+ * cyclically (len must be a multiple of its length) -- e.g. one GGSW row shared by the batch. */
+int ntt_b200_plan64_mul_assign_normalize_device(const ntt_b200_plan64 *plan, uint64_t *lhs,
+                                                size_t len, const uint64_t *rhs, size_t rhs_len,
+                                                void *stream);
+int ntt_b200_plan64_mul_accumulate_device(const ntt_b200_plan64 *plan, uint64_t *acc, size_t len,
+                                          const uint64_t *lhs, size_t lhs_len,
+                                          const uint64_t *rhs, size_t rhs_len, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * prime32::Plan   (tfhe-ntt/src/prime32.rs:632-648); same shape with u32 and n >= 32
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ntt_b200_plan32 ntt_b200_plan32;
+
+int ntt_b200_plan32_try_new(size_t n, uint32_t p, ntt_b200_plan32 **out); /* prime32.rs:662-765 */
+int ntt_b200_plan32_clone(const ntt_b200_plan32 *plan, ntt_b200_plan32 **out);
+void ntt_b200_plan32_free(ntt_b200_plan32 *plan);
+size_t ntt_b200_plan32_ntt_size(const ntt_b200_plan32 *plan);                 /* prime32.rs:773 */
+uint32_t ntt_b200_plan32_modulus(const ntt_b200_plan32 *plan);                /* prime32.rs:779 */
+int ntt_b200_plan32_can_use_fast_reduction_code(const ntt_b200_plan32 *plan); /* prime32.rs:785 */
+int ntt_b200_plan32_device(const ntt_b200_plan32 *plan);
+
+int ntt_b200_plan32_fwd(const ntt_b200_plan32 *plan, uint32_t *buf, size_t len); /* :797-843 */
+int ntt_b200_plan32_inv(const ntt_b200_plan32 *plan, uint32_t *buf, size_t len); /* :850-896 */
+int ntt_b200_plan32_normalize(const ntt_b200_plan32 *plan, uint32_t *values, size_t len); /* :956 */
+int ntt_b200_plan32_mul_assign_normalize(const ntt_b200_plan32 *plan, uint32_t *lhs,
+                                         size_t lhs_len, const uint32_t *rhs,
+                                         size_t rhs_len); /* :900-952 */
+int ntt_b200_plan32_mul_accumulate(const ntt_b200_plan32 *plan, uint32_t *acc, size_t acc_len,
+                                   const uint32_t *lhs, size_t lhs_len, const uint32_t *rhs,
+                                   size_t rhs_len); /* :993-1015 */
+int ntt_b200_plan32_fwd_batch(const ntt_b200_plan32 *plan, uint32_t *host, size_t batch);
+int ntt_b200_plan32_inv_batch(const ntt_b200_plan32 *plan, uint32_t *host, size_t batch);
+int ntt_b200_plan32_fwd_device(const ntt_b200_plan32 *plan, uint32_t *dev, size_t batch,
+                               void *stream);
+int ntt_b200_plan32_inv_device(const ntt_b200_plan32 *plan, uint32_t *dev, size_t batch,
+                               void *stream);
+int ntt_b200_plan32_normalize_device(const ntt_b200_plan32 *plan, uint32_t *dev, size_t len,
+                                     void *stream);
+int ntt_b200_plan32_mul_assign_normalize_device(const ntt_b200_plan32 *plan, uint32_t *lhs,
+                                                size_t len, const uint32_t *rhs, size_t rhs_len,
+                                                void *stream);
+int ntt_b200_plan32_mul_accumulate_device(const ntt_b200_plan32 *plan, uint32_t *acc, size_t len,
+                                          const uint32_t *lhs, size_t lhs_len,
+                                          const uint32_t *rhs, size_t rhs_len, void *stream);
+
+/* Fused fwd -> mul_accumulate -> inv on device (BASELINE config C2):
+ *   out[b] = inv(acc[b] + fwd(lhs[b]) (*) rhs[b])   with rhs, acc already in the NTT domain.
+ * rhs_polys / acc_polys < batch reuse those operands cyclically (0 acc_polys = no accumulator).
+ * Equivalent to Plan::fwd + Plan::mul_accumulate + Plan::inv called in sequence. */
+int ntt_b200_plan32_fwd_mac_inv_device(const ntt_b200_plan32 *plan, uint32_t *out,
+                                       const uint32_t *lhs, const uint32_t *rhs, size_t rhs_polys,
+                                       const uint32_t *acc, size_t acc_polys, size_t batch,
+                                       void *stream);
+int ntt_b200_plan64_fwd_mac_inv_device(const ntt_b200_plan64 *plan, uint64_t *out,
+                                       const uint64_t *lhs, const uint64_t *rhs, size_t rhs_polys,
+                                       const uint64_t *acc, size_t acc_polys, size_t batch,
+                                       void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CRT ("native") plans
+ *   native32::{Plan32,Plan52}          native32.rs:8-18,  :334-498
+ *   native64::{Plan32,Plan52}          native64.rs:16-33, :929-1164
+ *   native128::Plan32                  native128.rs:6-17, :120-349
+ *   native_binary32::{Plan32,Plan52}   native_binary32.rs:11-18, :186-310
+ *   native_binary64::{Plan32,Plan52}   native_binary64.rs:17-28, :341-515
+ *   native_binary128::Plan32           native_binary128.rs:4-10, :65-200
+ * One handle type; `kind` selects the reference type.  value elements are u32 / u64 / u128
+ * (16 bytes, little endian) and residues are u32 (Plan32) or u64 (Plan52):
+ * see ntt_b200_native_value_bytes / _residue_bytes / _num_primes.
+ * Plan52::try_new in the reference also requires an AVX512-IFMA CPU (native64.rs:1079);
+ * the GPU engine always provides the 52-bit plans.
+ * ------------------------------------------------------------------------------------------ */
+enum ntt_b200_native_kind {
+    NTT_B200_NATIVE32_PLAN32 = 0,
+    NTT_B200_NATIVE32_PLAN52 = 1,
+    NTT_B200_NATIVE64_PLAN32 = 2,
+    NTT_B200_NATIVE64_PLAN52 = 3,
+    NTT_B200_NATIVE128_PLAN32 = 4,
+    NTT_B200_NATIVE_BINARY32_PLAN32 = 5,
+    NTT_B200_NATIVE_BINARY32_PLAN52 = 6,
+    NTT_B200_NATIVE_BINARY64_PLAN32 = 7,
+    NTT_B200_NATIVE_BINARY64_PLAN52 = 8,
+    NTT_B200_NATIVE_BINARY128_PLAN32 = 9
+};
+typedef struct ntt_b200_native_plan ntt_b200_native_plan;
+
+int ntt_b200_native_num_primes(int kind);
+int ntt_b200_native_residue_bytes(int kind);
+int ntt_b200_native_value_bytes(int kind);
+
+/* PlanXX::try_new(n) -> Option<Self>   e.g. native64.rs:932-941 */
+int ntt_b200_native_try_new(int kind, size_t n, ntt_b200_native_plan **out);
+void ntt_b200_native_free(ntt_b200_native_plan *plan);
+size_t ntt_b200_native_ntt_size(const ntt_b200_native_plan *plan); /* e.g. native64.rs:945 */
+int ntt_b200_native_kind_of(const ntt_b200_native_plan *plan);
+/* PlanXX::ntt_0() .. ntt_9(): the per-prime plan (borrowed; owned by the native plan).
+ * Returns ntt_b200_plan32* for Plan32 kinds, ntt_b200_plan64* for Plan52 kinds. */
+const void *ntt_b200_native_ntt_i(const ntt_b200_native_plan *plan, int i); /* native64.rs:950-968 */
+
+/* PlanXX::fwd(value, mod_p0, ..)        e.g. native64.rs:970-998; binary != 0 selects
+ * fwd_binary (native_binary64.rs:371-388).  residues[i] points at `len` elements. */
+int ntt_b200_native_fwd(const ntt_b200_native_plan *plan, const void *value, size_t len,
+                        void *const *residues, int binary);
+/* PlanXX::inv(value, mod_p0, ..)        e.g. native64.rs:1000-1037.  The residue buffers are
+ * transformed in place (clobbered), as in the reference. */
+int ntt_b200_native_inv(const ntt_b200_native_plan *plan, void *value, size_t len,
+                        void *const *residues);
+/* PlanXX::negacyclic_polymul(prod, lhs, rhs)  e.g. native64.rs:1041-1068; the three slices must
+ * have equal length n (NTT_B200_ERR_LEN otherwise, where the reference asserts). */
+int ntt_b200_native_negacyclic_polymul(const ntt_b200_native_plan *plan, void *prod,
+                                       size_t prod_len, const void *lhs, size_t lhs_len,
+                                       const void *rhs, size_t rhs_len);
+/* batched host / device-resident forms: `batch` contiguous polynomials per operand */
+int ntt_b200_native_negacyclic_polymul_batch(const ntt_b200_native_plan *plan, void *prod,
+                                             const void *lhs, const void *rhs, size_t batch);
+int ntt_b200_native_negacyclic_polymul_device(const ntt_b200_native_plan *plan, void *prod,
+                                              const void *lhs, const void *rhs, size_t batch,
+                                              void *stream);
+int ntt_b200_native_fwd_device(const ntt_b200_native_plan *plan, const void *value,
+                               void *const *residues, size_t batch, int binary, void *stream);
+int ntt_b200_native_inv_device(const ntt_b200_native_plan *plan, void *value,
+                               void *const *residues, size_t batch, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * plan-build helpers that are public in the reference crate
+ * ------------------------------------------------------------------------------------------ */
+/* prime::is_prime64                                    prime.rs:76-126 */
+int ntt_b200_is_prime64(uint64_t n);
+/* prime::largest_prime_in_arithmetic_progression64     prime.rs:130-186 ; 0 = None */
+int ntt_b200_largest_prime_in_arithmetic_progression64(uint64_t factor, uint64_t offset,
+                                                       uint64_t lo, uint64_t hi, uint64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFHE_NTT_B200_H */

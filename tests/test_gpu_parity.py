@@ -1,0 +1,286 @@
+"""GPU parity: the CUDA engine (through the C ABI / the tfhe_ntt_b200 host mirror) against the
+CPU oracle on the same seeded inputs.  Bit-exact (integer path)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from oracle_lib import OraclePlan, OracleNativePlan, SOLINAS_P
+
+pytestmark = pytest.mark.gpu
+
+PRIMES64 = [1125899904679937, 2251799813554177, 4611686018427322369, 9223372036853661697,
+            18446744073707716609, SOLINAS_P]
+PRIMES32 = [1062862849, 1073479681, 2147352577, 4293918721]
+
+
+@pytest.fixture(scope="module")
+def T():
+    import tfhe_ntt_b200
+    return tfhe_ntt_b200
+
+
+def rand_below(rng, p, shape, dtype):
+    hi = rng.integers(0, 1 << 32, size=shape, dtype=np.uint64)
+    lo = rng.integers(0, 1 << 32, size=shape, dtype=np.uint64)
+    v = (hi << np.uint64(32)) | lo
+    if p <= (1 << 32):
+        return (v % np.uint64(p)).astype(dtype)
+    # python ints for the 64-bit moduli (numpy % on uint64 is exact too, but keep it obviously so)
+    return np.array([int(x) % p for x in v.ravel()], dtype=np.uint64).reshape(shape).astype(dtype)
+
+
+def edge_rows(p, n, dtype):
+    rows = [np.zeros(n, dtype=dtype), np.full(n, p - 1, dtype=dtype), np.full(n, 1, dtype=dtype),
+            np.arange(n, dtype=np.uint64).astype(dtype)]
+    rows[3] = (rows[3].astype(np.uint64) % np.uint64(min(p, (1 << 63)))).astype(dtype)
+    return np.stack(rows)
+
+
+def plan_pair(T, bits, n, p):
+    mod = T.prime64 if bits == 64 else T.prime32
+    return mod.Plan.try_new(n, p), OraclePlan.try_new(bits, n, p)
+
+
+@pytest.mark.parametrize("p", PRIMES64)
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768])
+def test_prime64_fwd_inv(T, p, n):
+    gp, op = plan_pair(T, 64, n, p)
+    assert (gp is None) == (op is None)
+    if gp is None:
+        pytest.skip("no plan")
+    rng = np.random.default_rng(n + p % 9973)
+    nrand = 3 if n <= 4096 else 2
+    x = np.concatenate([rand_below(rng, p, (nrand, n), np.uint64), edge_rows(p, n, np.uint64)])
+    want_f = op.fwd(x)
+    got = x.copy()
+    gp.fwd_batch(got)
+    assert (got == want_f).all()
+    assert (got < np.uint64(p)).all()
+    want_i = op.inv(want_f)
+    gp.inv_batch(got)
+    assert (got == want_i).all()
+    # per-polynomial drop-in call
+    one = x[0].copy()
+    gp.fwd(one)
+    assert (one == want_f[0]).all()
+    gp.inv(one)
+    assert (one == want_i[0]).all()
+
+
+def test_prime64_solinas_large_n(T):
+    for n in [65536, 131072]:
+        gp, op = plan_pair(T, 64, n, SOLINAS_P)
+        rng = np.random.default_rng(n)
+        x = rand_below(rng, SOLINAS_P, (2, n), np.uint64)
+        want = op.fwd(x)
+        got = x.copy()
+        gp.fwd_batch(got)
+        assert (got == want).all()
+        gp.inv_batch(got)
+        assert (got == op.inv(want)).all()
+
+
+@pytest.mark.parametrize("p", PRIMES32)
+@pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536])
+def test_prime32_fwd_inv(T, p, n):
+    gp, op = plan_pair(T, 32, n, p)
+    assert (gp is None) == (op is None)
+    if gp is None:
+        pytest.skip("no plan")
+    rng = np.random.default_rng(n + p % 9973)
+    x = np.concatenate([rand_below(rng, p, (3, n), np.uint32), edge_rows(p, n, np.uint32)])
+    want_f = op.fwd(x)
+    got = x.copy()
+    gp.fwd_batch(got)
+    assert (got == want_f).all()
+    want_i = op.inv(want_f)
+    gp.inv_batch(got)
+    assert (got == want_i).all()
+
+
+@pytest.mark.parametrize("bits,p", [(64, p) for p in PRIMES64] + [(32, p) for p in PRIMES32])
+def test_pointwise(T, bits, p):
+    n = 256
+    gp, op = plan_pair(T, bits, n, p)
+    dt = np.uint64 if bits == 64 else np.uint32
+    rng = np.random.default_rng(p % 1000)
+    acc, lhs, rhs = (rand_below(rng, p, n, dt) for _ in range(3))
+    for edge in (0, p - 1):
+        lhs[edge % 7] = edge
+        rhs[edge % 5] = edge
+    a = acc.copy()
+    gp.mul_accumulate(a, lhs, rhs)
+    assert (a == op.mul_accumulate(acc, lhs, rhs)).all()
+    l = lhs.copy()
+    gp.mul_assign_normalize(l, rhs)
+    assert (l == op.mul_assign_normalize(lhs, rhs)).all()
+    v = lhs.copy()
+    gp.normalize(v)
+    assert (v == op.normalize(lhs)).all()
+    # izip! truncation (lib.rs:658-688): the shortest slice bounds the work
+    a = acc.copy()
+    gp.mul_accumulate(a, lhs[:100], rhs[:50])
+    assert (a[:50] == op.mul_accumulate(acc[:50], lhs[:50], rhs[:50])).all()
+    assert (a[50:] == acc[50:]).all()
+    assert gp.can_use_fast_reduction_code() == bool(op.s.can_use_fast_reduction_code)
+    assert gp.ntt_size() == n and gp.modulus() == p
+
+
+def test_try_new_rejections_and_errors(T):
+    assert T.prime64.Plan.try_new(2048, 1024) is None          # prime64.rs:1988-1990
+    assert T.prime64.Plan.try_new(8, SOLINAS_P) is None
+    assert T.prime64.Plan.try_new(48, SOLINAS_P) is None
+    assert T.prime32.Plan.try_new(16, 1062862849) is None
+    assert T.prime32.Plan.try_new(1 << 17, 1062862849) is None
+    plan = T.prime64.Plan.try_new(32, SOLINAS_P)
+    assert not plan.use_ifma()
+    with pytest.raises(AssertionError):  # assert_eq!(buf.len(), self.ntt_size()) prime64.rs:898
+        plan.fwd(np.zeros(64, dtype=np.uint64))
+    with pytest.raises(AssertionError):
+        plan.inv(np.zeros(16, dtype=np.uint64))
+    c = plan.clone()
+    x = np.arange(32, dtype=np.uint64)
+    y = x.copy()
+    plan.fwd(x)
+    c.fwd(y)
+    assert (x == y).all()
+    # empty batch is a no-op
+    plan.fwd_batch(np.zeros(0, dtype=np.uint64))
+
+
+def test_doc_example(T):
+    # crate doc example lib.rs:25-49
+    N, p = 32, 1062862849
+    plan = T.prime32.Plan.try_new(N, p)
+    data = np.arange(N, dtype=np.uint32)
+    t = data.copy()
+    plan.fwd(t)
+    assert [int(v) for v in t[:4]] == [8337849, 878691898, 914453352, 923715776]
+    plan.inv(t)
+    assert (t == (data.astype(np.uint64) * N % p).astype(np.uint32)).all()
+
+
+def test_device_api_and_fused(T):
+    import torch
+    n, p, batch = 2048, 1073479681, 24
+    gp, op = plan_pair(T, 32, n, p)
+    rng = np.random.default_rng(3)
+    lhs = rand_below(rng, p, (batch, n), np.uint32)
+    rhs = rand_below(rng, p, (batch, n), np.uint32)
+    acc = rand_below(rng, p, (batch, n), np.uint32)
+    want = op.inv(op.mul_accumulate(acc, op.fwd(lhs), rhs))
+    d_l = torch.from_numpy(lhs.view(np.int32)).cuda()
+    d_r = torch.from_numpy(rhs.view(np.int32)).cuda()
+    d_a = torch.from_numpy(acc.view(np.int32)).cuda()
+    d_o = torch.empty_like(d_l)
+    st = torch.cuda.current_stream()
+    gp.fwd_mac_inv_device(d_o, d_l, d_r, d_a, stream=st)
+    got = d_o.cpu().numpy().view(np.uint32)
+    assert (got == want).all()
+    # shared rhs row (one GGSW row for the whole batch), no accumulator
+    want2 = op.inv(op.mul_accumulate(np.zeros_like(lhs), op.fwd(lhs), np.tile(rhs[0], (batch, 1))))
+    gp.fwd_mac_inv_device(d_o, d_l, d_r[:1].contiguous(), None, stream=st)
+    assert (d_o.cpu().numpy().view(np.uint32) == want2).all()
+    # unfused device sequence gives the same
+    d_x = d_l.clone()
+    gp.fwd_device(d_x, stream=st)
+    gp.mul_accumulate_device(d_a, d_x, d_r, stream=st)
+    gp.inv_device(d_a, stream=st)
+    assert (d_a.cpu().numpy().view(np.uint32) == want).all()
+
+    n, batch = 2048, 16
+    gp, op = plan_pair(T, 64, n, SOLINAS_P)
+    x = rand_below(rng, SOLINAS_P, (batch, n), np.uint64)
+    g = rand_below(rng, SOLINAS_P, (2, n), np.uint64)
+    d_x = torch.from_numpy(x.view(np.int64)).cuda()
+    d_g = torch.from_numpy(g.view(np.int64)).cuda()
+    d_o = torch.empty_like(d_x)
+    gp.fwd_mac_inv_device(d_o, d_x, d_g, None, stream=st)
+    want = op.inv(op.mul_accumulate(np.zeros_like(x), op.fwd(x), np.tile(g, (batch // 2, 1))))
+    assert (d_o.cpu().numpy().view(np.uint64) == want).all()
+    d_n = d_o.clone()
+    gp.normalize_device(d_n, stream=st)
+    assert (d_n.cpu().numpy().view(np.uint64).ravel() == op.normalize(want.ravel())).all()
+
+
+def rand_values(rng, value_bytes, shape, binary=False):
+    n = int(np.prod(shape))
+    if binary:
+        bits = rng.integers(0, 2, size=n, dtype=np.uint64)
+        if value_bytes == 16:
+            return np.stack([bits, np.zeros(n, dtype=np.uint64)], axis=1)
+        return bits.astype(O.VALUE_DTYPES[value_bytes])
+    raw = rng.integers(0, 1 << 63, size=(n, 2), dtype=np.uint64) * 2 + rng.integers(0, 2, size=(n, 2), dtype=np.uint64)
+    if value_bytes == 16:
+        return np.ascontiguousarray(raw)
+    return raw[:, 0].astype(O.VALUE_DTYPES[value_bytes])
+
+
+def native_cls(T, kind):
+    return [T.native32.Plan32, T.native32.Plan52, T.native64.Plan32, T.native64.Plan52,
+            T.native128.Plan32, T.native_binary32.Plan32, T.native_binary32.Plan52,
+            T.native_binary64.Plan32, T.native_binary64.Plan52, T.native_binary128.Plan32][kind]
+
+
+@pytest.mark.parametrize("kind", range(10))
+@pytest.mark.parametrize("n", [32, 256, 2048])
+def test_native_plans(T, kind, n):
+    gp = native_cls(T, kind).try_new(n)
+    op = OracleNativePlan(kind, n)
+    vb = op.value_bytes
+    is_binary = kind >= O.NATIVE_BINARY32_PLAN32
+    rng = np.random.default_rng(kind * 31 + n)
+    value = rand_values(rng, vb, n)
+    # fwd
+    res = [np.zeros(n, dtype=op.rdtype) for _ in range(op.num_primes)]
+    gp.fwd(value, *res)
+    want_res = op.fwd(value)
+    for a, b in zip(res, want_res):
+        assert (a == b).all()
+    if is_binary:
+        bval = rand_values(rng, vb, n, binary=True)
+        bres = [np.zeros(n, dtype=op.rdtype) for _ in range(op.num_primes)]
+        gp.fwd_binary(bval, *bres)
+        for a, b in zip(bres, op.fwd(bval, binary=True)):
+            assert (a == b).all()
+    # inv on arbitrary canonical residues (the reference's scalar-vs-SIMD CRT test, native64.rs:1246-1292)
+    rr = [rand_below(rng, int(op.lib.tfo_primes32(j)) if op.residue_bytes == 4 else int(op.lib.tfo_primes52(j)),
+                     n, op.rdtype) for j in range(op.num_primes)]
+    want_val, want_clobbered = op.inv(rr)
+    got_val = op.value_array()
+    got_res = [r.copy() for r in rr]
+    gp.inv(got_val, *got_res)
+    assert (got_val == want_val).all()
+    for a, b in zip(got_res, want_clobbered):  # inv clobbers the residue buffers (native64.rs:1009-1013)
+        assert (a == b).all()
+    # polymul
+    lhs = rand_values(rng, vb, n)
+    rhs = rand_values(rng, vb, n, binary=is_binary)
+    prod = op.value_array()
+    gp.negacyclic_polymul(prod, lhs, rhs)
+    assert (prod == op.negacyclic_polymul(lhs, rhs)).all()
+    assert (prod == O.negacyclic_convolution_wrapping(vb, lhs, rhs)).all()
+    assert gp.ntt_size() == n
+    assert gp.ntt_0().modulus() == (op.lib.tfo_primes32(0) if op.residue_bytes == 4 else op.lib.tfo_primes52(0))
+    with pytest.raises(AssertionError):
+        gp.negacyclic_polymul(prod, lhs[: n // 2], rhs)
+
+
+def test_native_try_new_none(T):
+    # P1,P5,P6,P7 are 1 mod 2^16 only: native64::Plan32 stops at n = 32768
+    assert T.native64.Plan32.try_new(65536) is None
+    assert T.native64.Plan32.try_new(16) is None
+    assert T.native64.Plan32.try_new(32768) is not None
+
+
+def test_native_batch(T):
+    n, batch = 1024, 20
+    gp = T.native64.Plan32.try_new(n)
+    op = OracleNativePlan(O.NATIVE64_PLAN32, n)
+    rng = np.random.default_rng(77)
+    lhs = rand_values(rng, 8, batch * n).reshape(batch, n)
+    rhs = rand_values(rng, 8, batch * n).reshape(batch, n)
+    prod = np.zeros_like(lhs)
+    gp.negacyclic_polymul_batch(prod, lhs, rhs)
+    for b in range(batch):
+        assert (prod[b] == op.negacyclic_polymul(lhs[b], rhs[b])).all()

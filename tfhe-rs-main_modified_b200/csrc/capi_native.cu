@@ -1,0 +1,586 @@
+// CRT ("native") plans: split into residues, per-prime NTTs, Garner recombination.
+// Reference: tfhe-ntt/src/native32.rs, native64.rs, native128.rs, native_binary{32,64,128}.rs;
+// constants tfhe-ntt/src/lib.rs:451-656 (recomputed here from the literal primes).
+#include <algorithm>
+#include <vector>
+
+#include "capi_common.cuh"
+#include "ntt_arith.cuh"
+#include "plan_math.hpp"
+
+using namespace nttb200;
+using pm::u128;
+
+namespace {
+
+struct KindInfo {
+    int num_primes, residue_bytes, value_bytes, binary;
+};
+const KindInfo kKinds[10] = {
+    {3, 4, 4, 0},   // native32::Plan32          native32.rs:8-12
+    {2, 8, 4, 0},   // native32::Plan52          native32.rs:18
+    {5, 4, 8, 0},   // native64::Plan32          native64.rs:16-22
+    {3, 8, 8, 0},   // native64::Plan52          native64.rs:28-33
+    {10, 4, 16, 0}, // native128::Plan32         native128.rs:6-17
+    {2, 4, 4, 1},   // native_binary32::Plan32   native_binary32.rs:11
+    {1, 8, 4, 1},   // native_binary32::Plan52   native_binary32.rs:18
+    {3, 4, 8, 1},   // native_binary64::Plan32   native_binary64.rs:17-21
+    {2, 8, 8, 1},   // native_binary64::Plan52   native_binary64.rs:28
+    {5, 4, 16, 1},  // native_binary128::Plan32  native_binary128.rs:4-10
+};
+
+struct U128 {
+    uint64_t lo, hi;
+};
+__host__ __device__ inline U128 u128_add(U128 a, U128 b) {
+    U128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo);
+    return r;
+}
+__host__ __device__ inline U128 u128_sub(U128 a, U128 b) {
+    U128 r;
+    r.lo = a.lo - b.lo;
+    r.hi = a.hi - b.hi - (a.lo < b.lo);
+    return r;
+}
+__device__ inline U128 u128_mul(U128 a, U128 b) {  // wrapping
+    U128 r;
+    r.lo = a.lo * b.lo;
+    r.hi = __umul64hi(a.lo, b.lo) + a.lo * b.hi + a.hi * b.lo;
+    return r;
+}
+inline U128 to_U128(u128 v) { return U128{(uint64_t)v, (uint64_t)(v >> 64)}; }
+
+// All CRT constants (lib.rs:517-598, :639-653), by value as a kernel parameter.
+struct CrtConsts {
+    uint32_t P[10];
+    uint64_t P_b64[10];  // floor(2^64 / P_i): exact 64-bit Barrett for `% P_i`
+    uint32_t P_c64[10];  // 2^64 mod P_i (u128 split)
+    uint64_t Q[3];       // primes52 P0..P2
+    uint64_t Q_b64[3];
+    // primes32
+    uint32_t P0_INV_MOD_P1, P01_INV_MOD_P2, P1_INV_MOD_P2, P3_INV_MOD_P4;
+    uint32_t P2_INV_MOD_P3, P4_INV_MOD_P5, P6_INV_MOD_P7, P8_INV_MOD_P9;
+    uint64_t P12, P34, P0_INV_MOD_P12, P0_INV_MOD_P12_SHOUP, P0_MOD_P34_SHOUP, P012_INV_MOD_P34,
+        P012_INV_MOD_P34_SHOUP;
+    uint64_t P01, P23, P45, P67, P89;
+    uint64_t P01_MOD_P45_SHOUP, P01_MOD_P67_SHOUP, P01_MOD_P89_SHOUP, P23_MOD_P67_SHOUP,
+        P23_MOD_P89_SHOUP, P45_MOD_P89_SHOUP;
+    uint64_t P01_INV_MOD_P23, P01_INV_MOD_P23_SHOUP, P0123_INV_MOD_P45, P0123_INV_MOD_P45_SHOUP,
+        P012345_INV_MOD_P67, P012345_INV_MOD_P67_SHOUP, P01234567_INV_MOD_P89,
+        P01234567_INV_MOD_P89_SHOUP;
+    U128 P0123, P012345, P01234567, P0123456789;
+    // primes52: exact products through 64-bit Shoup pairs
+    uint64_t Q0_INV_MOD_Q1, Q0_INV_MOD_Q1_SHOUP, Q01_INV_MOD_Q2, Q01_INV_MOD_Q2_SHOUP,
+        Q0_MOD_Q2_SHOUP;
+};
+
+uint64_t inv_mod_composite(uint64_t x, uint64_t modulus, uint64_t pa, uint64_t pb) {
+    // lib.rs:539-548: x^(phi(pa*pb) - 1)
+    return pm::powmod(x, (pa - 1) * (pb - 1) - 1, modulus);
+}
+
+CrtConsts make_consts() {
+    CrtConsts k{};
+    const uint32_t* P = pm::kPrimes32;
+    for (int i = 0; i < 10; ++i) {
+        k.P[i] = P[i];
+        k.P_b64[i] = ~uint64_t(0) / P[i];
+        k.P_c64[i] = (uint32_t)((((u128)1) << 64) % P[i]);
+    }
+    for (int i = 0; i < 3; ++i) {
+        k.Q[i] = pm::kPrimes52[i];
+        k.Q_b64[i] = ~uint64_t(0) / k.Q[i];
+    }
+    auto inv32 = [](uint32_t x, uint32_t p) { return (uint32_t)pm::inv_mod_prime(x % p, p); };
+    k.P0_INV_MOD_P1 = inv32(P[0], P[1]);
+    k.P01_INV_MOD_P2 = inv32((uint32_t)pm::mulmod(P[0], P[1], P[2]), P[2]);
+    k.P1_INV_MOD_P2 = inv32(P[1], P[2]);
+    k.P3_INV_MOD_P4 = inv32(P[3], P[4]);
+    k.P2_INV_MOD_P3 = inv32(P[2], P[3]);
+    k.P4_INV_MOD_P5 = inv32(P[4], P[5]);
+    k.P6_INV_MOD_P7 = inv32(P[6], P[7]);
+    k.P8_INV_MOD_P9 = inv32(P[8], P[9]);
+    k.P12 = (uint64_t)P[1] * P[2];
+    k.P34 = (uint64_t)P[3] * P[4];
+    k.P0_INV_MOD_P12 = inv_mod_composite(P[0], k.P12, P[1], P[2]);
+    k.P0_INV_MOD_P12_SHOUP = pm::shoup64(k.P0_INV_MOD_P12, k.P12);
+    k.P0_MOD_P34_SHOUP = pm::shoup64(P[0], k.P34);
+    k.P012_INV_MOD_P34 = inv_mod_composite(pm::mulmod(P[0], k.P12, k.P34), k.P34, P[3], P[4]);
+    k.P012_INV_MOD_P34_SHOUP = pm::shoup64(k.P012_INV_MOD_P34, k.P34);
+    k.P01 = (uint64_t)P[0] * P[1];
+    k.P23 = (uint64_t)P[2] * P[3];
+    k.P45 = (uint64_t)P[4] * P[5];
+    k.P67 = (uint64_t)P[6] * P[7];
+    k.P89 = (uint64_t)P[8] * P[9];
+    k.P01_MOD_P45_SHOUP = pm::shoup64(k.P01, k.P45);
+    k.P01_MOD_P67_SHOUP = pm::shoup64(k.P01, k.P67);
+    k.P01_MOD_P89_SHOUP = pm::shoup64(k.P01, k.P89);
+    k.P23_MOD_P67_SHOUP = pm::shoup64(k.P23, k.P67);
+    k.P23_MOD_P89_SHOUP = pm::shoup64(k.P23, k.P89);
+    k.P45_MOD_P89_SHOUP = pm::shoup64(k.P45, k.P89);
+    k.P01_INV_MOD_P23 = inv_mod_composite(k.P01, k.P23, P[2], P[3]);
+    k.P01_INV_MOD_P23_SHOUP = pm::shoup64(k.P01_INV_MOD_P23, k.P23);
+    uint64_t p0123_45 = pm::mulmod(k.P01 % k.P45, k.P23 % k.P45, k.P45);
+    k.P0123_INV_MOD_P45 = inv_mod_composite(p0123_45, k.P45, P[4], P[5]);
+    k.P0123_INV_MOD_P45_SHOUP = pm::shoup64(k.P0123_INV_MOD_P45, k.P45);
+    uint64_t p012345_67 =
+        pm::mulmod(pm::mulmod(k.P01 % k.P67, k.P23 % k.P67, k.P67), k.P45 % k.P67, k.P67);
+    k.P012345_INV_MOD_P67 = inv_mod_composite(p012345_67, k.P67, P[6], P[7]);
+    k.P012345_INV_MOD_P67_SHOUP = pm::shoup64(k.P012345_INV_MOD_P67, k.P67);
+    uint64_t p01234567_89 = pm::mulmod(
+        pm::mulmod(pm::mulmod(k.P01 % k.P89, k.P23 % k.P89, k.P89), k.P45 % k.P89, k.P89),
+        k.P67 % k.P89, k.P89);
+    k.P01234567_INV_MOD_P89 = inv_mod_composite(p01234567_89, k.P89, P[8], P[9]);
+    k.P01234567_INV_MOD_P89_SHOUP = pm::shoup64(k.P01234567_INV_MOD_P89, k.P89);
+    u128 p0123 = (u128)k.P01 * k.P23, p012345 = p0123 * k.P45, p01234567 = p012345 * k.P67;
+    k.P0123 = to_U128(p0123);
+    k.P012345 = to_U128(p012345);
+    k.P01234567 = to_U128(p01234567);
+    k.P0123456789 = to_U128(p01234567 * (u128)k.P89);
+    const uint64_t* Q = pm::kPrimes52;
+    k.Q0_INV_MOD_Q1 = pm::inv_mod_prime(Q[0] % Q[1], Q[1]);
+    k.Q0_INV_MOD_Q1_SHOUP = pm::shoup64(k.Q0_INV_MOD_Q1, Q[1]);
+    k.Q01_INV_MOD_Q2 = pm::inv_mod_prime(pm::mulmod(Q[0], Q[1], Q[2]), Q[2]);
+    k.Q01_INV_MOD_Q2_SHOUP = pm::shoup64(k.Q01_INV_MOD_Q2, Q[2]);
+    k.Q0_MOD_Q2_SHOUP = pm::shoup64(Q[0], Q[2]);
+    return k;
+}
+
+// ---- device arithmetic for the recombinations -------------------------------------------
+// exact (a*b) mod p, p < 2^32  (reference mul_mod32 = `%`, native32.rs:21-24)
+NTT_DEVINL uint32_t mm32(uint32_t p, uint64_t b64, uint32_t a, uint32_t b) {
+    return barrett32((uint64_t)a * b, p, b64);
+}
+// native64.rs:36-40 (Shoup product with one conditional subtract), restated literally
+NTT_DEVINL uint64_t mm64s(uint64_t p_neg, uint64_t a, uint64_t b, uint64_t b_shoup) {
+    uint64_t q = __umul64hi(a, b_shoup);
+    uint64_t r = a * b + p_neg * q;
+    uint64_t r2 = r + p_neg;
+    return r < r2 ? r : r2;
+}
+NTT_DEVINL uint64_t rem64(uint64_t v, uint64_t p, uint64_t b64) {  // exact v % p
+    uint64_t q = __umul64hi(v, b64);
+    uint64_t r = v - q * p;
+    return r >= p ? r - p : r;
+}
+
+struct ResPtrs {
+    void* r[10];
+};
+
+// value -> residues.  VT: uint32_t / uint64_t / U128 ; RT: uint32_t / uint64_t.
+// reduce == false copies the (truncated) value: fwd_binary and the u32-into-52-bit plans
+// (native_binary64.rs:371-388, native32.rs:452-464).
+template <class VT, class RT>
+__global__ void crt_split_kernel(const VT* __restrict__ value, ResPtrs res, int num_primes,
+                                 size_t total, int reduce, CrtConsts k) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        VT v = value[i];
+#pragma unroll 1
+        for (int j = 0; j < num_primes; ++j) {
+            RT out;
+            if constexpr (sizeof(VT) == 16) {
+                if (!reduce) {
+                    out = (RT)v.lo;
+                } else {  // (hi * 2^64 + lo) mod P_j
+                    uint32_t p = k.P[j];
+                    uint64_t h = rem64(v.hi, p, k.P_b64[j]), l = rem64(v.lo, p, k.P_b64[j]);
+                    out = (RT)rem64(h * k.P_c64[j] + l, p, k.P_b64[j]);
+                }
+            } else if constexpr (sizeof(RT) == 4) {
+                out = reduce ? (RT)rem64((uint64_t)v, k.P[j], k.P_b64[j]) : (RT)v;
+            } else {
+                out = reduce ? (RT)rem64((uint64_t)v, k.Q[j], k.Q_b64[j]) : (RT)v;
+            }
+            static_cast<RT*>(res.r[j])[i] = out;
+        }
+    }
+}
+
+// pairwise Garner used by the v2 recombinations: (ra mod Pa, rb mod Pb) -> value mod Pa*Pb
+NTT_DEVINL uint64_t pair32(const CrtConsts& k, int a, int b, uint32_t inv, uint32_t ra, uint32_t rb) {
+    uint32_t vb = mm32(k.P[b], k.P_b64[b], inv, 2 * k.P[b] + rb - ra);
+    return (uint64_t)ra + (uint64_t)vb * k.P[a];
+}
+
+template <int KIND>
+NTT_DEVINL void crt_one(const CrtConsts& k, const ResPtrs& res, size_t i, void* value) {
+    auto r32 = [&](int j) { return static_cast<const uint32_t*>(res.r[j])[i]; };
+    auto r64 = [&](int j) { return static_cast<const uint64_t*>(res.r[j])[i]; };
+    if constexpr (KIND == NTT_B200_NATIVE32_PLAN32 || KIND == NTT_B200_NATIVE_BINARY64_PLAN32) {
+        // native32.rs:27-55 / native_binary64.rs:32-60 (same Garner chain, u32 vs u64 accumulation)
+        uint32_t P0 = k.P[0], P1 = k.P[1], P2 = k.P[2];
+        uint32_t v0 = r32(0);
+        uint32_t v1 = mm32(P1, k.P_b64[1], k.P0_INV_MOD_P1, 2 * P1 + r32(1) - v0);
+        uint32_t v2 = mm32(P2, k.P_b64[2], k.P01_INV_MOD_P2,
+                           2 * P2 + r32(2) - (v0 + mm32(P2, k.P_b64[2], P0, v1)));
+        bool sign = v2 > P2 / 2;
+        if constexpr (KIND == NTT_B200_NATIVE32_PLAN32) {
+            uint32_t _01 = P0 * P1, _012 = _01 * P2;
+            uint32_t pos = v0 + v1 * P0 + v2 * _01;
+            static_cast<uint32_t*>(value)[i] = sign ? pos - _012 : pos;
+        } else {
+            uint64_t _01 = (uint64_t)P0 * P1, _012 = _01 * P2;
+            uint64_t pos = (uint64_t)v0 + (uint64_t)v1 * P0 + (uint64_t)v2 * _01;
+            static_cast<uint64_t*>(value)[i] = sign ? pos - _012 : pos;
+        }
+    } else if constexpr (KIND == NTT_B200_NATIVE32_PLAN52 || KIND == NTT_B200_NATIVE_BINARY64_PLAN52) {
+        // native32.rs:222-252 / native_binary64.rs:229-260
+        uint64_t Q0 = k.Q[0], Q1 = k.Q[1];
+        uint64_t v0 = r64(0);
+        uint64_t v1 = mm64s(0 - Q1, 2 * Q1 + r64(1) - v0, k.Q0_INV_MOD_Q1, k.Q0_INV_MOD_Q1_SHOUP);
+        bool sign = v1 > Q1 / 2;
+        uint64_t pos = v0 + v1 * Q0;
+        uint64_t out = sign ? pos - Q0 * Q1 : pos;
+        if constexpr (KIND == NTT_B200_NATIVE32_PLAN52)
+            static_cast<uint32_t*>(value)[i] = (uint32_t)out;
+        else
+            static_cast<uint64_t*>(value)[i] = out;
+    } else if constexpr (KIND == NTT_B200_NATIVE64_PLAN32 || KIND == NTT_B200_NATIVE_BINARY128_PLAN32) {
+        // native64.rs:90-140 / native_binary128.rs:13-63
+        uint64_t mod_p12 = pair32(k, 1, 2, k.P1_INV_MOD_P2, r32(1), r32(2));
+        uint64_t mod_p34 = pair32(k, 3, 4, k.P3_INV_MOD_P4, r32(3), r32(4));
+        uint64_t v0 = r32(0);
+        uint64_t v12 = mm64s(0 - k.P12, 2 * k.P12 + mod_p12 - v0, k.P0_INV_MOD_P12, k.P0_INV_MOD_P12_SHOUP);
+        uint64_t v34 = mm64s(0 - k.P34,
+                             2 * k.P34 + mod_p34 - (v0 + mm64s(0 - k.P34, v12, k.P[0], k.P0_MOD_P34_SHOUP)),
+                             k.P012_INV_MOD_P34, k.P012_INV_MOD_P34_SHOUP);
+        bool sign = v34 > k.P34 / 2;
+        if constexpr (KIND == NTT_B200_NATIVE64_PLAN32) {
+            uint64_t _0 = k.P[0], _012 = _0 * k.P12, _01234 = _012 * k.P34;
+            uint64_t pos = v0 + v12 * _0 + v34 * _012;
+            static_cast<uint64_t*>(value)[i] = sign ? pos - _01234 : pos;
+        } else {
+            U128 _0{k.P[0], 0}, _012 = u128_mul(_0, U128{k.P12, 0}), _01234 = u128_mul(_012, U128{k.P34, 0});
+            U128 pos = u128_add(u128_add(U128{v0, 0}, u128_mul(U128{v12, 0}, _0)), u128_mul(U128{v34, 0}, _012));
+            static_cast<U128*>(value)[i] = sign ? u128_sub(pos, _01234) : pos;
+        }
+    } else if constexpr (KIND == NTT_B200_NATIVE64_PLAN52) {
+        // native64.rs:769-828
+        uint64_t Q0 = k.Q[0], Q1 = k.Q[1], Q2 = k.Q[2];
+        uint64_t v0 = r64(0);
+        uint64_t v1 = mm64s(0 - Q1, 2 * Q1 + r64(1) - v0, k.Q0_INV_MOD_Q1, k.Q0_INV_MOD_Q1_SHOUP);
+        uint64_t v2 = mm64s(0 - Q2, 2 * Q2 + r64(2) - (v0 + mm64s(0 - Q2, v1, Q0, k.Q0_MOD_Q2_SHOUP)),
+                            k.Q01_INV_MOD_Q2, k.Q01_INV_MOD_Q2_SHOUP);
+        bool sign = v2 > Q2 / 2;
+        uint64_t pos = v0 + v1 * Q0 + v2 * (Q0 * Q1);
+        static_cast<uint64_t*>(value)[i] = sign ? pos - Q0 * Q1 * Q2 : pos;
+    } else if constexpr (KIND == NTT_B200_NATIVE128_PLAN32) {
+        // native128.rs:20-118
+        uint64_t v01 = pair32(k, 0, 1, k.P0_INV_MOD_P1, r32(0), r32(1));
+        uint64_t m23 = pair32(k, 2, 3, k.P2_INV_MOD_P3, r32(2), r32(3));
+        uint64_t m45 = pair32(k, 4, 5, k.P4_INV_MOD_P5, r32(4), r32(5));
+        uint64_t m67 = pair32(k, 6, 7, k.P6_INV_MOD_P7, r32(6), r32(7));
+        uint64_t m89 = pair32(k, 8, 9, k.P8_INV_MOD_P9, r32(8), r32(9));
+        uint64_t n23 = 0 - k.P23, n45 = 0 - k.P45, n67 = 0 - k.P67, n89 = 0 - k.P89;
+        uint64_t v23 = mm64s(n23, 2 * k.P23 + m23 - v01, k.P01_INV_MOD_P23, k.P01_INV_MOD_P23_SHOUP);
+        uint64_t v45 = mm64s(n45, 2 * k.P45 + m45 - (v01 + mm64s(n45, v23, k.P01, k.P01_MOD_P45_SHOUP)),
+                             k.P0123_INV_MOD_P45, k.P0123_INV_MOD_P45_SHOUP);
+        uint64_t v67 = mm64s(
+            n67,
+            2 * k.P67 + m67 -
+                (v01 + mm64s(n67, v23 + mm64s(n67, v45, k.P23, k.P23_MOD_P67_SHOUP), k.P01, k.P01_MOD_P67_SHOUP)),
+            k.P012345_INV_MOD_P67, k.P012345_INV_MOD_P67_SHOUP);
+        uint64_t v89 = mm64s(
+            n89,
+            2 * k.P89 + m89 -
+                (v01 + mm64s(n89,
+                             v23 + mm64s(n89, v45 + mm64s(n89, v67, k.P45, k.P45_MOD_P89_SHOUP), k.P23,
+                                         k.P23_MOD_P89_SHOUP),
+                             k.P01, k.P01_MOD_P89_SHOUP)),
+            k.P01234567_INV_MOD_P89, k.P01234567_INV_MOD_P89_SHOUP);
+        bool sign = v89 > k.P89 / 2;
+        U128 pos = U128{v01, 0};
+        pos = u128_add(pos, u128_mul(U128{v23, 0}, U128{k.P01, 0}));
+        pos = u128_add(pos, u128_mul(U128{v45, 0}, k.P0123));
+        pos = u128_add(pos, u128_mul(U128{v67, 0}, k.P012345));
+        pos = u128_add(pos, u128_mul(U128{v89, 0}, k.P01234567));
+        static_cast<U128*>(value)[i] = sign ? u128_sub(pos, k.P0123456789) : pos;
+    } else if constexpr (KIND == NTT_B200_NATIVE_BINARY32_PLAN32) {
+        // native_binary32.rs:21-40
+        uint32_t P0 = k.P[0], P1 = k.P[1];
+        uint32_t v0 = r32(0);
+        uint32_t v1 = mm32(P1, k.P_b64[1], k.P0_INV_MOD_P1, 2 * P1 + r32(1) - v0);
+        bool sign = v1 > P1 / 2;
+        uint32_t pos = v0 + v1 * P0;
+        static_cast<uint32_t*>(value)[i] = sign ? pos - P0 * P1 : pos;
+    } else if constexpr (KIND == NTT_B200_NATIVE_BINARY32_PLAN52) {
+        // native_binary32.rs:110-123
+        uint64_t v0 = r64(0), Q0 = k.Q[0];
+        static_cast<uint32_t*>(value)[i] = (uint32_t)(v0 > Q0 / 2 ? v0 - Q0 : v0);
+    }
+}
+
+template <int KIND>
+__global__ void crt_merge_kernel(void* value, ResPtrs res, size_t total, CrtConsts k) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x)
+        crt_one<KIND>(k, res, i, value);
+}
+
+}  // namespace
+
+struct ntt_b200_native_plan {
+    int kind = 0;
+    size_t n = 0;
+    KindInfo info{};
+    int device = 0;
+    std::vector<ntt_b200_plan32> p32;
+    std::vector<ntt_b200_plan64> p64;
+    CrtConsts consts{};
+
+    const PrimePlan* prime(int i) const {
+        return info.residue_bytes == 4 ? p32[i].impl.get() : p64[i].impl.get();
+    }
+    unsigned blocks(size_t total) const { return (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16); }
+
+    void split(const void* value, const ResPtrs& res, size_t total, bool reduce, cudaStream_t st) const {
+        // the u32 -> 52-bit plans never reduce (u32 < P0): native32.rs:452-464
+        if (kind == NTT_B200_NATIVE32_PLAN52 || kind == NTT_B200_NATIVE_BINARY32_PLAN52) reduce = false;
+        unsigned nb = blocks(total);
+        int np = info.num_primes;
+        if (info.value_bytes == 4 && info.residue_bytes == 4)
+            crt_split_kernel<uint32_t, uint32_t><<<nb, 256, 0, st>>>((const uint32_t*)value, res, np, total, reduce, consts);
+        else if (info.value_bytes == 4)
+            crt_split_kernel<uint32_t, uint64_t><<<nb, 256, 0, st>>>((const uint32_t*)value, res, np, total, reduce, consts);
+        else if (info.value_bytes == 8 && info.residue_bytes == 4)
+            crt_split_kernel<uint64_t, uint32_t><<<nb, 256, 0, st>>>((const uint64_t*)value, res, np, total, reduce, consts);
+        else if (info.value_bytes == 8)
+            crt_split_kernel<uint64_t, uint64_t><<<nb, 256, 0, st>>>((const uint64_t*)value, res, np, total, reduce, consts);
+        else
+            crt_split_kernel<U128, uint32_t><<<nb, 256, 0, st>>>((const U128*)value, res, np, total, reduce, consts);
+        NTT_CUDA_CHECK(cudaGetLastError());
+    }
+    void merge(void* value, const ResPtrs& res, size_t total, cudaStream_t st) const {
+        unsigned nb = blocks(total);
+        switch (kind) {
+#define NTT_CASE(K) \
+    case K: crt_merge_kernel<K><<<nb, 256, 0, st>>>(value, res, total, consts); break;
+            NTT_CASE(NTT_B200_NATIVE32_PLAN32)
+            NTT_CASE(NTT_B200_NATIVE32_PLAN52)
+            NTT_CASE(NTT_B200_NATIVE64_PLAN32)
+            NTT_CASE(NTT_B200_NATIVE64_PLAN52)
+            NTT_CASE(NTT_B200_NATIVE128_PLAN32)
+            NTT_CASE(NTT_B200_NATIVE_BINARY32_PLAN32)
+            NTT_CASE(NTT_B200_NATIVE_BINARY32_PLAN52)
+            NTT_CASE(NTT_B200_NATIVE_BINARY64_PLAN32)
+            NTT_CASE(NTT_B200_NATIVE_BINARY64_PLAN52)
+            NTT_CASE(NTT_B200_NATIVE_BINARY128_PLAN32)
+#undef NTT_CASE
+        }
+        NTT_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void fwd_dev(const void* value, const ResPtrs& res, size_t batch, bool binary, cudaStream_t st) const {
+        split(value, res, batch * n, !binary, st);
+        for (int j = 0; j < info.num_primes; ++j) prime(j)->fwd(res.r[j], batch, st);
+    }
+    void inv_dev(void* value, const ResPtrs& res, size_t batch, cudaStream_t st) const {
+        for (int j = 0; j < info.num_primes; ++j) prime(j)->inv(res.r[j], batch, st);
+        merge(value, res, batch * n, st);
+    }
+    // negacyclic_polymul over `batch` polynomial pairs; residues live in a scratch arena that is
+    // sized to stay L2-resident (chunks of the batch), so they never travel to HBM and back.
+    void polymul_dev(void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st) const {
+        if (!batch) return;
+        const size_t rb = (size_t)info.residue_bytes, vb = (size_t)info.value_bytes;
+        const int np = info.num_primes;
+        size_t per_poly = 2 * (size_t)np * n * rb;
+        size_t chunk = std::max<size_t>(1, (size_t(48) << 20) / per_poly);
+        chunk = std::min(chunk, batch);
+        char* arena = nullptr;
+        NTT_CUDA_CHECK(cudaMallocAsync(&arena, chunk * per_poly, st));
+        ResPtrs l{}, r{};
+        for (int j = 0; j < np; ++j) {
+            l.r[j] = arena + (size_t)(2 * j) * chunk * n * rb;
+            r.r[j] = arena + (size_t)(2 * j + 1) * chunk * n * rb;
+        }
+        for (size_t b0 = 0; b0 < batch; b0 += chunk) {
+            size_t nb = std::min(chunk, batch - b0);
+            const char* lp = static_cast<const char*>(lhs) + b0 * n * vb;
+            const char* rp = static_cast<const char*>(rhs) + b0 * n * vb;
+            char* pp = static_cast<char*>(prod) + b0 * n * vb;
+            fwd_dev(lp, l, nb, false, st);
+            fwd_dev(rp, r, nb, info.binary != 0, st);
+            for (int j = 0; j < np; ++j)
+                prime(j)->mul_assign_normalize(l.r[j], r.r[j], nb * n, nb * n, st);
+            inv_dev(pp, l, nb, st);
+        }
+        NTT_CUDA_CHECK(cudaFreeAsync(arena, st));
+    }
+};
+
+namespace {
+
+// host-pointer wrapper: upload operands, run `f(stream, dev ptrs...)`, download results
+struct HostStage {
+    cudaStream_t st = nullptr;
+    std::vector<void*> bufs;
+    HostStage() { NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); }
+    void* alloc(size_t bytes) {
+        void* d = nullptr;
+        NTT_CUDA_CHECK(cudaMallocAsync(&d, std::max<size_t>(bytes, 16), st));
+        bufs.push_back(d);
+        return d;
+    }
+    void* upload(const void* h, size_t bytes) {
+        void* d = alloc(bytes);
+        NTT_CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st));
+        return d;
+    }
+    void download(void* h, const void* d, size_t bytes) {
+        NTT_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    void finish() {
+        for (void* d : bufs) cudaFreeAsync(d, st);
+        bufs.clear();
+        NTT_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    ~HostStage() {
+        for (void* d : bufs) cudaFreeAsync(d, st);
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ntt_b200_native_num_primes(int kind) { return (kind < 0 || kind > 9) ? 0 : kKinds[kind].num_primes; }
+int ntt_b200_native_residue_bytes(int kind) { return (kind < 0 || kind > 9) ? 0 : kKinds[kind].residue_bytes; }
+int ntt_b200_native_value_bytes(int kind) { return (kind < 0 || kind > 9) ? 0 : kKinds[kind].value_bytes; }
+
+int ntt_b200_native_try_new(int kind, size_t n, ntt_b200_native_plan** out) {
+    if (!out || kind < 0 || kind > 9) return NTT_B200_ERR_ARG;
+    *out = nullptr;
+    return guarded([&] {
+        auto pl = std::make_unique<ntt_b200_native_plan>();
+        pl->kind = kind;
+        pl->n = n;
+        pl->info = kKinds[kind];
+        NTT_CUDA_CHECK(cudaGetDevice(&pl->device));
+        for (int j = 0; j < pl->info.num_primes; ++j) {
+            std::shared_ptr<PrimePlan> impl = pl->info.residue_bytes == 4
+                                                  ? make_plan32(n, pm::kPrimes32[j])
+                                                  : make_plan64(n, pm::kPrimes52[j]);
+            if (!impl) return NTT_B200_NONE;  // the `?` in e.g. native64.rs:934-940
+            if (pl->info.residue_bytes == 4)
+                pl->p32.push_back(ntt_b200_plan32{impl});
+            else
+                pl->p64.push_back(ntt_b200_plan64{impl});
+        }
+        pl->consts = make_consts();
+        *out = pl.release();
+        return NTT_B200_OK;
+    });
+}
+void ntt_b200_native_free(ntt_b200_native_plan* plan) { delete plan; }
+size_t ntt_b200_native_ntt_size(const ntt_b200_native_plan* plan) { return plan->n; }
+int ntt_b200_native_kind_of(const ntt_b200_native_plan* plan) { return plan->kind; }
+const void* ntt_b200_native_ntt_i(const ntt_b200_native_plan* plan, int i) {
+    if (!plan || i < 0 || i >= plan->info.num_primes) return nullptr;
+    return plan->info.residue_bytes == 4 ? (const void*)&plan->p32[i] : (const void*)&plan->p64[i];
+}
+
+int ntt_b200_native_fwd_device(const ntt_b200_native_plan* plan, const void* value,
+                               void* const* residues, size_t batch, int binary, void* stream) {
+    if (!plan || !residues || (!value && batch)) return NTT_B200_ERR_ARG;
+    return guarded([&] {
+        DeviceGuard g(plan->device);
+        ResPtrs r{};
+        for (int j = 0; j < plan->info.num_primes; ++j) r.r[j] = residues[j];
+        plan->fwd_dev(value, r, batch, binary != 0, (cudaStream_t)stream);
+        return NTT_B200_OK;
+    });
+}
+int ntt_b200_native_inv_device(const ntt_b200_native_plan* plan, void* value, void* const* residues,
+                               size_t batch, void* stream) {
+    if (!plan || !residues || (!value && batch)) return NTT_B200_ERR_ARG;
+    return guarded([&] {
+        DeviceGuard g(plan->device);
+        ResPtrs r{};
+        for (int j = 0; j < plan->info.num_primes; ++j) r.r[j] = residues[j];
+        plan->inv_dev(value, r, batch, (cudaStream_t)stream);
+        return NTT_B200_OK;
+    });
+}
+int ntt_b200_native_negacyclic_polymul_device(const ntt_b200_native_plan* plan, void* prod,
+                                              const void* lhs, const void* rhs, size_t batch,
+                                              void* stream) {
+    if (!plan || (batch && (!prod || !lhs || !rhs))) return NTT_B200_ERR_ARG;
+    return guarded([&] {
+        DeviceGuard g(plan->device);
+        plan->polymul_dev(prod, lhs, rhs, batch, (cudaStream_t)stream);
+        return NTT_B200_OK;
+    });
+}
+
+int ntt_b200_native_fwd(const ntt_b200_native_plan* plan, const void* value, size_t len,
+                        void* const* residues, int binary) {
+    if (!plan || !value || !residues) return NTT_B200_ERR_ARG;
+    if (len != plan->n) return NTT_B200_ERR_LEN;
+    return guarded([&] {
+        DeviceGuard g(plan->device);
+        HostStage hs;
+        size_t rb = (size_t)plan->info.residue_bytes;
+        void* dv = hs.upload(value, len * (size_t)plan->info.value_bytes);
+        ResPtrs r{};
+        for (int j = 0; j < plan->info.num_primes; ++j) r.r[j] = hs.alloc(len * rb);
+        plan->fwd_dev(dv, r, 1, binary != 0, hs.st);
+        for (int j = 0; j < plan->info.num_primes; ++j) hs.download(residues[j], r.r[j], len * rb);
+        hs.finish();
+        return NTT_B200_OK;
+    });
+}
+int ntt_b200_native_inv(const ntt_b200_native_plan* plan, void* value, size_t len,
+                        void* const* residues) {
+    if (!plan || !value || !residues) return NTT_B200_ERR_ARG;
+    if (len != plan->n) return NTT_B200_ERR_LEN;
+    return guarded([&] {
+        DeviceGuard g(plan->device);
+        HostStage hs;
+        size_t rb = (size_t)plan->info.residue_bytes, vb = (size_t)plan->info.value_bytes;
+        void* dv = hs.alloc(len * vb);
+        ResPtrs r{};
+        for (int j = 0; j < plan->info.num_primes; ++j) r.r[j] = hs.upload(residues[j], len * rb);
+        plan->inv_dev(dv, r, 1, hs.st);
+        hs.download(value, dv, len * vb);
+        // the reference transforms the residue buffers in place; hand the same bytes back
+        for (int j = 0; j < plan->info.num_primes; ++j) hs.download(residues[j], r.r[j], len * rb);
+        hs.finish();
+        return NTT_B200_OK;
+    });
+}
+int ntt_b200_native_negacyclic_polymul_batch(const ntt_b200_native_plan* plan, void* prod,
+                                             const void* lhs, const void* rhs, size_t batch) {
+    if (!plan || (batch && (!prod || !lhs || !rhs))) return NTT_B200_ERR_ARG;
+    return guarded([&] {
+        if (!batch) return NTT_B200_OK;
+        DeviceGuard g(plan->device);
+        HostStage hs;
+        size_t bytes = batch * plan->n * (size_t)plan->info.value_bytes;
+        void* dl = hs.upload(lhs, bytes);
+        void* dr = hs.upload(rhs, bytes);
+        void* dp = hs.alloc(bytes);
+        plan->polymul_dev(dp, dl, dr, batch, hs.st);
+        hs.download(prod, dp, bytes);
+        hs.finish();
+        return NTT_B200_OK;
+    });
+}
+int ntt_b200_native_negacyclic_polymul(const ntt_b200_native_plan* plan, void* prod, size_t prod_len,
+                                       const void* lhs, size_t lhs_len, const void* rhs,
+                                       size_t rhs_len) {
+    if (!plan) return NTT_B200_ERR_ARG;
+    // native64.rs:1042-1044 asserts equal lengths; the per-prime fwd then asserts len == n
+    if (prod_len != lhs_len || prod_len != rhs_len || prod_len != plan->n) return NTT_B200_ERR_LEN;
+    return ntt_b200_native_negacyclic_polymul_batch(plan, prod, lhs, rhs, 1);
+}
+
+}  // extern "C"

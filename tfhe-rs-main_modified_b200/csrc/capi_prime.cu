@@ -1,0 +1,267 @@
+// C ABI for the prime plans (include/tfhe_ntt_b200.h).  No torch, no oracle, no CPU fallback:
+// every compute entry point runs CUDA kernels or fails with NTT_B200_ERR_CUDA.
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "capi_common.cuh"
+#include "plan_math.hpp"
+
+using namespace nttb200;
+
+namespace nttb200 {
+thread_local std::string g_last_error;
+}
+
+extern "C" {
+
+const char* ntt_b200_last_error(void) { return g_last_error.c_str(); }
+
+int ntt_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int ntt_b200_set_device(int device) {
+    return guarded([&] {
+        NTT_CUDA_CHECK(cudaSetDevice(device));
+        return NTT_B200_OK;
+    });
+}
+
+int ntt_b200_is_prime64(uint64_t n) { return pm::is_prime(n) ? 1 : 0; }
+int ntt_b200_largest_prime_in_arithmetic_progression64(uint64_t factor, uint64_t offset,
+                                                       uint64_t lo, uint64_t hi, uint64_t* out) {
+    auto r = pm::largest_prime_in_arithmetic_progression64(factor, offset, lo, hi);
+    if (!r) return 0;
+    if (out) *out = *r;
+    return 1;
+}
+
+}  // extern "C"
+
+namespace {
+
+// ---- host-pointer paths: stage through device memory, chunked and double-buffered ---------
+constexpr size_t kChunkBytes = size_t(32) << 20;
+
+struct Stage {
+    cudaStream_t st = nullptr;
+    void* d = nullptr;
+};
+
+int host_transform(const PrimePlan* pl, void* host, size_t batch, bool inverse) {
+    return guarded([&] {
+        if (!batch) return NTT_B200_OK;
+        DeviceGuard g(pl->device);
+        size_t poly_bytes = pl->n * (size_t)pl->elem_bytes;
+        size_t chunk_polys = std::max<size_t>(1, kChunkBytes / poly_bytes);
+        chunk_polys = std::min(chunk_polys, batch);
+        size_t nchunks = (batch + chunk_polys - 1) / chunk_polys;
+        int ns = (int)std::min<size_t>(3, nchunks);
+        Stage sg[3];
+        for (int i = 0; i < ns; ++i) {
+            NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&sg[i].st, cudaStreamNonBlocking));
+            NTT_CUDA_CHECK(cudaMallocAsync(&sg[i].d, chunk_polys * poly_bytes, sg[i].st));
+        }
+        for (size_t c = 0; c < nchunks; ++c) {
+            Stage& s = sg[c % ns];
+            size_t b0 = c * chunk_polys, nb = std::min(chunk_polys, batch - b0);
+            char* h = static_cast<char*>(host) + b0 * poly_bytes;
+            NTT_CUDA_CHECK(cudaMemcpyAsync(s.d, h, nb * poly_bytes, cudaMemcpyHostToDevice, s.st));
+            if (inverse)
+                pl->inv(s.d, nb, s.st);
+            else
+                pl->fwd(s.d, nb, s.st);
+            NTT_CUDA_CHECK(cudaMemcpyAsync(h, s.d, nb * poly_bytes, cudaMemcpyDeviceToHost, s.st));
+        }
+        cudaError_t first = cudaSuccess;
+        for (int i = 0; i < ns; ++i) {
+            cudaFreeAsync(sg[i].d, sg[i].st);
+            cudaError_t e = cudaStreamSynchronize(sg[i].st);
+            if (first == cudaSuccess) first = e;
+            cudaStreamDestroy(sg[i].st);
+        }
+        NTT_CUDA_CHECK(first);
+        return NTT_B200_OK;
+    });
+}
+
+// dst[0..len) op= ...; operands uploaded whole (pointwise calls are per-polynomial sized)
+int host_pointwise(const PrimePlan* pl, int op, void* dst, size_t len, const void* a, size_t a_len,
+                   const void* b, size_t b_len) {
+    return guarded([&] {
+        if (!len) return NTT_B200_OK;
+        DeviceGuard g(pl->device);
+        size_t eb = (size_t)pl->elem_bytes;
+        cudaStream_t st;
+        NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        void *dd = nullptr, *da = nullptr, *db = nullptr;
+        auto up = [&](void** d, const void* h, size_t n) {
+            NTT_CUDA_CHECK(cudaMallocAsync(d, n * eb, st));
+            NTT_CUDA_CHECK(cudaMemcpyAsync(*d, h, n * eb, cudaMemcpyHostToDevice, st));
+        };
+        up(&dd, dst, len);
+        if (a) up(&da, a, a_len);
+        if (b) up(&db, b, b_len);
+        if (op == 0) pl->normalize(dd, len, st);
+        if (op == 1) pl->mul_assign_normalize(dd, da, len, a_len, st);
+        if (op == 2) pl->mul_accumulate(dd, da, db, len, a_len, b_len, st);
+        NTT_CUDA_CHECK(cudaMemcpyAsync(dst, dd, len * eb, cudaMemcpyDeviceToHost, st));
+        cudaFreeAsync(dd, st);
+        if (da) cudaFreeAsync(da, st);
+        if (db) cudaFreeAsync(db, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+        NTT_CUDA_CHECK(e);
+        return NTT_B200_OK;
+    });
+}
+
+int dev_pointwise_check(size_t len, size_t sub_len) {
+    if (sub_len == 0 || sub_len > len || len % sub_len != 0) return NTT_B200_ERR_LEN;
+    return NTT_B200_OK;
+}
+
+}  // namespace
+
+// The 32- and 64-bit families share every code path; only the handle and element types differ.
+#define NTT_DEFINE_PRIME_API(SFX, ELEM, MAKE)                                                      \
+    extern "C" {                                                                                   \
+    int ntt_b200_plan##SFX##_try_new(size_t n, ELEM p, ntt_b200_plan##SFX** out) {                 \
+        if (!out) return NTT_B200_ERR_ARG;                                                         \
+        *out = nullptr;                                                                            \
+        return guarded([&] {                                                                       \
+            auto impl = MAKE(n, p);                                                                \
+            if (!impl) return NTT_B200_NONE;                                                       \
+            *out = new ntt_b200_plan##SFX{impl};                                                   \
+            return NTT_B200_OK;                                                                    \
+        });                                                                                        \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_clone(const ntt_b200_plan##SFX* plan, ntt_b200_plan##SFX** out) {     \
+        if (!plan || !out) return NTT_B200_ERR_ARG;                                                \
+        *out = new ntt_b200_plan##SFX{plan->impl->clone()};                                        \
+        return NTT_B200_OK;                                                                        \
+    }                                                                                              \
+    void ntt_b200_plan##SFX##_free(ntt_b200_plan##SFX* plan) { delete plan; }                      \
+    size_t ntt_b200_plan##SFX##_ntt_size(const ntt_b200_plan##SFX* plan) { return plan->impl->n; } \
+    ELEM ntt_b200_plan##SFX##_modulus(const ntt_b200_plan##SFX* plan) {                            \
+        return (ELEM)plan->impl->p;                                                                \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_can_use_fast_reduction_code(const ntt_b200_plan##SFX* plan) {         \
+        return plan->impl->can_use_fast_reduction_code ? 1 : 0;                                    \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_device(const ntt_b200_plan##SFX* plan) { return plan->impl->device; } \
+    int ntt_b200_plan##SFX##_fwd(const ntt_b200_plan##SFX* plan, ELEM* buf, size_t len) {          \
+        if (!plan || !buf) return NTT_B200_ERR_ARG;                                                \
+        if (len != plan->impl->n) return NTT_B200_ERR_LEN;                                         \
+        return host_transform(plan->impl.get(), buf, 1, false);                                    \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_inv(const ntt_b200_plan##SFX* plan, ELEM* buf, size_t len) {          \
+        if (!plan || !buf) return NTT_B200_ERR_ARG;                                                \
+        if (len != plan->impl->n) return NTT_B200_ERR_LEN;                                         \
+        return host_transform(plan->impl.get(), buf, 1, true);                                     \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_fwd_batch(const ntt_b200_plan##SFX* plan, ELEM* host, size_t batch) { \
+        if (!plan || (!host && batch)) return NTT_B200_ERR_ARG;                                    \
+        return host_transform(plan->impl.get(), host, batch, false);                               \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_inv_batch(const ntt_b200_plan##SFX* plan, ELEM* host, size_t batch) { \
+        if (!plan || (!host && batch)) return NTT_B200_ERR_ARG;                                    \
+        return host_transform(plan->impl.get(), host, batch, true);                                \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_normalize(const ntt_b200_plan##SFX* plan, ELEM* v, size_t len) {      \
+        if (!plan || (!v && len)) return NTT_B200_ERR_ARG;                                         \
+        return host_pointwise(plan->impl.get(), 0, v, len, nullptr, 0, nullptr, 0);                \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_mul_assign_normalize(const ntt_b200_plan##SFX* plan, ELEM* lhs,       \
+                                                  size_t lhs_len, const ELEM* rhs,                 \
+                                                  size_t rhs_len) {                                \
+        if (!plan) return NTT_B200_ERR_ARG;                                                        \
+        size_t len = std::min(lhs_len, rhs_len); /* izip! truncation, lib.rs:658-688 */            \
+        if (len && (!lhs || !rhs)) return NTT_B200_ERR_ARG;                                        \
+        return host_pointwise(plan->impl.get(), 1, lhs, len, rhs, len, nullptr, 0);                \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_mul_accumulate(const ntt_b200_plan##SFX* plan, ELEM* acc,             \
+                                            size_t acc_len, const ELEM* lhs, size_t lhs_len,       \
+                                            const ELEM* rhs, size_t rhs_len) {                     \
+        if (!plan) return NTT_B200_ERR_ARG;                                                        \
+        size_t len = std::min(acc_len, std::min(lhs_len, rhs_len));                                \
+        if (len && (!acc || !lhs || !rhs)) return NTT_B200_ERR_ARG;                                \
+        return host_pointwise(plan->impl.get(), 2, acc, len, lhs, len, rhs, len);                  \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_fwd_device(const ntt_b200_plan##SFX* plan, ELEM* dev, size_t batch,   \
+                                        void* stream) {                                            \
+        if (!plan || (!dev && batch)) return NTT_B200_ERR_ARG;                                     \
+        return guarded([&] {                                                                       \
+            plan->impl->fwd(dev, batch, (cudaStream_t)stream);                                     \
+            return NTT_B200_OK;                                                                    \
+        });                                                                                        \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_inv_device(const ntt_b200_plan##SFX* plan, ELEM* dev, size_t batch,   \
+                                        void* stream) {                                            \
+        if (!plan || (!dev && batch)) return NTT_B200_ERR_ARG;                                     \
+        return guarded([&] {                                                                       \
+            plan->impl->inv(dev, batch, (cudaStream_t)stream);                                     \
+            return NTT_B200_OK;                                                                    \
+        });                                                                                        \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_normalize_device(const ntt_b200_plan##SFX* plan, ELEM* dev,           \
+                                              size_t len, void* stream) {                          \
+        if (!plan || (!dev && len)) return NTT_B200_ERR_ARG;                                       \
+        return guarded([&] {                                                                       \
+            plan->impl->normalize(dev, len, (cudaStream_t)stream);                                 \
+            return NTT_B200_OK;                                                                    \
+        });                                                                                        \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_mul_assign_normalize_device(const ntt_b200_plan##SFX* plan,           \
+                                                         ELEM* lhs, size_t len, const ELEM* rhs,   \
+                                                         size_t rhs_len, void* stream) {           \
+        if (!plan) return NTT_B200_ERR_ARG;                                                        \
+        if (!len) return NTT_B200_OK;                                                              \
+        if (!lhs || !rhs) return NTT_B200_ERR_ARG;                                                 \
+        if (int e = dev_pointwise_check(len, rhs_len)) return e;                                   \
+        return guarded([&] {                                                                       \
+            plan->impl->mul_assign_normalize(lhs, rhs, len, rhs_len, (cudaStream_t)stream);        \
+            return NTT_B200_OK;                                                                    \
+        });                                                                                        \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_mul_accumulate_device(const ntt_b200_plan##SFX* plan, ELEM* acc,      \
+                                                   size_t len, const ELEM* lhs, size_t lhs_len,    \
+                                                   const ELEM* rhs, size_t rhs_len,                \
+                                                   void* stream) {                                 \
+        if (!plan) return NTT_B200_ERR_ARG;                                                        \
+        if (!len) return NTT_B200_OK;                                                              \
+        if (!acc || !lhs || !rhs) return NTT_B200_ERR_ARG;                                         \
+        if (int e = dev_pointwise_check(len, lhs_len)) return e;                                   \
+        if (int e = dev_pointwise_check(len, rhs_len)) return e;                                   \
+        return guarded([&] {                                                                       \
+            plan->impl->mul_accumulate(acc, lhs, rhs, len, lhs_len, rhs_len,                       \
+                                       (cudaStream_t)stream);                                      \
+            return NTT_B200_OK;                                                                    \
+        });                                                                                        \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_fwd_mac_inv_device(const ntt_b200_plan##SFX* plan, ELEM* out,         \
+                                                const ELEM* lhs, const ELEM* rhs,                  \
+                                                size_t rhs_polys, const ELEM* acc,                 \
+                                                size_t acc_polys, size_t batch, void* stream) {    \
+        if (!plan) return NTT_B200_ERR_ARG;                                                        \
+        if (!batch) return NTT_B200_OK;                                                            \
+        if (!out || !lhs || !rhs) return NTT_B200_ERR_ARG;                                         \
+        if (rhs_polys == 0 || batch % rhs_polys) return NTT_B200_ERR_LEN;                          \
+        if (acc && (acc_polys == 0 || batch % acc_polys)) return NTT_B200_ERR_LEN;                 \
+        return guarded([&] {                                                                       \
+            plan->impl->fwd_mac_inv(out, lhs, rhs, rhs_polys, acc, acc_polys, batch,               \
+                                    (cudaStream_t)stream);                                         \
+            return NTT_B200_OK;                                                                    \
+        });                                                                                        \
+    }                                                                                              \
+    }
+
+NTT_DEFINE_PRIME_API(64, uint64_t, make_plan64)
+NTT_DEFINE_PRIME_API(32, uint32_t, make_plan32)
+
+extern "C" int ntt_b200_plan64_use_ifma(const ntt_b200_plan64*) { return 0; }

@@ -1,0 +1,295 @@
+// Device-side modular arithmetic classes for the B200 NTT engine (sm_100a).
+//
+// Each class implements one modulus family that the reference dispatches on
+// (tfhe-ntt/src/prime64.rs:897-968, prime32.rs:797-843):
+//
+//   Shoup<T, HARVEY>  p < 2^(W-1)  lazy Shoup/Harvey butterflies; HARVEY (values in [0,4p))
+//                     needs p < 2^(W-2)      (reference: prime64/less_than_6{2,3}bit.rs,
+//                                              prime32/less_than_3{0,1}bit.rs)
+//   Solinas64         p = 2^64-2^32+1        (reference: prime64/generic_solinas.rs:77-129)
+//   Mont64            any other p >= 2^63    (reference: generic_solinas.rs:42-75, exact `%`)
+//   Wide32            p >= 2^31              (reference: prime32/generic.rs:9-31, exact `%`)
+//
+// Every class ends a transform with canonical values in [0,p), so results are bit-identical
+// to the reference for canonical inputs no matter which exact algorithm runs in between
+// ("canonical-form invariants").
+//
+// Interface of an arithmetic class A:
+//   A::T            element type (uint32_t / uint64_t)
+//   A::TW           twiddle record as stored in device tables
+//   A::Ctx          per-plan constants passed by value to kernels
+//   fwd_bf / inv_bf lazy Cooley-Tukey / Gentleman-Sande butterflies
+//   fwd_fin/inv_fin canonicalise after the last stage
+//   mul_full        exact (a*b) mod p of two canonical values, canonical result (pointwise ops)
+//   add_full        exact (a+b) mod p
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nttb200 {
+
+#define NTT_DEVINL __device__ __forceinline__
+
+template <class T>
+NTT_DEVINL T umin_(T a, T b) {
+    return a < b ? a : b;
+}
+NTT_DEVINL uint32_t mulhi_(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+NTT_DEVINL uint64_t mulhi_(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
+
+// ------------------------------------------------------------------------------------
+// Shoup / Harvey lazy arithmetic, W = 32 or 64
+// ------------------------------------------------------------------------------------
+template <class T_>
+struct ShoupTw {
+    T_ w, ws;  // w and floor(w * 2^W / p)
+};
+
+template <class T_, bool HARVEY>
+struct Shoup {
+    using T = T_;
+    using TW = ShoupTw<T_>;
+    struct Ctx {
+        T p, two_p;
+        // pointwise constants: Montgomery (W=64) or 64-bit Barrett (W=32)
+        T pinv;     // p^-1 mod 2^W
+        T r2;       // 2^(2W) mod p
+        uint64_t barrett64;  // floor(2^64 / p), W=32 only
+    };
+    static constexpr bool kHarvey = HARVEY;
+
+    NTT_DEVINL static T csub(T a, T m) { return umin_<T>(a, a - m); }
+
+    // t = b*w mod p in [0,2p) for any b < 2^W
+    NTT_DEVINL static T mul_lazy(const Ctx& c, T b, TW w) {
+        T q = mulhi_(b, w.ws);
+        return b * w.w - q * c.p;
+    }
+    NTT_DEVINL static void fwd_bf(const Ctx& c, T& a, T& b, TW w) {
+        if (HARVEY) {  // [0,4p) -> [0,4p)
+            T z0 = csub(a, c.two_p);
+            T t = mul_lazy(c, b, w);
+            a = z0 + t;
+            b = z0 - t + c.two_p;
+        } else {  // [0,2p) -> [0,2p)
+            T z0 = csub(a, c.p);
+            T t = csub(mul_lazy(c, b, w), c.p);
+            a = z0 + t;
+            b = z0 - t + c.p;
+        }
+    }
+    NTT_DEVINL static void inv_bf(const Ctx& c, T& a, T& b, TW w) {
+        if (HARVEY) {  // [0,2p) -> [0,2p)
+            T y0 = csub(a + b, c.two_p);
+            T t = a - b + c.two_p;
+            a = y0;
+            b = mul_lazy(c, t, w);
+        } else {  // [0,p) -> [0,p)
+            T y0 = csub(a + b, c.p);
+            T t = a - b + c.p;
+            a = y0;
+            b = csub(mul_lazy(c, t, w), c.p);
+        }
+    }
+    NTT_DEVINL static T fwd_fin(const Ctx& c, T a) {
+        if (HARVEY) a = csub(a, c.two_p);
+        return csub(a, c.p);
+    }
+    NTT_DEVINL static T inv_fin(const Ctx& c, T a) { return HARVEY ? csub(a, c.p) : a; }
+    // multiply by a plan constant given as a Shoup pair, canonical result (used by normalize)
+    NTT_DEVINL static T mul_const(const Ctx& c, T a, TW w) { return csub(mul_lazy(c, a, w), c.p); }
+
+    NTT_DEVINL static T add_full(const Ctx& c, T a, T b) { return csub(a + b, c.p); }  // p < 2^(W-1)
+    NTT_DEVINL static T mul_full(const Ctx& c, T a, T b);
+};
+
+// Montgomery REDC for odd p < 2^64: returns (hi:lo) * 2^-64 mod p, canonical, for hi < p.
+NTT_DEVINL uint64_t redc64(uint64_t lo, uint64_t hi, uint64_t p, uint64_t pinv) {
+    uint64_t m = lo * pinv;
+    uint64_t t = __umul64hi(m, p);
+    uint64_t r = hi - t;
+    return hi < t ? r + p : r;
+}
+
+template <>
+NTT_DEVINL uint64_t Shoup<uint64_t, true>::mul_full(const Ctx& c, uint64_t a, uint64_t b) {
+    uint64_t x = redc64(a * b, __umul64hi(a, b), c.p, c.pinv);
+    return redc64(x * c.r2, __umul64hi(x, c.r2), c.p, c.pinv);
+}
+template <>
+NTT_DEVINL uint64_t Shoup<uint64_t, false>::mul_full(const Ctx& c, uint64_t a, uint64_t b) {
+    uint64_t x = redc64(a * b, __umul64hi(a, b), c.p, c.pinv);
+    return redc64(x * c.r2, __umul64hi(x, c.r2), c.p, c.pinv);
+}
+// exact a*b mod p for any p < 2^32 via a 64-bit Barrett quotient
+NTT_DEVINL uint32_t barrett32(uint64_t d, uint32_t p, uint64_t b64) {
+    uint64_t q = __umul64hi(d, b64);  // floor(d/p) - {0,1}
+    uint64_t r = d - q * p;           // < 2p
+    return (uint32_t)(r >= p ? r - p : r);
+}
+template <>
+NTT_DEVINL uint32_t Shoup<uint32_t, true>::mul_full(const Ctx& c, uint32_t a, uint32_t b) {
+    return barrett32((uint64_t)a * b, c.p, c.barrett64);
+}
+template <>
+NTT_DEVINL uint32_t Shoup<uint32_t, false>::mul_full(const Ctx& c, uint32_t a, uint32_t b) {
+    return barrett32((uint64_t)a * b, c.p, c.barrett64);
+}
+
+// ------------------------------------------------------------------------------------
+// Wide32: p >= 2^31, exact arithmetic through 64-bit intermediates
+// ------------------------------------------------------------------------------------
+struct Wide32 {
+    using T = uint32_t;
+    using TW = ShoupTw<uint32_t>;
+    struct Ctx {
+        uint32_t p, two_p, pinv, r2;
+        uint64_t barrett64;
+    };
+    static constexpr bool kHarvey = false;
+    NTT_DEVINL static T mul_exact(const Ctx& c, T b, TW w) {
+        uint32_t q = __umulhi(b, w.ws);
+        uint64_t r = (uint64_t)b * w.w - (uint64_t)q * c.p;  // [0, 2p)
+        return (uint32_t)(r >= c.p ? r - c.p : r);
+    }
+    NTT_DEVINL static T add_full(const Ctx& c, T a, T b) {
+        uint64_t s = (uint64_t)a + b;
+        return (uint32_t)(s >= c.p ? s - c.p : s);
+    }
+    NTT_DEVINL static T sub_full(const Ctx& c, T a, T b) { return a >= b ? a - b : a + (c.p - b); }
+    NTT_DEVINL static void fwd_bf(const Ctx& c, T& a, T& b, TW w) {
+        T t = mul_exact(c, b, w), z0 = a;
+        a = add_full(c, z0, t);
+        b = sub_full(c, z0, t);
+    }
+    NTT_DEVINL static void inv_bf(const Ctx& c, T& a, T& b, TW w) {
+        T s = add_full(c, a, b), d = sub_full(c, a, b);
+        a = s;
+        b = mul_exact(c, d, w);
+    }
+    NTT_DEVINL static T fwd_fin(const Ctx&, T a) { return a; }
+    NTT_DEVINL static T inv_fin(const Ctx&, T a) { return a; }
+    NTT_DEVINL static T mul_const(const Ctx& c, T a, TW w) { return mul_exact(c, a, w); }
+    NTT_DEVINL static T mul_full(const Ctx& c, T a, T b) {
+        return barrett32((uint64_t)a * b, c.p, c.barrett64);
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// Solinas64: p = 2^64 - 2^32 + 1.  Values travel as arbitrary 64-bit representatives
+// (2^64 == 2^32-1 =: eps mod p) and are canonicalised once at the end.
+// ------------------------------------------------------------------------------------
+struct Solinas64 {
+    using T = uint64_t;
+    using TW = uint64_t;
+    struct Ctx {
+        uint64_t p;  // unused in the butterflies (compile-time constant); keeps the interface uniform
+    };
+    static constexpr bool kHarvey = false;
+    static constexpr uint64_t P = 0xFFFFFFFF00000001ull;
+    static constexpr uint64_t EPS = 0xFFFFFFFFull;
+
+    // (hi:lo) mod p, result <= p-1+... canonical: in [0,p)
+    NTT_DEVINL static uint64_t reduce128(uint64_t lo, uint64_t hi) {
+        uint32_t hh = (uint32_t)(hi >> 32), mid = (uint32_t)hi;
+        // lo - hh, borrow folds as -eps
+        uint64_t t0 = lo - hh;
+        if (lo < (uint64_t)hh) t0 -= EPS;
+        // + mid*eps = (mid<<32) - mid
+        uint64_t m = ((uint64_t)mid << 32) - mid;
+        uint64_t t1 = t0 + m;
+        if (t1 < m) t1 += EPS;  // wrapped: +2^64 == +eps ; cannot wrap twice (m <= 2^64-2^33+1)
+        // canonicalise: t1 >= p  <=>  t1 + eps wraps, and then t1 - p = wrapped(t1 + eps)
+        uint64_t u = t1 + EPS;
+        return u < t1 ? u : t1;
+    }
+    NTT_DEVINL static uint64_t mul(uint64_t a, uint64_t b) { return reduce128(a * b, __umul64hi(a, b)); }
+    // a arbitrary, b <= p : result arbitrary 64-bit representative
+    NTT_DEVINL static uint64_t add_lazy(uint64_t a, uint64_t b) {
+        uint64_t s = a + b;
+        if (s < a) s += EPS;
+        return s;
+    }
+    // a arbitrary, b <= p
+    NTT_DEVINL static uint64_t sub_lazy(uint64_t a, uint64_t b) {
+        uint64_t d = a - b;
+        if (a < b) d -= EPS;
+        return d;
+    }
+    // both arbitrary
+    NTT_DEVINL static uint64_t add_any(uint64_t a, uint64_t b) {
+        uint64_t s = a + b;
+        if (s < a) {
+            uint64_t s2 = s + EPS;
+            s = s2 < s ? s2 + EPS : s2;
+        }
+        return s;
+    }
+    NTT_DEVINL static uint64_t sub_any(uint64_t a, uint64_t b) {
+        uint64_t d = a - b;
+        if (a < b) {
+            uint64_t d2 = d - EPS;
+            d = d2 > d ? d2 - EPS : d2;
+        }
+        return d;
+    }
+    NTT_DEVINL static uint64_t canon(uint64_t a) {
+        uint64_t u = a + EPS;
+        return u < a ? u : a;
+    }
+    NTT_DEVINL static void fwd_bf(const Ctx&, T& a, T& b, TW w) {
+        T t = mul(b, w), z0 = a;
+        a = add_lazy(z0, t);
+        b = sub_lazy(z0, t);
+    }
+    NTT_DEVINL static void inv_bf(const Ctx&, T& a, T& b, TW w) {
+        T s = add_any(a, b), d = sub_any(a, b);
+        a = s;
+        b = mul(d, w);
+    }
+    NTT_DEVINL static T fwd_fin(const Ctx&, T a) { return canon(a); }
+    NTT_DEVINL static T inv_fin(const Ctx&, T a) { return canon(a); }
+    NTT_DEVINL static T mul_const(const Ctx&, T a, TW w) { return mul(a, w); }
+    NTT_DEVINL static T add_full(const Ctx&, T a, T b) { return canon(add_lazy(a, b)); }
+    NTT_DEVINL static T mul_full(const Ctx&, T a, T b) { return mul(a, b); }
+};
+
+// ------------------------------------------------------------------------------------
+// Mont64: any odd prime p >= 2^63 other than Solinas.  Twiddles are stored in Montgomery
+// form (w * 2^64 mod p) so that one REDC gives the exact canonical product.
+// ------------------------------------------------------------------------------------
+struct Mont64 {
+    using T = uint64_t;
+    using TW = uint64_t;  // w * 2^64 mod p
+    struct Ctx {
+        uint64_t p, pinv, r2;
+    };
+    static constexpr bool kHarvey = false;
+    NTT_DEVINL static T mul_exact(const Ctx& c, T a, TW wm) {
+        return redc64(a * wm, __umul64hi(a, wm), c.p, c.pinv);
+    }
+    NTT_DEVINL static T add_full(const Ctx& c, T a, T b) {
+        uint64_t s = a + b;
+        return (s < a || s >= c.p) ? s - c.p : s;
+    }
+    NTT_DEVINL static T sub_full(const Ctx& c, T a, T b) { return a >= b ? a - b : a - b + c.p; }
+    NTT_DEVINL static void fwd_bf(const Ctx& c, T& a, T& b, TW w) {
+        T t = mul_exact(c, b, w), z0 = a;
+        a = add_full(c, z0, t);
+        b = sub_full(c, z0, t);
+    }
+    NTT_DEVINL static void inv_bf(const Ctx& c, T& a, T& b, TW w) {
+        T s = add_full(c, a, b), d = sub_full(c, a, b);
+        a = s;
+        b = mul_exact(c, d, w);
+    }
+    NTT_DEVINL static T fwd_fin(const Ctx&, T a) { return a; }
+    NTT_DEVINL static T inv_fin(const Ctx&, T a) { return a; }
+    NTT_DEVINL static T mul_const(const Ctx& c, T a, TW wm) { return mul_exact(c, a, wm); }
+    NTT_DEVINL static T mul_full(const Ctx& c, T a, T b) {
+        uint64_t x = redc64(a * b, __umul64hi(a, b), c.p, c.pinv);
+        return redc64(x * c.r2, __umul64hi(x, c.r2), c.p, c.pinv);
+    }
+};
+
+}  // namespace nttb200

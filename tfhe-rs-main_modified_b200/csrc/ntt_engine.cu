@@ -1,0 +1,295 @@
+// Plan construction (host) + kernel launch logic for the prime plans.
+#include "ntt_engine.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+#include "ntt_kernels.cuh"
+#include "plan_math.hpp"
+
+namespace nttb200 {
+
+namespace {
+
+using pm::u128;
+
+template <class A>
+__global__ void mul_add_kernel(typename A::T* __restrict__ out, const typename A::T* __restrict__ rhs,
+                               const typename A::T* __restrict__ acc, size_t total,
+                               size_t rhs_period, size_t acc_period, typename A::Ctx c) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        typename A::T r = rhs[rhs_period == total ? i : i % rhs_period];
+        typename A::T v = A::mul_full(c, out[i], r);
+        if (acc) v = A::add_full(c, v, acc[acc_period == total ? i : i % acc_period]);
+        out[i] = v;
+    }
+}
+
+uint64_t inv_mod_2_64(uint64_t p) {  // Newton iteration, p odd
+    uint64_t x = p;                  // correct to 3 bits
+    for (int i = 0; i < 6; ++i) x *= 2 - p * x;
+    return x;
+}
+
+// ---- per-family table / constant builders ------------------------------------------------
+template <class A>
+struct Build;
+
+template <class T, bool H>
+struct Build<Shoup<T, H>> {
+    using A = Shoup<T, H>;
+    static constexpr unsigned W = sizeof(T) * 8;
+    static typename A::TW tw(uint64_t w, uint64_t p) {
+        return {(T)w, (T)((((u128)w) << W) / p)};
+    }
+    static typename A::Ctx ctx(uint64_t p) {
+        typename A::Ctx c{};
+        c.p = (T)p;
+        c.two_p = (T)(2 * p);
+        if (W == 64) {
+            c.pinv = (T)inv_mod_2_64(p);
+            uint64_t r = (uint64_t)((((u128)1) << 64) % p);
+            c.r2 = (T)pm::mulmod(r, r, p);
+        } else {
+            c.barrett64 = ~uint64_t(0) / p;
+        }
+        return c;
+    }
+    static const char* name() {
+        return W == 64 ? (H ? "shoup64-harvey" : "shoup64") : (H ? "shoup32-harvey" : "shoup32");
+    }
+};
+template <>
+struct Build<Wide32> {
+    using A = Wide32;
+    static A::TW tw(uint64_t w, uint64_t p) { return {(uint32_t)w, (uint32_t)((w << 32) / p)}; }
+    static A::Ctx ctx(uint64_t p) {
+        A::Ctx c{};
+        c.p = (uint32_t)p;
+        c.barrett64 = ~uint64_t(0) / p;
+        return c;
+    }
+    static const char* name() { return "wide32"; }
+};
+template <>
+struct Build<Solinas64> {
+    using A = Solinas64;
+    static A::TW tw(uint64_t w, uint64_t) { return w; }
+    static A::Ctx ctx(uint64_t p) { return A::Ctx{p}; }
+    static const char* name() { return "solinas64"; }
+};
+template <>
+struct Build<Mont64> {
+    using A = Mont64;
+    static A::TW tw(uint64_t w, uint64_t p) { return (uint64_t)((((u128)w) << 64) % p); }
+    static A::Ctx ctx(uint64_t p) {
+        A::Ctx c{};
+        c.p = p;
+        c.pinv = inv_mod_2_64(p);
+        uint64_t r = (uint64_t)((((u128)1) << 64) % p);
+        c.r2 = pm::mulmod(r, r, p);
+        return c;
+    }
+    static const char* name() { return "mont64"; }
+};
+
+int sm_count(int device) {
+    static std::mutex mu;
+    static int cache[64];
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 64 && cache[device]) return cache[device];
+    int v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    if (device < 64) cache[device] = v;
+    return v;
+}
+
+template <class A>
+struct PlanImpl final : PrimePlan {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    typename A::Ctx ctx{};
+    TW n_inv{};
+    // device tables in the reference's index order (twid[m + i]); owned through shared_ptr so
+    // that clones share them
+    std::shared_ptr<TW> d_fwd, d_inv;
+
+    // Longest row one CTA keeps in shared memory: 2^14 u64 / 2^15 u32 = 128 KiB
+    static constexpr int kMaxLogRow = sizeof(T) == 8 ? 14 : 15;
+
+    static std::shared_ptr<TW> upload(const std::vector<TW>& h) {
+        TW* d = nullptr;
+        NTT_CUDA_CHECK(cudaMalloc(&d, h.size() * sizeof(TW)));
+        std::shared_ptr<TW> sp(d, [](TW* q) { cudaFree(q); });
+        NTT_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(TW), cudaMemcpyHostToDevice));
+        return sp;
+    }
+
+    static std::shared_ptr<PlanImpl> create(size_t n, uint64_t p, const pm::Twiddles& t) {
+        auto pl = std::make_shared<PlanImpl>();
+        pl->n = n;
+        pl->logn = __builtin_ctzll((uint64_t)n);
+        pl->elem_bytes = sizeof(T);
+        pl->p = p;
+        pl->family = Build<A>::name();
+        NTT_CUDA_CHECK(cudaGetDevice(&pl->device));
+        pl->ctx = Build<A>::ctx(p);
+        std::vector<TW> f(n), i(n);
+        for (size_t k = 0; k < n; ++k) {
+            f[k] = Build<A>::tw(t.fwd[k], p);
+            i[k] = Build<A>::tw(t.inv[k], p);
+        }
+        pl->d_fwd = upload(f);
+        pl->d_inv = upload(i);
+        pl->n_inv = Build<A>::tw(pm::powmod((uint64_t)n, p - 2, p), p);
+        auto bi = pm::barrett_info(p, sizeof(T) * 8);
+        if (sizeof(T) == 8)  // prime64.rs:815-817 (use_ifma = false)
+            pl->can_use_fast_reduction_code =
+                p < 6148914691236517206ull || (bi.single_step && p < (uint64_t(1) << 63));
+        else  // prime32.rs:748-749
+            pl->can_use_fast_reduction_code =
+                p < 1431655766ull || (bi.single_step && p <= (uint64_t(1) << 31));
+        return pl;
+    }
+
+    std::shared_ptr<PrimePlan> clone() const override { return std::make_shared<PlanImpl>(*this); }
+
+    template <bool INV>
+    void launch_rows(T* data, size_t num_rows, int log_row, int depth, int finalize,
+                     cudaStream_t st) const {
+        size_t row = size_t(1) << log_row;
+        unsigned rows_per_cta = row >= 2048 ? 1u : (unsigned)(2048 / row);
+        if (num_rows < rows_per_cta) rows_per_cta = (unsigned)num_rows;
+        size_t elems = row * rows_per_cta;
+        unsigned threads = (unsigned)std::min<size_t>(1024, std::max<size_t>(64, elems / 8));
+        size_t smem = elems * sizeof(T);
+        auto kern = ntt_rows_kernel<A, INV>;
+        if (smem > 48 * 1024) {
+            static std::once_flag once[2];
+            // the attribute is per function per device; set it every time on a cheap path
+            NTT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(size_t(1) << kMaxLogRow) * (int)sizeof(T)));
+            (void)once;
+        }
+        size_t ctas = (num_rows + rows_per_cta - 1) / rows_per_cta;
+        kern<<<(unsigned)ctas, threads, smem, st>>>(data, num_rows, log_row, depth,
+                                                    INV ? d_inv.get() : d_fwd.get(), ctx,
+                                                    rows_per_cta, finalize);
+        NTT_CUDA_CHECK(cudaGetLastError());
+    }
+
+    template <bool INV, int R>
+    void launch_global(T* data, size_t batch, int stage, int finalize, cudaStream_t st) const {
+        size_t total = batch << (logn - R);
+        unsigned threads = 256;
+        size_t blocks = std::min<size_t>((total + threads - 1) / threads, (size_t)sm_count(device) * 32);
+        ntt_global_pass_kernel<A, R, INV><<<(unsigned)blocks, threads, 0, st>>>(
+            data, batch, logn, stage, INV ? d_inv.get() : d_fwd.get(), ctx, finalize);
+        NTT_CUDA_CHECK(cudaGetLastError());
+    }
+    template <bool INV>
+    void launch_global_r(int r, T* data, size_t batch, int stage, int finalize,
+                         cudaStream_t st) const {
+        if (r == 1) launch_global<INV, 1>(data, batch, stage, finalize, st);
+        if (r == 2) launch_global<INV, 2>(data, batch, stage, finalize, st);
+        if (r == 3) launch_global<INV, 3>(data, batch, stage, finalize, st);
+    }
+
+    void fwd(void* data, size_t batch, cudaStream_t st) const override {
+        if (!batch) return;
+        DeviceGuard g(device);
+        T* d = static_cast<T*>(data);
+        int depth = std::max(0, logn - kMaxLogRow);
+        for (int s = 0; s < depth;) {  // top stages in global memory, 3 at a time
+            int r = std::min(3, depth - s);
+            launch_global_r<false>(r, d, batch, s, 0, st);
+            s += r;
+        }
+        launch_rows<false>(d, batch << depth, logn - depth, depth, 1, st);
+    }
+    void inv(void* data, size_t batch, cudaStream_t st) const override {
+        if (!batch) return;
+        DeviceGuard g(device);
+        T* d = static_cast<T*>(data);
+        int depth = std::max(0, logn - kMaxLogRow);
+        launch_rows<true>(d, batch << depth, logn - depth, depth, depth == 0, st);
+        // mirror of fwd: the same stage groups in reverse order
+        std::vector<std::pair<int, int>> groups;
+        for (int s = 0; s < depth;) {
+            int r = std::min(3, depth - s);
+            groups.push_back({s, r});
+            s += r;
+        }
+        for (size_t k = groups.size(); k-- > 0;)
+            launch_global_r<true>(groups[k].second, d, batch, groups[k].first, k == 0, st);
+    }
+
+    unsigned pointwise_blocks(size_t total) const {
+        return (unsigned)std::min<size_t>((total + 255) / 256, (size_t)sm_count(device) * 16);
+    }
+    void normalize(void* v, size_t total, cudaStream_t st) const override {
+        if (!total) return;
+        DeviceGuard g(device);
+        normalize_kernel<A><<<pointwise_blocks(total), 256, 0, st>>>(static_cast<T*>(v), total, ctx, n_inv);
+        NTT_CUDA_CHECK(cudaGetLastError());
+    }
+    void mul_assign_normalize(void* lhs, const void* rhs, size_t total, size_t rhs_period,
+                              cudaStream_t st) const override {
+        if (!total) return;
+        DeviceGuard g(device);
+        mul_assign_normalize_kernel<A><<<pointwise_blocks(total), 256, 0, st>>>(
+            static_cast<T*>(lhs), static_cast<const T*>(rhs), total, rhs_period, ctx, n_inv);
+        NTT_CUDA_CHECK(cudaGetLastError());
+    }
+    void mul_accumulate(void* acc, const void* lhs, const void* rhs, size_t total,
+                        size_t lhs_period, size_t rhs_period, cudaStream_t st) const override {
+        if (!total) return;
+        DeviceGuard g(device);
+        mul_accumulate_kernel<A><<<pointwise_blocks(total), 256, 0, st>>>(
+            static_cast<T*>(acc), static_cast<const T*>(lhs), static_cast<const T*>(rhs), total,
+            lhs_period, rhs_period, ctx);
+        NTT_CUDA_CHECK(cudaGetLastError());
+    }
+    void fwd_mac_inv(void* out, const void* lhs, const void* rhs, size_t rhs_polys,
+                     const void* acc, size_t acc_polys, size_t batch,
+                     cudaStream_t st) const override {
+        if (!batch) return;
+        DeviceGuard g(device);
+        size_t total = batch * n;
+        if (out != lhs)
+            NTT_CUDA_CHECK(cudaMemcpyAsync(out, lhs, total * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        fwd(out, batch, st);
+        mul_add_kernel<A><<<pointwise_blocks(total), 256, 0, st>>>(
+            static_cast<T*>(out), static_cast<const T*>(rhs), static_cast<const T*>(acc), total,
+            rhs_polys * n, acc ? acc_polys * n : total, ctx);
+        NTT_CUDA_CHECK(cudaGetLastError());
+        inv(out, batch, st);
+    }
+};
+
+template <class A>
+std::shared_ptr<PrimePlan> make_impl(size_t n, uint64_t p, const pm::Twiddles& t) {
+    return PlanImpl<A>::create(n, p, t);
+}
+
+}  // namespace
+
+std::shared_ptr<PrimePlan> make_plan64(size_t n, uint64_t p) {
+    auto t = pm::build_twiddles(n, p, 16);
+    if (!t) return nullptr;
+    if (p == pm::kSolinas) return make_impl<Solinas64>(n, p, *t);
+    if (p < (uint64_t(1) << 62)) return make_impl<Shoup<uint64_t, true>>(n, p, *t);
+    if (p < (uint64_t(1) << 63)) return make_impl<Shoup<uint64_t, false>>(n, p, *t);
+    return make_impl<Mont64>(n, p, *t);
+}
+
+std::shared_ptr<PrimePlan> make_plan32(size_t n, uint32_t p) {
+    auto t = pm::build_twiddles(n, p, 32);
+    if (!t) return nullptr;
+    if (p < (uint32_t(1) << 30)) return make_impl<Shoup<uint32_t, true>>(n, p, *t);
+    if (p < (uint32_t(1) << 31)) return make_impl<Shoup<uint32_t, false>>(n, p, *t);
+    return make_impl<Wide32>(n, p, *t);
+}
+
+}  // namespace nttb200

@@ -1,0 +1,69 @@
+// Host-side engine: plan objects that own device tables and launch the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace nttb200 {
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define NTT_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            throw ::nttb200::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__));  \
+    } while (0)
+
+// Abstract prime plan (prime32::Plan / prime64::Plan); one concrete class per modulus family.
+struct PrimePlan {
+    size_t n = 0;
+    int logn = 0;
+    int elem_bytes = 0;  // 4 or 8
+    uint64_t p = 0;
+    bool can_use_fast_reduction_code = false;
+    int device = 0;
+    const char* family = "";
+
+    virtual ~PrimePlan() = default;
+    // all pointers are device pointers on `device`; asynchronous on `stream`
+    virtual void fwd(void* data, size_t batch, cudaStream_t stream) const = 0;
+    virtual void inv(void* data, size_t batch, cudaStream_t stream) const = 0;
+    virtual void normalize(void* v, size_t total, cudaStream_t stream) const = 0;
+    virtual void mul_assign_normalize(void* lhs, const void* rhs, size_t total, size_t rhs_period,
+                                      cudaStream_t stream) const = 0;
+    virtual void mul_accumulate(void* acc, const void* lhs, const void* rhs, size_t total,
+                                size_t lhs_period, size_t rhs_period,
+                                cudaStream_t stream) const = 0;
+    // out[b] = inv(acc[b % acc_polys] + fwd(lhs[b]) * rhs[b % rhs_polys]); acc may be null
+    virtual void fwd_mac_inv(void* out, const void* lhs, const void* rhs, size_t rhs_polys,
+                             const void* acc, size_t acc_polys, size_t batch,
+                             cudaStream_t stream) const = 0;
+    virtual std::shared_ptr<PrimePlan> clone() const = 0;
+};
+
+// nullptr <=> the reference's try_new returns None.  Throws CudaError on CUDA failures.
+std::shared_ptr<PrimePlan> make_plan64(size_t n, uint64_t p);
+std::shared_ptr<PrimePlan> make_plan32(size_t n, uint32_t p);
+
+// RAII device scope
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        cur = dev;
+    }
+    ~DeviceGuard() {
+        if (prev != cur) cudaSetDevice(prev);
+    }
+    int cur;
+};
+
+}  // namespace nttb200
