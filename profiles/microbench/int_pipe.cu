@@ -4,18 +4,23 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <vector>
+#include <algorithm>
 
 #define ITERS 4096
 #define CHAINS 8
 
 template <int MODE>
 __global__ void bench(uint32_t* out, uint32_t a, uint32_t b, long long* cycles) {
+    // cycles[4*block + {0: min start clock, 1: max end clock, 2: smid, 3: max end globaltimer - min start}]
     uint32_t x[CHAINS], y[CHAINS];
 #pragma unroll
     for (int i = 0; i < CHAINS; ++i) {
         x[i] = threadIdx.x + i;
         y[i] = blockIdx.x + 3 * i;
     }
+    unsigned long long g0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
@@ -46,6 +51,11 @@ __global__ void bench(uint32_t* out, uint32_t a, uint32_t b, long long* cycles) 
                 asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(y[i]) : "r"(x[i]));
             } else if (MODE == 7) {  // mul.hi.u32 (IMAD.HI)
                 asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(a));
+            } else if (MODE == 9) {  // pure IMAD.WIDE.U32: 64-bit accumulator chain
+                uint64_t w = ((uint64_t)y[i] << 32) | x[i];
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w) : "r"(x[i]), "r"(a));
+                x[i] = (uint32_t)w;
+                y[i] = (uint32_t)(w >> 32);
             } else if (MODE == 8) {  // min.u32
                 asm volatile("min.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
                 asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a));
@@ -57,53 +67,79 @@ __global__ void bench(uint32_t* out, uint32_t a, uint32_t b, long long* cycles) 
 #pragma unroll
     for (int i = 0; i < CHAINS; ++i) s += x[i] ^ y[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    if ((threadIdx.x & 31) == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        atomicMin((unsigned long long*)&cycles[4 * blockIdx.x + 0], (unsigned long long)t0);
+        atomicMax((unsigned long long*)&cycles[4 * blockIdx.x + 1], (unsigned long long)t1);
+        cycles[4 * blockIdx.x + 2] = smid;
+        atomicMin((unsigned long long*)&cycles[4 * blockIdx.x + 3], g0);
+        atomicMax((unsigned long long*)&cycles[4 * blockIdx.x + 3 + 4 * gridDim.x], g1);
+    }
 }
 
 template <int MODE>
-void run(const char* name, int ops_per_chain_iter) {
+void run(const char* name, int instr_per_chain_iter) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int threads = 1024, blocks = sms * 2;
     uint32_t* out;
     long long* cyc;
+    size_t cyc_n = (size_t)blocks * 8;
     cudaMalloc(&out, (size_t)blocks * threads * 4);
-    cudaMalloc(&cyc, blocks * sizeof(long long));
-    bench<MODE><<<blocks, threads>>>(out, 12345u, 678u, cyc);
+    cudaMalloc(&cyc, cyc_n * sizeof(long long));
+    std::vector<long long> init(cyc_n, 0);
+    for (int b = 0; b < blocks; ++b) { init[4 * b + 0] = -1; init[4 * b + 3] = -1; }  // min slots = UINT64_MAX
+    // spin the clocks up first: ~50 ms of the same kernel
+    for (int w = 0; w < 40; ++w) {
+        cudaMemcpy(cyc, init.data(), cyc_n * sizeof(long long), cudaMemcpyHostToDevice);
+        bench<MODE><<<blocks, threads>>>(out, 12345u, 678u, cyc);
+    }
     cudaDeviceSynchronize();
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaEventRecord(e0);
-    bench<MODE><<<blocks, threads>>>(out, 12345u, 678u, cyc);
-    cudaEventRecord(e1);
-    cudaDeviceSynchronize();
-    float ms;
-    cudaEventElapsedTime(&ms, e0, e1);
-    long long h[4096];
-    cudaMemcpy(h, cyc, blocks * sizeof(long long), cudaMemcpyDeviceToHost);
-    double avg = 0;
-    for (int i = 0; i < blocks; ++i) avg += h[i];
-    avg /= blocks;
-    // per SM: 2 resident blocks of 1024 threads run concurrently for ~avg cycles
-    double lane_ops_per_sm = 2.0 * threads * (double)ITERS * CHAINS * ops_per_chain_iter;
-    double per_clk = lane_ops_per_sm / avg;
-    double total_ops = lane_ops_per_sm * sms;
-    printf("%-34s %8.1f lane-ops/clk/SM  (%.2f warp-instr/clk/SM)  %7.2f Tops/s  %.3f ms  clk~%.0f MHz\n", name,
-           per_clk, per_clk / 32, total_ops / (ms * 1e-3) / 1e12, ms, avg / (ms * 1e-3) / 1e6);
+    std::vector<long long> h(cyc_n);
+    cudaMemcpy(h.data(), cyc, cyc_n * sizeof(long long), cudaMemcpyDeviceToHost);
+    // per SM: span between the earliest start and the latest end of the blocks that ran there
+    std::vector<unsigned long long> s0(1024, ~0ull), s1(1024, 0), nb(1024, 0);
+    unsigned long long g0 = ~0ull, g1 = 0;
+    for (int b = 0; b < blocks; ++b) {
+        int sm = (int)h[4 * b + 2];
+        s0[sm] = std::min<unsigned long long>(s0[sm], (unsigned long long)h[4 * b + 0]);
+        s1[sm] = std::max<unsigned long long>(s1[sm], (unsigned long long)h[4 * b + 1]);
+        nb[sm]++;
+        g0 = std::min<unsigned long long>(g0, (unsigned long long)h[4 * b + 3]);
+        g1 = std::max<unsigned long long>(g1, (unsigned long long)h[4 * b + 3 + 4 * blocks]);
+    }
+    double rate_sum = 0, span_sum = 0;
+    int used = 0;
+    for (int sm = 0; sm < 1024; ++sm)
+        if (nb[sm]) {
+            double span = (double)(s1[sm] - s0[sm]);
+            double work = (double)nb[sm] * threads * (double)ITERS * CHAINS * instr_per_chain_iter;
+            rate_sum += work / span;
+            span_sum += span;
+            ++used;
+        }
+    double per_clk = rate_sum / used;  // lane-instr / clk / SM
+    double mhz = (span_sum / used) / (double)(g1 - g0) * 1e3;
+    printf("%-34s %7.1f lane-instr/clk/SM = %.2f warp-instr/clk/SM (%.2f per SMSP)   SM clock %.0f MHz  -> %.2f T lane-instr/s\n",
+           name, per_clk, per_clk / 32, per_clk / 128, mhz, per_clk * sms * mhz * 1e6 / 1e12);
     cudaFree(out);
     cudaFree(cyc);
 }
 
 int main() {
+    // second argument = SASS instructions per chain per iteration (checked with cuobjdump)
     run<0>("IMAD (mad.lo.u32)", 1);
-    run<1>("IMAD.WIDE.U32", 1);
-    run<2>("IADD (add.u32 x2)", 2);
-    run<3>("64-bit add (add.cc+addc)", 2);
+    run<1>("IMAD.WIDE+IADD3+IMAD.X (3/chain)", 3);
+    run<2>("IADD3 / IMAD.IADD mix (add.u32 x2)", 2);
+    run<3>("IADD3 + IADD3.X (64-bit add)", 2);
     run<4>("IMAD + IADD interleaved", 2);
-    run<5>("IMAD.WIDE + 2 IADD3 (carry)", 3);
+    run<5>("IMAD.WIDE + 3 IADD3", 4);
     run<6>("LOP3 + SHF", 2);
     run<7>("IMAD.HI (mul.hi.u32)", 1);
-    run<8>("IMNMX + IADD", 2);
+    run<8>("VIMNMX + IMAD.IADD", 2);
+    run<9>("IMAD.WIDE+IADD3+IMAD.X (b)", 3);
     return 0;
 }

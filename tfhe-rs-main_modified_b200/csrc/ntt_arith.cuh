@@ -181,77 +181,94 @@ struct Wide32 {
 // ------------------------------------------------------------------------------------
 struct Solinas64 {
     using T = uint64_t;
-    using TW = uint64_t;
+    using TW = uint64_t;  // twiddle in Montgomery form: w * 2^64 mod p
     struct Ctx {
-        uint64_t p;  // unused in the butterflies (compile-time constant); keeps the interface uniform
+        uint64_t p;  // compile-time constant in the butterflies; kept for a uniform interface
     };
     static constexpr bool kHarvey = false;
     static constexpr uint64_t P = 0xFFFFFFFF00000001ull;
     static constexpr uint64_t EPS = 0xFFFFFFFFull;
 
-    // (hi:lo) mod p, result <= p-1+... canonical: in [0,p)
-    NTT_DEVINL static uint64_t reduce128(uint64_t lo, uint64_t hi) {
-        uint32_t hh = (uint32_t)(hi >> 32), mid = (uint32_t)hi;
-        // lo - hh, borrow folds as -eps
-        uint64_t t0 = lo - hh;
-        if (lo < (uint64_t)hh) t0 -= EPS;
-        // + mid*eps = (mid<<32) - mid
-        uint64_t m = ((uint64_t)mid << 32) - mid;
-        uint64_t t1 = t0 + m;
-        if (t1 < m) t1 += EPS;  // wrapped: +2^64 == +eps ; cannot wrap twice (m <= 2^64-2^33+1)
-        // canonicalise: t1 >= p  <=>  t1 + eps wraps, and then t1 - p = wrapped(t1 + eps)
-        uint64_t u = t1 + EPS;
-        return u < t1 ? u : t1;
+    // Montgomery product b * wm * 2^-64 mod p, canonical, for any 64-bit b and wm < p.
+    // With p = 2^64 - 2^32 + 1 the REDC needs no multiplication (p^-1 = 2^32 + 1 mod 2^64):
+    //   T = b*wm = (hi : x1 : x0);  m1 = (x0 + x1) mod 2^32, c = its carry
+    //   S = m1*(2^32-1) + x0 - c = ((m1 + c) << 32) - (x1 + c)        (0 <= S < 2^64)
+    //   r = hi - S  in (-p, p);  negative -> + p, i.e. - (2^32-1) in wrapping arithmetic
+    // Only carry chains of one family are combined (add.cc/addc, sub.cc/subc are never mixed).
+    NTT_DEVINL static uint64_t mulm(uint64_t b, uint64_t wm) {
+        unsigned __int128 t = (unsigned __int128)b * wm;  // 4 IMAD.WIDE.U32 + 3
+        uint64_t lo = (uint64_t)t, hi = (uint64_t)(t >> 64), r;
+        asm("{ .reg .u32 x0,x1,h0,h1,m1,c,s0,s1,m;\n\t"
+            "mov.b64 {x0,x1}, %1; mov.b64 {h0,h1}, %2;\n\t"
+            "add.cc.u32 m1,x0,x1; addc.u32 c,0,0;\n\t"
+            "sub.cc.u32 s0,0,x1; subc.u32 s1,m1,0;\n\t"
+            "sub.u32 s0,s0,c; add.u32 s1,s1,c;\n\t"
+            "sub.cc.u32 h0,h0,s0; subc.cc.u32 h1,h1,s1; subc.u32 m,0,0;\n\t"
+            "sub.cc.u32 h0,h0,m; subc.u32 h1,h1,0;\n\t"
+            "mov.b64 %0,{h0,h1}; }"
+            : "=l"(r)
+            : "l"(lo), "l"(hi));
+        return r;
     }
-    NTT_DEVINL static uint64_t mul(uint64_t a, uint64_t b) { return reduce128(a * b, __umul64hi(a, b)); }
-    // a arbitrary, b <= p : result arbitrary 64-bit representative
+    // a arbitrary 64-bit representative, b <= p: a + b with a wrap folded as +eps
+    // (s + 2^64 == s + eps; cannot wrap twice because b <= p)
     NTT_DEVINL static uint64_t add_lazy(uint64_t a, uint64_t b) {
-        uint64_t s = a + b;
-        if (s < a) s += EPS;
-        return s;
+        uint64_t r;
+        asm("{ .reg .u32 a0,a1,b0,b1,c;\n\t"
+            "mov.b64 {a0,a1}, %1; mov.b64 {b0,b1}, %2;\n\t"
+            "add.cc.u32 a0,a0,b0; addc.cc.u32 a1,a1,b1; addc.u32 c,0,0;\n\t"
+            "add.u32 a1,a1,c; sub.cc.u32 a0,a0,c; subc.u32 a1,a1,0;\n\t"
+            "mov.b64 %0, {a0,a1}; }"
+            : "=l"(r)
+            : "l"(a), "l"(b));
+        return r;
     }
-    // a arbitrary, b <= p
+    // a arbitrary, b <= p: a - b with a borrow folded as -eps (cannot underflow twice)
     NTT_DEVINL static uint64_t sub_lazy(uint64_t a, uint64_t b) {
-        uint64_t d = a - b;
-        if (a < b) d -= EPS;
-        return d;
+        uint64_t r;
+        asm("{ .reg .u32 a0,a1,b0,b1,m;\n\t"
+            "mov.b64 {a0,a1}, %1; mov.b64 {b0,b1}, %2;\n\t"
+            "sub.cc.u32 a0,a0,b0; subc.cc.u32 a1,a1,b1; subc.u32 m,0,0;\n\t"
+            "sub.cc.u32 a0,a0,m; subc.u32 a1,a1,0;\n\t"
+            "mov.b64 %0, {a0,a1}; }"
+            : "=l"(r)
+            : "l"(a), "l"(b));
+        return r;
     }
-    // both arbitrary
-    NTT_DEVINL static uint64_t add_any(uint64_t a, uint64_t b) {
-        uint64_t s = a + b;
-        if (s < a) {
-            uint64_t s2 = s + EPS;
-            s = s2 < s ? s2 + EPS : s2;
-        }
-        return s;
-    }
-    NTT_DEVINL static uint64_t sub_any(uint64_t a, uint64_t b) {
-        uint64_t d = a - b;
-        if (a < b) {
-            uint64_t d2 = d - EPS;
-            d = d2 > d ? d2 - EPS : d2;
-        }
-        return d;
-    }
+    // canonical representative of an arbitrary 64-bit value: a >= p <=> a + eps wraps
     NTT_DEVINL static uint64_t canon(uint64_t a) {
         uint64_t u = a + EPS;
         return u < a ? u : a;
     }
+    // plain (non-Montgomery) product of two arbitrary 64-bit values, canonical:
+    // the reference's fold (generic_solinas.rs:102-128) with 2^64 == eps, 2^96 == -1
+    NTT_DEVINL static uint64_t mul_plain(uint64_t a, uint64_t b) {
+        unsigned __int128 t = (unsigned __int128)a * b;
+        uint64_t lo = (uint64_t)t, hi = (uint64_t)(t >> 64);
+        uint32_t hh = (uint32_t)(hi >> 32), mid = (uint32_t)hi;
+        uint64_t t0 = lo - hh;
+        if (lo < (uint64_t)hh) t0 -= EPS;
+        uint64_t m = ((uint64_t)mid << 32) - mid;
+        uint64_t t1 = t0 + m;
+        if (t1 < m) t1 += EPS;
+        return canon(t1);
+    }
     NTT_DEVINL static void fwd_bf(const Ctx&, T& a, T& b, TW w) {
-        T t = mul(b, w), z0 = a;
+        T t = mulm(b, w), z0 = a;
         a = add_lazy(z0, t);
         b = sub_lazy(z0, t);
     }
+    // Gentleman-Sande: both inputs may be arbitrary representatives, so bring b into [0,p) first
     NTT_DEVINL static void inv_bf(const Ctx&, T& a, T& b, TW w) {
-        T s = add_any(a, b), d = sub_any(a, b);
-        a = s;
-        b = mul(d, w);
+        T bc = canon(b), z0 = a;
+        a = add_lazy(z0, bc);
+        b = mulm(sub_lazy(z0, bc), w);
     }
     NTT_DEVINL static T fwd_fin(const Ctx&, T a) { return canon(a); }
     NTT_DEVINL static T inv_fin(const Ctx&, T a) { return canon(a); }
-    NTT_DEVINL static T mul_const(const Ctx&, T a, TW w) { return mul(a, w); }
+    NTT_DEVINL static T mul_const(const Ctx&, T a, TW wm) { return mulm(a, wm); }
     NTT_DEVINL static T add_full(const Ctx&, T a, T b) { return canon(add_lazy(a, b)); }
-    NTT_DEVINL static T mul_full(const Ctx&, T a, T b) { return mul(a, b); }
+    NTT_DEVINL static T mul_full(const Ctx&, T a, T b) { return mul_plain(a, b); }
 };
 
 // ------------------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <mutex>
 
+#include "ntt_fast.cuh"
 #include "ntt_kernels.cuh"
 #include "plan_math.hpp"
 
@@ -75,7 +76,7 @@ struct Build<Wide32> {
 template <>
 struct Build<Solinas64> {
     using A = Solinas64;
-    static A::TW tw(uint64_t w, uint64_t) { return w; }
+    static A::TW tw(uint64_t w, uint64_t p) { return (uint64_t)((((u128)w) << 64) % p); }
     static A::Ctx ctx(uint64_t p) { return A::Ctx{p}; }
     static const char* name() { return "solinas64"; }
 };
@@ -93,6 +94,8 @@ struct Build<Mont64> {
     }
     static const char* name() { return "mont64"; }
 };
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count(int device) {
     static std::mutex mu;
@@ -162,7 +165,7 @@ struct PlanImpl final : PrimePlan {
         unsigned rows_per_cta = row >= 2048 ? 1u : (unsigned)(2048 / row);
         if (num_rows < rows_per_cta) rows_per_cta = (unsigned)num_rows;
         size_t elems = row * rows_per_cta;
-        unsigned threads = (unsigned)std::min<size_t>(1024, std::max<size_t>(64, elems / 8));
+        unsigned threads = (unsigned)std::min<size_t>(512, std::max<size_t>(64, elems / 8));
         size_t smem = elems * sizeof(T);
         auto kern = ntt_rows_kernel<A, INV>;
         if (smem > 48 * 1024) {
@@ -200,6 +203,7 @@ struct PlanImpl final : PrimePlan {
         if (!batch) return;
         DeviceGuard g(device);
         T* d = static_cast<T*>(data);
+        if (aligned16(d) && fast_fwd<A>(d, batch, logn, d_fwd.get(), ctx, st)) return;
         int depth = std::max(0, logn - kMaxLogRow);
         for (int s = 0; s < depth;) {  // top stages in global memory, 3 at a time
             int r = std::min(3, depth - s);
@@ -212,6 +216,7 @@ struct PlanImpl final : PrimePlan {
         if (!batch) return;
         DeviceGuard g(device);
         T* d = static_cast<T*>(data);
+        if (aligned16(d) && fast_inv<A>(d, batch, logn, d_inv.get(), ctx, st)) return;
         int depth = std::max(0, logn - kMaxLogRow);
         launch_rows<true>(d, batch << depth, logn - depth, depth, depth == 0, st);
         // mirror of fwd: the same stage groups in reverse order
@@ -257,6 +262,11 @@ struct PlanImpl final : PrimePlan {
         if (!batch) return;
         DeviceGuard g(device);
         size_t total = batch * n;
+        if (aligned16(out) && aligned16(lhs) && aligned16(rhs) && aligned16(acc) &&
+            fast_fwd_mac_inv<A>(static_cast<T*>(out), static_cast<const T*>(lhs),
+                                static_cast<const T*>(rhs), rhs_polys, static_cast<const T*>(acc),
+                                acc_polys, batch, logn, d_fwd.get(), d_inv.get(), ctx, st))
+            return;
         if (out != lhs)
             NTT_CUDA_CHECK(cudaMemcpyAsync(out, lhs, total * sizeof(T), cudaMemcpyDeviceToDevice, st));
         fwd(out, batch, st);

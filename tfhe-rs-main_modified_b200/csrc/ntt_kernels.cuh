@@ -85,7 +85,7 @@ NTT_DEVINL void pass_over_rows(typename A::T* s, unsigned rows, unsigned row0, i
 // stages of each.  depth > 0 means the rows are the 2^depth sub-blocks of longer polynomials
 // whose first `depth` stages run in ntt_global_pass_kernel.
 template <class A, bool INV>
-__global__ void ntt_rows_kernel(typename A::T* __restrict__ data, size_t num_rows, int log_row,
+__global__ void __launch_bounds__(512) ntt_rows_kernel(typename A::T* __restrict__ data, size_t num_rows, int log_row,
                                 int depth, const typename A::TW* __restrict__ tw,
                                 typename A::Ctx c, unsigned rows_per_cta, int finalize) {
     using T = typename A::T;
@@ -150,7 +150,7 @@ __global__ void ntt_rows_kernel(typename A::T* __restrict__ data, size_t num_row
 // Strided pass in global memory over whole polynomials of length 2^logn: stages
 // [stage, stage+R).  Used for the top `depth` stages when a polynomial does not fit one CTA.
 template <class A, int R, bool INV>
-__global__ void ntt_global_pass_kernel(typename A::T* __restrict__ data, size_t num_polys,
+__global__ void __launch_bounds__(256) ntt_global_pass_kernel(typename A::T* __restrict__ data, size_t num_polys,
                                        int logn, int stage,
                                        const typename A::TW* __restrict__ tw, typename A::Ctx c,
                                        int finalize) {
