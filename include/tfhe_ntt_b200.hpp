@@ -1,0 +1,242 @@
+// tfhe_ntt_b200.hpp -- header-only C++17 host layer over the C ABI (tfhe_ntt_b200.h).
+//
+// The reference is compiled code (Rust) and this image has no Rust toolchain, so this is the
+// compiled-language mirror of the reference's public API: same module (namespace), type and
+// method names, same argument meaning and error behaviour
+//   tfhe_ntt::prime64::Plan   <- tfhe-ntt/src/prime64.rs:245-1223
+//   tfhe_ntt::prime32::Plan   <- tfhe-ntt/src/prime32.rs:632-1016
+//   tfhe_ntt::native64::Plan32 ... <- tfhe-ntt/src/native{32,64,128}.rs, native_binary*.rs
+//   tfhe_ntt::fastdiv::{Div32,Div64} <- tfhe-ntt/src/fastdiv.rs:29-150
+// `try_new` returns std::optional (Rust Option); length assertions throw std::logic_error where
+// the reference panics; CUDA failures throw std::runtime_error.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "tfhe_ntt_b200.h"
+
+namespace tfhe_ntt {
+
+inline void check(int status, const char* what) {
+    if (status == NTT_B200_OK) return;
+    if (status == NTT_B200_ERR_LEN)
+        throw std::logic_error(std::string("assertion failed: length mismatch in ") + what);
+    throw std::runtime_error(std::string(what) + ": " + ntt_b200_last_error());
+}
+
+namespace prime {
+inline bool is_prime64(uint64_t n) { return ntt_b200_is_prime64(n) != 0; }
+inline std::optional<uint64_t> largest_prime_in_arithmetic_progression64(uint64_t factor,
+                                                                         uint64_t offset,
+                                                                         uint64_t lo, uint64_t hi) {
+    uint64_t out = 0;
+    if (!ntt_b200_largest_prime_in_arithmetic_progression64(factor, offset, lo, hi, &out))
+        return std::nullopt;
+    return out;
+}
+}  // namespace prime
+
+namespace fastdiv {
+// Exact division by an invariant divisor (the reference uses Lemire's method; only the exact
+// quotient/remainder is observable, fastdiv.rs:159-195).
+struct Div32 {
+    uint32_t d;
+    explicit constexpr Div32(uint32_t divisor) : d(divisor) {}
+    static constexpr uint32_t div(uint32_t n, Div32 x) { return n / x.d; }
+    static constexpr uint32_t rem(uint32_t n, Div32 x) { return n % x.d; }
+    static constexpr uint64_t div_u64(uint64_t n, Div32 x) { return n / x.d; }
+    static constexpr uint32_t rem_u64(uint64_t n, Div32 x) { return (uint32_t)(n % x.d); }
+    constexpr uint32_t divisor() const { return d; }
+};
+struct Div64 {
+    uint64_t d;
+    explicit constexpr Div64(uint64_t divisor) : d(divisor) {}
+    static constexpr uint64_t div(uint64_t n, Div64 x) { return n / x.d; }
+    static constexpr uint64_t rem(uint64_t n, Div64 x) { return n % x.d; }
+    static constexpr unsigned __int128 div_u128(unsigned __int128 n, Div64 x) { return n / x.d; }
+    static constexpr uint64_t rem_u128(unsigned __int128 n, Div64 x) { return (uint64_t)(n % x.d); }
+    constexpr uint64_t divisor() const { return d; }
+};
+}  // namespace fastdiv
+
+#define TFHE_NTT_PRIME_PLAN(NS, SFX, ELEM)                                                        \
+    namespace NS {                                                                                \
+    class Plan {                                                                                  \
+        struct Del {                                                                              \
+            void operator()(ntt_b200_plan##SFX* p) const { ntt_b200_plan##SFX##_free(p); }        \
+        };                                                                                        \
+        std::unique_ptr<ntt_b200_plan##SFX, Del> h_;                                              \
+        explicit Plan(ntt_b200_plan##SFX* h) : h_(h) {}                                           \
+                                                                                                  \
+       public:                                                                                    \
+        static std::optional<Plan> try_new(size_t polynomial_size, ELEM modulus) {                \
+            ntt_b200_plan##SFX* h = nullptr;                                                      \
+            int st = ntt_b200_plan##SFX##_try_new(polynomial_size, modulus, &h);                  \
+            if (st == NTT_B200_NONE) return std::nullopt;                                         \
+            check(st, #NS "::Plan::try_new");                                                     \
+            return Plan(h);                                                                       \
+        }                                                                                         \
+        Plan clone() const {                                                                      \
+            ntt_b200_plan##SFX* h = nullptr;                                                      \
+            check(ntt_b200_plan##SFX##_clone(h_.get(), &h), "clone");                             \
+            return Plan(h);                                                                       \
+        }                                                                                         \
+        size_t ntt_size() const { return ntt_b200_plan##SFX##_ntt_size(h_.get()); }               \
+        ELEM modulus() const { return ntt_b200_plan##SFX##_modulus(h_.get()); }                   \
+        bool can_use_fast_reduction_code() const {                                                \
+            return ntt_b200_plan##SFX##_can_use_fast_reduction_code(h_.get()) != 0;               \
+        }                                                                                         \
+        int device() const { return ntt_b200_plan##SFX##_device(h_.get()); }                      \
+        const ntt_b200_plan##SFX* raw() const { return h_.get(); }                                \
+        void fwd(ELEM* buf, size_t len) const {                                                   \
+            check(ntt_b200_plan##SFX##_fwd(h_.get(), buf, len), #NS "::Plan::fwd");               \
+        }                                                                                         \
+        void inv(ELEM* buf, size_t len) const {                                                   \
+            check(ntt_b200_plan##SFX##_inv(h_.get(), buf, len), #NS "::Plan::inv");               \
+        }                                                                                         \
+        void fwd(std::vector<ELEM>& buf) const { fwd(buf.data(), buf.size()); }                   \
+        void inv(std::vector<ELEM>& buf) const { inv(buf.data(), buf.size()); }                   \
+        void normalize(ELEM* values, size_t len) const {                                          \
+            check(ntt_b200_plan##SFX##_normalize(h_.get(), values, len), "normalize");            \
+        }                                                                                         \
+        void mul_assign_normalize(ELEM* lhs, size_t lhs_len, const ELEM* rhs,                     \
+                                  size_t rhs_len) const {                                         \
+            check(ntt_b200_plan##SFX##_mul_assign_normalize(h_.get(), lhs, lhs_len, rhs, rhs_len),\
+                  "mul_assign_normalize");                                                        \
+        }                                                                                         \
+        void mul_accumulate(ELEM* acc, size_t acc_len, const ELEM* lhs, size_t lhs_len,           \
+                            const ELEM* rhs, size_t rhs_len) const {                              \
+            check(ntt_b200_plan##SFX##_mul_accumulate(h_.get(), acc, acc_len, lhs, lhs_len, rhs,  \
+                                                      rhs_len),                                   \
+                  "mul_accumulate");                                                              \
+        }                                                                                         \
+        /* new: batched host / device-resident */                                                 \
+        void fwd_batch(ELEM* host, size_t batch) const {                                          \
+            check(ntt_b200_plan##SFX##_fwd_batch(h_.get(), host, batch), "fwd_batch");            \
+        }                                                                                         \
+        void inv_batch(ELEM* host, size_t batch) const {                                          \
+            check(ntt_b200_plan##SFX##_inv_batch(h_.get(), host, batch), "inv_batch");            \
+        }                                                                                         \
+        void fwd_device(ELEM* dev, size_t batch, void* stream = nullptr) const {                  \
+            check(ntt_b200_plan##SFX##_fwd_device(h_.get(), dev, batch, stream), "fwd_device");   \
+        }                                                                                         \
+        void inv_device(ELEM* dev, size_t batch, void* stream = nullptr) const {                  \
+            check(ntt_b200_plan##SFX##_inv_device(h_.get(), dev, batch, stream), "inv_device");   \
+        }                                                                                         \
+        void normalize_device(ELEM* dev, size_t len, void* stream = nullptr) const {              \
+            check(ntt_b200_plan##SFX##_normalize_device(h_.get(), dev, len, stream),              \
+                  "normalize_device");                                                            \
+        }                                                                                         \
+        void mul_accumulate_device(ELEM* acc, size_t len, const ELEM* lhs, size_t lhs_len,        \
+                                   const ELEM* rhs, size_t rhs_len, void* stream = nullptr) const {\
+            check(ntt_b200_plan##SFX##_mul_accumulate_device(h_.get(), acc, len, lhs, lhs_len,    \
+                                                             rhs, rhs_len, stream),               \
+                  "mul_accumulate_device");                                                       \
+        }                                                                                         \
+        void fwd_mac_inv_device(ELEM* out, const ELEM* lhs, const ELEM* rhs, size_t rhs_polys,    \
+                                const ELEM* acc, size_t acc_polys, size_t batch,                  \
+                                void* stream = nullptr) const {                                   \
+            check(ntt_b200_plan##SFX##_fwd_mac_inv_device(h_.get(), out, lhs, rhs, rhs_polys, acc,\
+                                                          acc_polys, batch, stream),              \
+                  "fwd_mac_inv_device");                                                          \
+        }                                                                                         \
+    };                                                                                            \
+    }
+
+TFHE_NTT_PRIME_PLAN(prime64, 64, uint64_t)
+TFHE_NTT_PRIME_PLAN(prime32, 32, uint32_t)
+#undef TFHE_NTT_PRIME_PLAN
+
+namespace prime64 {
+constexpr uint64_t SOLINAS_PRIME = 0xFFFFFFFF00000001ull;  // prime64.rs:8
+struct Solinas {
+    static constexpr uint64_t P = SOLINAS_PRIME;  // generic_solinas.rs:38-40
+};
+}  // namespace prime64
+
+// CRT plans: KIND selects the reference type, V the value word, R the residue word, NP the
+// number of primes (= number of mod_p* buffers of fwd/inv).
+template <int KIND, class V, class R, int NP, bool BINARY>
+class NativePlan {
+    struct Del {
+        void operator()(ntt_b200_native_plan* p) const { ntt_b200_native_free(p); }
+    };
+    std::unique_ptr<ntt_b200_native_plan, Del> h_;
+    explicit NativePlan(ntt_b200_native_plan* h) : h_(h) {}
+
+   public:
+    using value_type = V;
+    using residue_type = R;
+    static constexpr int num_primes = NP;
+    static std::optional<NativePlan> try_new(size_t n) {
+        ntt_b200_native_plan* h = nullptr;
+        int st = ntt_b200_native_try_new(KIND, n, &h);
+        if (st == NTT_B200_NONE) return std::nullopt;
+        check(st, "try_new");
+        return NativePlan(h);
+    }
+    size_t ntt_size() const { return ntt_b200_native_ntt_size(h_.get()); }
+    // fwd(value, mod_p0, .., mod_p{NP-1})   e.g. native64.rs:970
+    void fwd(const V* value, size_t len, const std::array<R*, NP>& mod_p) const {
+        void* r[NP];
+        for (int i = 0; i < NP; ++i) r[i] = mod_p[i];
+        check(ntt_b200_native_fwd(h_.get(), value, len, r, 0), "fwd");
+    }
+    void fwd_binary(const V* value, size_t len, const std::array<R*, NP>& mod_p) const {
+        static_assert(BINARY, "fwd_binary exists on the native_binary plans only");
+        void* r[NP];
+        for (int i = 0; i < NP; ++i) r[i] = mod_p[i];
+        check(ntt_b200_native_fwd(h_.get(), value, len, r, 1), "fwd_binary");
+    }
+    // inv(value, mod_p0, ..) -- clobbers the residue buffers like the reference (native64.rs:1009)
+    void inv(V* value, size_t len, const std::array<R*, NP>& mod_p) const {
+        void* r[NP];
+        for (int i = 0; i < NP; ++i) r[i] = mod_p[i];
+        check(ntt_b200_native_inv(h_.get(), value, len, r), "inv");
+    }
+    void negacyclic_polymul(V* prod, size_t prod_len, const V* lhs, size_t lhs_len, const V* rhs,
+                            size_t rhs_len) const {
+        check(ntt_b200_native_negacyclic_polymul(h_.get(), prod, prod_len, lhs, lhs_len, rhs, rhs_len),
+              "negacyclic_polymul");
+    }
+    void negacyclic_polymul_batch(V* prod, const V* lhs, const V* rhs, size_t batch) const {
+        check(ntt_b200_native_negacyclic_polymul_batch(h_.get(), prod, lhs, rhs, batch),
+              "negacyclic_polymul_batch");
+    }
+    void negacyclic_polymul_device(V* prod, const V* lhs, const V* rhs, size_t batch,
+                                   void* stream = nullptr) const {
+        check(ntt_b200_native_negacyclic_polymul_device(h_.get(), prod, lhs, rhs, batch, stream),
+              "negacyclic_polymul_device");
+    }
+};
+
+using u128 = unsigned __int128;
+namespace native32 {
+using Plan32 = NativePlan<NTT_B200_NATIVE32_PLAN32, uint32_t, uint32_t, 3, false>;
+using Plan52 = NativePlan<NTT_B200_NATIVE32_PLAN52, uint32_t, uint64_t, 2, false>;
+}  // namespace native32
+namespace native64 {
+using Plan32 = NativePlan<NTT_B200_NATIVE64_PLAN32, uint64_t, uint32_t, 5, false>;
+using Plan52 = NativePlan<NTT_B200_NATIVE64_PLAN52, uint64_t, uint64_t, 3, false>;
+}  // namespace native64
+namespace native128 {
+using Plan32 = NativePlan<NTT_B200_NATIVE128_PLAN32, u128, uint32_t, 10, false>;
+}
+namespace native_binary32 {
+using Plan32 = NativePlan<NTT_B200_NATIVE_BINARY32_PLAN32, uint32_t, uint32_t, 2, true>;
+using Plan52 = NativePlan<NTT_B200_NATIVE_BINARY32_PLAN52, uint32_t, uint64_t, 1, true>;
+}  // namespace native_binary32
+namespace native_binary64 {
+using Plan32 = NativePlan<NTT_B200_NATIVE_BINARY64_PLAN32, uint64_t, uint32_t, 3, true>;
+using Plan52 = NativePlan<NTT_B200_NATIVE_BINARY64_PLAN52, uint64_t, uint64_t, 2, true>;
+}  // namespace native_binary64
+namespace native_binary128 {
+using Plan32 = NativePlan<NTT_B200_NATIVE_BINARY128_PLAN32, u128, uint32_t, 5, true>;
+}
+
+}  // namespace tfhe_ntt

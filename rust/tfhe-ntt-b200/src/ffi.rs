@@ -1,0 +1,78 @@
+//! Hand-written `extern "C"` block for include/tfhe_ntt_b200.h (no bindgen: no libclang needed).
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_void};
+
+pub const OK: c_int = 0;
+pub const NONE: c_int = 1;
+pub const ERR_LEN: c_int = 2;
+pub const ERR_CUDA: c_int = 3;
+
+#[repr(C)] pub struct ntt_b200_plan64 { _p: [u8; 0] }
+#[repr(C)] pub struct ntt_b200_plan32 { _p: [u8; 0] }
+#[repr(C)] pub struct ntt_b200_native_plan { _p: [u8; 0] }
+
+extern "C" {
+    pub fn ntt_b200_last_error() -> *const c_char;
+    pub fn ntt_b200_set_device(device: c_int) -> c_int;
+    pub fn ntt_b200_is_prime64(n: u64) -> c_int;
+    pub fn ntt_b200_largest_prime_in_arithmetic_progression64(factor: u64, offset: u64, lo: u64, hi: u64, out: *mut u64) -> c_int;
+
+    pub fn ntt_b200_plan64_try_new(n: usize, p: u64, out: *mut *mut ntt_b200_plan64) -> c_int;
+    pub fn ntt_b200_plan64_clone(plan: *const ntt_b200_plan64, out: *mut *mut ntt_b200_plan64) -> c_int;
+    pub fn ntt_b200_plan64_free(plan: *mut ntt_b200_plan64);
+    pub fn ntt_b200_plan64_ntt_size(plan: *const ntt_b200_plan64) -> usize;
+    pub fn ntt_b200_plan64_modulus(plan: *const ntt_b200_plan64) -> u64;
+    pub fn ntt_b200_plan64_use_ifma(plan: *const ntt_b200_plan64) -> c_int;
+    pub fn ntt_b200_plan64_can_use_fast_reduction_code(plan: *const ntt_b200_plan64) -> c_int;
+    pub fn ntt_b200_plan64_fwd(plan: *const ntt_b200_plan64, buf: *mut u64, len: usize) -> c_int;
+    pub fn ntt_b200_plan64_inv(plan: *const ntt_b200_plan64, buf: *mut u64, len: usize) -> c_int;
+    pub fn ntt_b200_plan64_normalize(plan: *const ntt_b200_plan64, values: *mut u64, len: usize) -> c_int;
+    pub fn ntt_b200_plan64_mul_assign_normalize(plan: *const ntt_b200_plan64, lhs: *mut u64, lhs_len: usize, rhs: *const u64, rhs_len: usize) -> c_int;
+    pub fn ntt_b200_plan64_mul_accumulate(plan: *const ntt_b200_plan64, acc: *mut u64, acc_len: usize, lhs: *const u64, lhs_len: usize, rhs: *const u64, rhs_len: usize) -> c_int;
+    pub fn ntt_b200_plan64_fwd_batch(plan: *const ntt_b200_plan64, host: *mut u64, batch: usize) -> c_int;
+    pub fn ntt_b200_plan64_inv_batch(plan: *const ntt_b200_plan64, host: *mut u64, batch: usize) -> c_int;
+    pub fn ntt_b200_plan64_fwd_device(plan: *const ntt_b200_plan64, dev: *mut u64, batch: usize, stream: *mut c_void) -> c_int;
+    pub fn ntt_b200_plan64_inv_device(plan: *const ntt_b200_plan64, dev: *mut u64, batch: usize, stream: *mut c_void) -> c_int;
+
+    pub fn ntt_b200_plan32_try_new(n: usize, p: u32, out: *mut *mut ntt_b200_plan32) -> c_int;
+    pub fn ntt_b200_plan32_clone(plan: *const ntt_b200_plan32, out: *mut *mut ntt_b200_plan32) -> c_int;
+    pub fn ntt_b200_plan32_free(plan: *mut ntt_b200_plan32);
+    pub fn ntt_b200_plan32_ntt_size(plan: *const ntt_b200_plan32) -> usize;
+    pub fn ntt_b200_plan32_modulus(plan: *const ntt_b200_plan32) -> u32;
+    pub fn ntt_b200_plan32_can_use_fast_reduction_code(plan: *const ntt_b200_plan32) -> c_int;
+    pub fn ntt_b200_plan32_fwd(plan: *const ntt_b200_plan32, buf: *mut u32, len: usize) -> c_int;
+    pub fn ntt_b200_plan32_inv(plan: *const ntt_b200_plan32, buf: *mut u32, len: usize) -> c_int;
+    pub fn ntt_b200_plan32_normalize(plan: *const ntt_b200_plan32, values: *mut u32, len: usize) -> c_int;
+    pub fn ntt_b200_plan32_mul_assign_normalize(plan: *const ntt_b200_plan32, lhs: *mut u32, lhs_len: usize, rhs: *const u32, rhs_len: usize) -> c_int;
+    pub fn ntt_b200_plan32_mul_accumulate(plan: *const ntt_b200_plan32, acc: *mut u32, acc_len: usize, lhs: *const u32, lhs_len: usize, rhs: *const u32, rhs_len: usize) -> c_int;
+    pub fn ntt_b200_plan32_fwd_batch(plan: *const ntt_b200_plan32, host: *mut u32, batch: usize) -> c_int;
+    pub fn ntt_b200_plan32_inv_batch(plan: *const ntt_b200_plan32, host: *mut u32, batch: usize) -> c_int;
+
+    pub fn ntt_b200_plan32_fwd_device(plan: *const ntt_b200_plan32, dev: *mut u32, batch: usize, stream: *mut c_void) -> c_int;
+    pub fn ntt_b200_plan32_inv_device(plan: *const ntt_b200_plan32, dev: *mut u32, batch: usize, stream: *mut c_void) -> c_int;
+
+    pub fn ntt_b200_native_try_new(kind: c_int, n: usize, out: *mut *mut ntt_b200_native_plan) -> c_int;
+    pub fn ntt_b200_native_free(plan: *mut ntt_b200_native_plan);
+    pub fn ntt_b200_native_ntt_size(plan: *const ntt_b200_native_plan) -> usize;
+    pub fn ntt_b200_native_ntt_i(plan: *const ntt_b200_native_plan, i: c_int) -> *const c_void;
+    pub fn ntt_b200_native_fwd(plan: *const ntt_b200_native_plan, value: *const c_void, len: usize, residues: *const *mut c_void, binary: c_int) -> c_int;
+    pub fn ntt_b200_native_inv(plan: *const ntt_b200_native_plan, value: *mut c_void, len: usize, residues: *const *mut c_void) -> c_int;
+    pub fn ntt_b200_native_negacyclic_polymul(plan: *const ntt_b200_native_plan, prod: *mut c_void, prod_len: usize, lhs: *const c_void, lhs_len: usize, rhs: *const c_void, rhs_len: usize) -> c_int;
+    pub fn ntt_b200_native_negacyclic_polymul_batch(plan: *const ntt_b200_native_plan, prod: *mut c_void, lhs: *const c_void, rhs: *const c_void, batch: usize) -> c_int;
+}
+
+/// Status -> the reference's behaviour: length errors panic like `assert_eq!` (prime64.rs:898),
+/// CUDA failures print and abort like the reference's own CUDA backend
+/// (backends/tfhe-cuda-backend/cuda/include/device.h:11-19).
+#[track_caller]
+pub fn check(status: c_int, what: &str) {
+    match status {
+        OK => {}
+        ERR_LEN => panic!("assertion failed: length mismatch in {what}"),
+        _ => {
+            let msg = unsafe { core::ffi::CStr::from_ptr(ntt_b200_last_error()) };
+            eprintln!("tfhe-ntt-b200: {what}: {}", msg.to_string_lossy());
+            std::process::abort();
+        }
+    }
+}

@@ -1,0 +1,9 @@
+//! `tfhe-ntt`-compatible API over the B200 CUDA engine (reference: tfhe-ntt/src/lib.rs:83-116).
+//! Module tree, type names and method signatures are the reference's; batched and
+//! device-resident entry points are added alongside.  There is no CPU fallback.
+pub mod ffi;
+pub mod prime;
+pub mod prime32;
+pub mod prime64;
+mod native;
+pub use native::{native128, native32, native64, native_binary128, native_binary32, native_binary64};

@@ -1,0 +1,86 @@
+//! CRT plans (reference: native32.rs, native64.rs, native128.rs, native_binary{32,64,128}.rs).
+//! One macro instantiates every reference type with its own value / residue types and arity.
+use crate::ffi::{self, check};
+use core::ffi::c_void;
+
+macro_rules! native_plan {
+    ($modname:ident, $ty:ident, $kind:expr, $V:ty, $R:ty, $prime:ident, [$($res:ident),+], $binary:expr) => {
+        pub struct $ty { raw: *mut ffi::ntt_b200_native_plan }
+        unsafe impl Send for $ty {}
+        unsafe impl Sync for $ty {}
+        impl $ty {
+            /// e.g. native64.rs:932 — `None` when any per-prime plan is `None`
+            pub fn try_new(n: usize) -> Option<Self> {
+                let mut raw = core::ptr::null_mut();
+                match unsafe { ffi::ntt_b200_native_try_new($kind, n, &mut raw) } {
+                    ffi::OK => Some(Self { raw }), ffi::NONE => None,
+                    e => { check(e, "try_new"); None }
+                }
+            }
+            #[inline] pub fn ntt_size(&self) -> usize { unsafe { ffi::ntt_b200_native_ntt_size(self.raw) } }
+            /// ntt_0() .. ntt_9() of the reference, by index (native64.rs:950-968)
+            pub fn ntt_i(&self, i: usize) -> core::mem::ManuallyDrop<crate::$prime::Plan> {
+                unsafe { crate::$prime::Plan::borrowed(ffi::ntt_b200_native_ntt_i(self.raw, i as i32) as *const _) }
+            }
+            /// e.g. native64.rs:970
+            pub fn fwd(&self, value: &[$V], $($res: &mut [$R]),+) {
+                let r = [$($res.as_mut_ptr() as *mut c_void),+];
+                check(unsafe { ffi::ntt_b200_native_fwd(self.raw, value.as_ptr() as *const c_void, value.len(), r.as_ptr(), 0) }, "fwd")
+            }
+            /// native_binary64.rs:371 (present on the binary plans only in the reference)
+            pub fn fwd_binary(&self, value: &[$V], $($res: &mut [$R]),+) {
+                assert!($binary, "fwd_binary exists on the native_binary plans only");
+                let r = [$($res.as_mut_ptr() as *mut c_void),+];
+                check(unsafe { ffi::ntt_b200_native_fwd(self.raw, value.as_ptr() as *const c_void, value.len(), r.as_ptr(), 1) }, "fwd_binary")
+            }
+            /// e.g. native64.rs:1000 — transforms (clobbers) the residue buffers like the reference
+            pub fn inv(&self, value: &mut [$V], $($res: &mut [$R]),+) {
+                let r = [$($res.as_mut_ptr() as *mut c_void),+];
+                check(unsafe { ffi::ntt_b200_native_inv(self.raw, value.as_mut_ptr() as *mut c_void, value.len(), r.as_ptr()) }, "inv")
+            }
+            /// e.g. native64.rs:1041
+            pub fn negacyclic_polymul(&self, prod: &mut [$V], lhs: &[$V], rhs: &[$V]) {
+                check(unsafe { ffi::ntt_b200_native_negacyclic_polymul(self.raw, prod.as_mut_ptr() as *mut c_void, prod.len(),
+                    lhs.as_ptr() as *const c_void, lhs.len(), rhs.as_ptr() as *const c_void, rhs.len()) }, "negacyclic_polymul")
+            }
+            /// New: `prod.len() / ntt_size()` products in one call.
+            pub fn negacyclic_polymul_batch(&self, prod: &mut [$V], lhs: &[$V], rhs: &[$V]) {
+                assert_eq!(prod.len(), lhs.len()); assert_eq!(prod.len(), rhs.len());
+                assert_eq!(prod.len() % self.ntt_size(), 0);
+                check(unsafe { ffi::ntt_b200_native_negacyclic_polymul_batch(self.raw, prod.as_mut_ptr() as *mut c_void,
+                    lhs.as_ptr() as *const c_void, rhs.as_ptr() as *const c_void, prod.len() / self.ntt_size()) }, "negacyclic_polymul_batch")
+            }
+        }
+        impl Drop for $ty { fn drop(&mut self) { unsafe { ffi::ntt_b200_native_free(self.raw) } } }
+    };
+}
+
+pub mod native32 {
+    use super::*;
+    native_plan!(native32, Plan32, 0, u32, u32, prime32, [mod_p0, mod_p1, mod_p2], false);
+    native_plan!(native32, Plan52, 1, u32, u64, prime64, [mod_p0, mod_p1], false);
+}
+pub mod native64 {
+    use super::*;
+    native_plan!(native64, Plan32, 2, u64, u32, prime32, [mod_p0, mod_p1, mod_p2, mod_p3, mod_p4], false);
+    native_plan!(native64, Plan52, 3, u64, u64, prime64, [mod_p0, mod_p1, mod_p2], false);
+}
+pub mod native128 {
+    use super::*;
+    native_plan!(native128, Plan32, 4, u128, u32, prime32,
+        [mod_p0, mod_p1, mod_p2, mod_p3, mod_p4, mod_p5, mod_p6, mod_p7, mod_p8, mod_p9], false);
+}
+pub mod native_binary32 {
+    use super::*;
+    native_plan!(native_binary32, Plan32, 5, u32, u32, prime32, [mod_p0, mod_p1], true);
+    native_plan!(native_binary32, Plan52, 6, u32, u64, prime64, [mod_p0], true);
+}
+pub mod native_binary64 {
+    use super::*;
+    native_plan!(native_binary64, Plan32, 7, u64, u32, prime32, [mod_p0, mod_p1, mod_p2], true);
+    native_plan!(native_binary64, Plan52, 8, u64, u64, prime64, [mod_p0, mod_p1], true);
+}
+pub mod native_binary128 {
+    use super::*;
+    native_plan!(native_binary128, Plan32, 9, u128, u32, prime32, [mod_p0, mod_p1, mod_p2, mod_p3, mod_p4], true);
+}

@@ -1,0 +1,84 @@
+//! `prime32::Plan` (reference: tfhe-ntt/src/prime32.rs:632-1016).
+use crate::ffi::{self, check};
+use core::ptr;
+
+
+/// Negacyclic NTT plan for 32bit primes.
+pub struct Plan { raw: *mut ffi::ntt_b200_plan32 }
+// tables are immutable after construction and every entry point is re-entrant
+unsafe impl Send for Plan {}
+unsafe impl Sync for Plan {}
+
+impl Plan {
+    /// prime32.rs:662
+    pub fn try_new(polynomial_size: usize, modulus: u32) -> Option<Self> {
+        let mut raw = ptr::null_mut();
+        match unsafe { ffi::ntt_b200_plan32_try_new(polynomial_size, modulus, &mut raw) } {
+            ffi::OK => Some(Self { raw }),
+            ffi::NONE => None,
+            e => { check(e, "prime32::Plan::try_new"); None }
+        }
+    }
+    #[inline] pub fn ntt_size(&self) -> usize { unsafe { ffi::ntt_b200_plan32_ntt_size(self.raw) } }
+    #[inline] pub fn modulus(&self) -> u32 { unsafe { ffi::ntt_b200_plan32_modulus(self.raw) } }
+    #[inline] pub fn can_use_fast_reduction_code(&self) -> bool {
+        unsafe { ffi::ntt_b200_plan32_can_use_fast_reduction_code(self.raw) != 0 }
+    }
+    /// prime32.rs:797 — standard order in, bit-reversed order out
+    pub fn fwd(&self, buf: &mut [u32]) {
+        check(unsafe { ffi::ntt_b200_plan32_fwd(self.raw, buf.as_mut_ptr(), buf.len()) }, "prime32::Plan::fwd")
+    }
+    /// prime32.rs:850
+    pub fn inv(&self, buf: &mut [u32]) {
+        check(unsafe { ffi::ntt_b200_plan32_inv(self.raw, buf.as_mut_ptr(), buf.len()) }, "prime32::Plan::inv")
+    }
+    /// prime32.rs:900
+    pub fn mul_assign_normalize(&self, lhs: &mut [u32], rhs: &[u32]) {
+        check(unsafe { ffi::ntt_b200_plan32_mul_assign_normalize(self.raw, lhs.as_mut_ptr(), lhs.len(), rhs.as_ptr(), rhs.len()) }, "mul_assign_normalize")
+    }
+    /// prime32.rs:956
+    pub fn normalize(&self, values: &mut [u32]) {
+        check(unsafe { ffi::ntt_b200_plan32_normalize(self.raw, values.as_mut_ptr(), values.len()) }, "normalize")
+    }
+    /// prime32.rs:993
+    pub fn mul_accumulate(&self, acc: &mut [u32], lhs: &[u32], rhs: &[u32]) {
+        check(unsafe { ffi::ntt_b200_plan32_mul_accumulate(self.raw, acc.as_mut_ptr(), acc.len(), lhs.as_ptr(), lhs.len(), rhs.as_ptr(), rhs.len()) }, "mul_accumulate")
+    }
+    /// New: `polys.len() / ntt_size()` transforms in one call (host memory).
+    pub fn fwd_batch(&self, polys: &mut [u32]) {
+        assert_eq!(polys.len() % self.ntt_size(), 0);
+        check(unsafe { ffi::ntt_b200_plan32_fwd_batch(self.raw, polys.as_mut_ptr(), polys.len() / self.ntt_size()) }, "fwd_batch")
+    }
+    pub fn inv_batch(&self, polys: &mut [u32]) {
+        assert_eq!(polys.len() % self.ntt_size(), 0);
+        check(unsafe { ffi::ntt_b200_plan32_inv_batch(self.raw, polys.as_mut_ptr(), polys.len() / self.ntt_size()) }, "inv_batch")
+    }
+    /// New: device-resident, asynchronous on `stream` (a `cudaStream_t`).
+    /// # Safety
+    /// `dev` must point at `batch * ntt_size()` u32 on the plan's GPU.
+    pub unsafe fn fwd_device(&self, dev: *mut u32, batch: usize, stream: *mut core::ffi::c_void) {
+        check(ffi::ntt_b200_plan32_fwd_device(self.raw, dev, batch, stream), "fwd_device")
+    }
+    /// # Safety
+    /// as [`Plan::fwd_device`]
+    pub unsafe fn inv_device(&self, dev: *mut u32, batch: usize, stream: *mut core::ffi::c_void) {
+        check(ffi::ntt_b200_plan32_inv_device(self.raw, dev, batch, stream), "inv_device")
+    }
+    pub(crate) unsafe fn borrowed(raw: *const ffi::ntt_b200_plan32) -> core::mem::ManuallyDrop<Self> {
+        core::mem::ManuallyDrop::new(Self { raw: raw as *mut _ })
+    }
+}
+impl Clone for Plan {
+    fn clone(&self) -> Self {
+        let mut raw = ptr::null_mut();
+        check(unsafe { ffi::ntt_b200_plan32_clone(self.raw, &mut raw) }, "clone");
+        Self { raw }
+    }
+}
+impl Drop for Plan { fn drop(&mut self) { unsafe { ffi::ntt_b200_plan32_free(self.raw) } } }
+impl core::fmt::Debug for Plan {
+    // prime32.rs:650-657
+    fn fmt(&self, f: &mut core::fmt::Formatter<'_>) -> core::fmt::Result {
+        f.debug_struct("Plan").field("ntt_size", &self.ntt_size()).field("modulus", &self.modulus()).finish()
+    }
+}

@@ -1,0 +1,89 @@
+//! `prime64::Plan` (reference: tfhe-ntt/src/prime64.rs:245-1223).
+use crate::ffi::{self, check};
+use core::ptr;
+
+pub const SOLINAS_PRIME: u64 = ((1u128 << 64) - (1u128 << 32) + 1) as u64;
+#[derive(Copy, Clone, Debug)]
+pub struct Solinas;
+impl Solinas { pub const P: u64 = SOLINAS_PRIME; }
+
+/// Negacyclic NTT plan for 64bit primes.
+pub struct Plan { raw: *mut ffi::ntt_b200_plan64 }
+// tables are immutable after construction and every entry point is re-entrant
+unsafe impl Send for Plan {}
+unsafe impl Sync for Plan {}
+
+impl Plan {
+    /// prime64.rs:764
+    pub fn try_new(polynomial_size: usize, modulus: u64) -> Option<Self> {
+        let mut raw = ptr::null_mut();
+        match unsafe { ffi::ntt_b200_plan64_try_new(polynomial_size, modulus, &mut raw) } {
+            ffi::OK => Some(Self { raw }),
+            ffi::NONE => None,
+            e => { check(e, "prime64::Plan::try_new"); None }
+        }
+    }
+    #[inline] pub fn ntt_size(&self) -> usize { unsafe { ffi::ntt_b200_plan64_ntt_size(self.raw) } }
+    #[inline] pub fn modulus(&self) -> u64 { unsafe { ffi::ntt_b200_plan64_modulus(self.raw) } }
+    #[inline] pub fn use_ifma(&self) -> bool { unsafe { ffi::ntt_b200_plan64_use_ifma(self.raw) != 0 } }
+    #[inline] pub fn can_use_fast_reduction_code(&self) -> bool {
+        unsafe { ffi::ntt_b200_plan64_can_use_fast_reduction_code(self.raw) != 0 }
+    }
+    /// prime64.rs:897 — standard order in, bit-reversed order out
+    pub fn fwd(&self, buf: &mut [u64]) {
+        check(unsafe { ffi::ntt_b200_plan64_fwd(self.raw, buf.as_mut_ptr(), buf.len()) }, "prime64::Plan::fwd")
+    }
+    /// prime64.rs:975
+    pub fn inv(&self, buf: &mut [u64]) {
+        check(unsafe { ffi::ntt_b200_plan64_inv(self.raw, buf.as_mut_ptr(), buf.len()) }, "prime64::Plan::inv")
+    }
+    /// prime64.rs:1050
+    pub fn mul_assign_normalize(&self, lhs: &mut [u64], rhs: &[u64]) {
+        check(unsafe { ffi::ntt_b200_plan64_mul_assign_normalize(self.raw, lhs.as_mut_ptr(), lhs.len(), rhs.as_ptr(), rhs.len()) }, "mul_assign_normalize")
+    }
+    /// prime64.rs:1137
+    pub fn normalize(&self, values: &mut [u64]) {
+        check(unsafe { ffi::ntt_b200_plan64_normalize(self.raw, values.as_mut_ptr(), values.len()) }, "normalize")
+    }
+    /// prime64.rs:1182
+    pub fn mul_accumulate(&self, acc: &mut [u64], lhs: &[u64], rhs: &[u64]) {
+        check(unsafe { ffi::ntt_b200_plan64_mul_accumulate(self.raw, acc.as_mut_ptr(), acc.len(), lhs.as_ptr(), lhs.len(), rhs.as_ptr(), rhs.len()) }, "mul_accumulate")
+    }
+    /// New: `polys.len() / ntt_size()` transforms in one call (host memory).
+    pub fn fwd_batch(&self, polys: &mut [u64]) {
+        assert_eq!(polys.len() % self.ntt_size(), 0);
+        check(unsafe { ffi::ntt_b200_plan64_fwd_batch(self.raw, polys.as_mut_ptr(), polys.len() / self.ntt_size()) }, "fwd_batch")
+    }
+    pub fn inv_batch(&self, polys: &mut [u64]) {
+        assert_eq!(polys.len() % self.ntt_size(), 0);
+        check(unsafe { ffi::ntt_b200_plan64_inv_batch(self.raw, polys.as_mut_ptr(), polys.len() / self.ntt_size()) }, "inv_batch")
+    }
+    /// New: device-resident, asynchronous on `stream` (a `cudaStream_t`).
+    /// # Safety
+    /// `dev` must point at `batch * ntt_size()` u64 on the plan's GPU.
+    pub unsafe fn fwd_device(&self, dev: *mut u64, batch: usize, stream: *mut core::ffi::c_void) {
+        check(ffi::ntt_b200_plan64_fwd_device(self.raw, dev, batch, stream), "fwd_device")
+    }
+    /// # Safety
+    /// as [`Plan::fwd_device`]
+    pub unsafe fn inv_device(&self, dev: *mut u64, batch: usize, stream: *mut core::ffi::c_void) {
+        check(ffi::ntt_b200_plan64_inv_device(self.raw, dev, batch, stream), "inv_device")
+    }
+    pub(crate) unsafe fn borrowed(raw: *const ffi::ntt_b200_plan64) -> core::mem::ManuallyDrop<Self> {
+        core::mem::ManuallyDrop::new(Self { raw: raw as *mut _ })
+    }
+}
+impl Clone for Plan {
+    fn clone(&self) -> Self {
+        let mut raw = ptr::null_mut();
+        check(unsafe { ffi::ntt_b200_plan64_clone(self.raw, &mut raw) }, "clone");
+        Self { raw }
+    }
+}
+impl Drop for Plan { fn drop(&mut self) { unsafe { ffi::ntt_b200_plan64_free(self.raw) } } }
+impl core::fmt::Debug for Plan {
+    // prime64.rs:263-270
+    fn fmt(&self, f: &mut core::fmt::Formatter<'_>) -> core::fmt::Result {
+        f.debug_struct("Plan").field("ntt_size", &self.ntt_size()).field("modulus", &self.modulus()).finish()
+    }
+}

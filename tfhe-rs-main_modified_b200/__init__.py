@@ -28,3 +28,4 @@ from ._binding import (  # noqa: F401
 from . import prime32, prime64, prime  # noqa: F401
 from . import native32, native64, native128  # noqa: F401
 from . import native_binary32, native_binary64, native_binary128  # noqa: F401
+from . import sharding  # noqa: F401

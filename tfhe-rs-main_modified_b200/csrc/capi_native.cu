@@ -464,6 +464,12 @@ int ntt_b200_native_try_new(int kind, size_t n, ntt_b200_native_plan** out) {
         pl->kind = kind;
         pl->n = n;
         pl->info = kKinds[kind];
+        // the `?` chain of e.g. native64.rs:934-940, decided on the host before any CUDA call
+        for (int j = 0; j < pl->info.num_primes; ++j) {
+            bool ok = pl->info.residue_bytes == 4 ? pm::build_twiddles(n, pm::kPrimes32[j], 32).has_value()
+                                                  : pm::build_twiddles(n, pm::kPrimes52[j], 16).has_value();
+            if (!ok) return NTT_B200_NONE;
+        }
         NTT_CUDA_CHECK(cudaGetDevice(&pl->device));
         for (int j = 0; j < pl->info.num_primes; ++j) {
             std::shared_ptr<PrimePlan> impl = pl->info.residue_bytes == 4
