@@ -56,6 +56,23 @@ __global__ void bench(uint32_t* out, uint32_t a, uint32_t b, long long* cycles) 
                 asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w) : "r"(x[i]), "r"(a));
                 x[i] = (uint32_t)w;
                 y[i] = (uint32_t)(w >> 32);
+            } else if (MODE == 10) {  // mul.wide.u32, both halves consumed (IMAD.WIDE.U32 + LOP3)
+                uint64_t w;
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x[i]), "r"(a));
+                x[i] = (uint32_t)(w >> 32) ^ (uint32_t)w;
+            } else if (MODE == 11) {  // mul.hi.u32 + LOP3 (same shape with IMAD.HI)
+                uint32_t h;
+                asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(h) : "r"(x[i]), "r"(a));
+                x[i] = h ^ y[i];
+            } else if (MODE == 12) {  // Shoup-32 product via IMAD.HI: q=hi(b*ws); t=b*w-q*p
+                uint32_t q;
+                asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(q) : "r"(x[i]), "r"(a));
+                x[i] = x[i] * b - q * y[i];
+            } else if (MODE == 13) {  // Shoup-32 product via mul.wide: (lo,hi)=b*ws; t=b*w-hi*p+ (lo&0)
+                uint64_t w;
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x[i]), "r"(a));
+                uint32_t q = (uint32_t)(w >> 32);
+                x[i] = x[i] * b - q * y[i] + ((uint32_t)w & 1u);
             } else if (MODE == 8) {  // min.u32
                 asm volatile("min.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
                 asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(a));
@@ -141,5 +158,9 @@ int main() {
     run<7>("IMAD.HI (mul.hi.u32)", 1);
     run<8>("VIMNMX + IMAD.IADD", 2);
     run<9>("IMAD.WIDE+IADD3+IMAD.X (b)", 3);
+    run<10>("IMAD.WIDE.U32 + LOP3", 2);
+    run<11>("IMAD.HI.U32 + LOP3", 2);
+    run<12>("Shoup32 via IMAD.HI (3 instr)", 3);
+    run<13>("Shoup32 via IMAD.WIDE (5 instr)", 5);
     return 0;
 }

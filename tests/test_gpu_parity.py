@@ -203,6 +203,29 @@ def test_device_api_and_fused(T):
     assert (d_n.cpu().numpy().view(np.uint64).ravel() == op.normalize(want.ravel())).all()
 
 
+def test_fwd_mac_inv_batch_host(T):
+    n, p = 1024, SOLINAS_P
+    gp, op = plan_pair(T, 64, n, p)
+    rng = np.random.default_rng(9)
+    batch = 9000  # > one staging chunk (32 MiB / 8 KiB = 4096 polynomials), ragged tail
+    lhs = rand_below(rng, p, (batch, n), np.uint64)
+    ggsw = rand_below(rng, p, (4, n), np.uint64)
+    acc = rand_below(rng, p, (2, n), np.uint64)
+    out = np.zeros_like(lhs)
+    gp.fwd_mac_inv_batch(out, lhs, ggsw, acc)
+    for b in (0, 1, 4095, 4096, 4097, 8999):
+        want = op.inv(op.mul_accumulate(acc[b % 2], op.fwd(lhs[b]), ggsw[b % 4]))
+        assert (out[b] == want).all(), b
+    # full-size operands, in place
+    rhs = rand_below(rng, p, (64, n), np.uint64)
+    x = lhs[:64].copy()
+    gp.fwd_mac_inv_batch(x, x, rhs)
+    want = op.inv(op.mul_accumulate(np.zeros_like(rhs), op.fwd(lhs[:64]), rhs))
+    assert (x == want).all()
+    with pytest.raises(AssertionError):
+        gp.fwd_mac_inv_batch(out, lhs, np.ascontiguousarray(lhs[:7]))  # 9000 % 7 != 0
+
+
 def rand_values(rng, value_bytes, shape, binary=False):
     n = int(np.prod(shape))
     if binary:

@@ -90,6 +90,19 @@ class PrimePlanBase:
     def inv_batch(self, buf):
         B.check(self._f("inv_batch")(self._h, B.host_ptr(buf, self._dtype, True), self._batch(buf)))
 
+    def fwd_mac_inv_batch(self, out, lhs, rhs, acc=None):
+        """out = inv(acc + fwd(lhs) * rhs) on host arrays; rhs / acc may hold fewer polynomials
+        than lhs (reused cyclically).  out may be lhs."""
+        n = self.ntt_size()
+        batch = self._batch(lhs)
+        if out.size != lhs.size:
+            raise AssertionError("length mismatch: out and lhs differ")
+        B.check(self._f("fwd_mac_inv_batch")(
+            self._h, B.host_ptr(out, self._dtype, True), B.host_ptr(lhs, self._dtype),
+            B.host_ptr(rhs, self._dtype), rhs.size // n,
+            None if acc is None else B.host_ptr(acc, self._dtype), 0 if acc is None else acc.size // n, batch),
+            "in fwd_mac_inv_batch")
+
     # device-resident calls
     def _eb(self):
         return np.dtype(self._dtype).itemsize

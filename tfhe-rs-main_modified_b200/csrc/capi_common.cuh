@@ -31,4 +31,18 @@ int guarded(F&& f) {
         return NTT_B200_ERR_CUDA;
     }
 }
+
+// Stream-ordered allocations of the host-pointer entry points come from the device's default
+// memory pool; keep freed blocks cached in the pool (the default threshold of 0 hands them back
+// to the driver at every synchronisation, which costs milliseconds per staging buffer).
+inline void keep_pool_cached(int device) {
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[device] = true;
+}
 }  // namespace nttb200

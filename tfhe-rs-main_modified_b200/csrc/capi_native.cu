@@ -386,6 +386,7 @@ struct ntt_b200_native_plan {
     // sized to stay L2-resident (chunks of the batch), so they never travel to HBM and back.
     void polymul_dev(void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st) const {
         if (!batch) return;
+        keep_pool_cached(device);
         const size_t rb = (size_t)info.residue_bytes, vb = (size_t)info.value_bytes;
         const int np = info.num_primes;
         size_t per_poly = 2 * (size_t)np * n * rb;
@@ -419,7 +420,12 @@ namespace {
 struct HostStage {
     cudaStream_t st = nullptr;
     std::vector<void*> bufs;
-    HostStage() { NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); }
+    HostStage() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        keep_pool_cached(dev);
+        NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    }
     void* alloc(size_t bytes) {
         void* d = nullptr;
         NTT_CUDA_CHECK(cudaMallocAsync(&d, std::max<size_t>(bytes, 16), st));

@@ -57,6 +57,7 @@ int host_transform(const PrimePlan* pl, void* host, size_t batch, bool inverse) 
     return guarded([&] {
         if (!batch) return NTT_B200_OK;
         DeviceGuard g(pl->device);
+        keep_pool_cached(pl->device);
         size_t poly_bytes = pl->n * (size_t)pl->elem_bytes;
         size_t chunk_polys = std::max<size_t>(1, kChunkBytes / poly_bytes);
         chunk_polys = std::min(chunk_polys, batch);
@@ -96,6 +97,7 @@ int host_pointwise(const PrimePlan* pl, int op, void* dst, size_t len, const voi
     return guarded([&] {
         if (!len) return NTT_B200_OK;
         DeviceGuard g(pl->device);
+        keep_pool_cached(pl->device);
         size_t eb = (size_t)pl->elem_bytes;
         cudaStream_t st;
         NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -117,6 +119,106 @@ int host_pointwise(const PrimePlan* pl, int op, void* dst, size_t len, const voi
         cudaError_t e = cudaStreamSynchronize(st);
         cudaStreamDestroy(st);
         NTT_CUDA_CHECK(e);
+        return NTT_B200_OK;
+    });
+}
+
+// out = inv(acc + fwd(lhs) * rhs) for host operands, chunked and pipelined on three streams
+int host_fwd_mac_inv(const PrimePlan* pl, void* out, const void* lhs, const void* rhs, size_t rhs_polys,
+                     const void* acc, size_t acc_polys, size_t batch) {
+    return guarded([&] {
+        if (!batch) return NTT_B200_OK;
+        DeviceGuard g(pl->device);
+        keep_pool_cached(pl->device);
+        const size_t pb = pl->n * (size_t)pl->elem_bytes;
+        const bool rhs_shared = rhs_polys < batch, acc_shared = acc && acc_polys < batch;
+        // chunk boundaries must fall on multiples of the shared operands' periods
+        size_t period = 1;
+        if (rhs_shared) period = rhs_polys;
+        if (acc_shared) {
+            size_t a = period, b = acc_polys;
+            while (b) {
+                size_t t = a % b;
+                a = b;
+                b = t;
+            }
+            period = period / a * acc_polys;
+        }
+        size_t chunk = std::max<size_t>(1, kChunkBytes / pb);
+        chunk = std::max(period, chunk / period * period);
+        chunk = std::min(chunk, batch);
+        size_t nchunks = (batch + chunk - 1) / chunk;
+        int ns = (int)std::min<size_t>(3, nchunks);
+        cudaStream_t st[3] = {};
+        void *d_io[3] = {}, *d_rhs[3] = {}, *d_acc[3] = {};
+        void *d_rhs_shared = nullptr, *d_acc_shared = nullptr;
+        cudaEvent_t shared_ready = nullptr;
+        for (int i = 0; i < ns; ++i) {
+            NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+            NTT_CUDA_CHECK(cudaMallocAsync(&d_io[i], chunk * pb, st[i]));
+            if (!rhs_shared) NTT_CUDA_CHECK(cudaMallocAsync(&d_rhs[i], chunk * pb, st[i]));
+            if (acc && !acc_shared) NTT_CUDA_CHECK(cudaMallocAsync(&d_acc[i], chunk * pb, st[i]));
+        }
+        if (rhs_shared || acc_shared) {
+            NTT_CUDA_CHECK(cudaEventCreateWithFlags(&shared_ready, cudaEventDisableTiming));
+            if (rhs_shared) {
+                NTT_CUDA_CHECK(cudaMallocAsync(&d_rhs_shared, rhs_polys * pb, st[0]));
+                NTT_CUDA_CHECK(cudaMemcpyAsync(d_rhs_shared, rhs, rhs_polys * pb, cudaMemcpyHostToDevice, st[0]));
+            }
+            if (acc_shared) {
+                NTT_CUDA_CHECK(cudaMallocAsync(&d_acc_shared, acc_polys * pb, st[0]));
+                NTT_CUDA_CHECK(cudaMemcpyAsync(d_acc_shared, acc, acc_polys * pb, cudaMemcpyHostToDevice, st[0]));
+            }
+            NTT_CUDA_CHECK(cudaEventRecord(shared_ready, st[0]));
+            for (int i = 1; i < ns; ++i) NTT_CUDA_CHECK(cudaStreamWaitEvent(st[i], shared_ready, 0));
+        }
+        for (size_t c = 0; c < nchunks; ++c) {
+            int i = (int)(c % ns);
+            size_t b0 = c * chunk, nb = std::min(chunk, batch - b0);
+            const char* hl = static_cast<const char*>(lhs) + b0 * pb;
+            char* ho = static_cast<char*>(out) + b0 * pb;
+            NTT_CUDA_CHECK(cudaMemcpyAsync(d_io[i], hl, nb * pb, cudaMemcpyHostToDevice, st[i]));
+            const void* r = d_rhs_shared;
+            size_t rp = rhs_polys;
+            if (!rhs_shared) {
+                NTT_CUDA_CHECK(cudaMemcpyAsync(d_rhs[i], static_cast<const char*>(rhs) + b0 * pb, nb * pb,
+                                               cudaMemcpyHostToDevice, st[i]));
+                r = d_rhs[i];
+                rp = nb;
+            }
+            const void* a = nullptr;
+            size_t ap = 0;
+            if (acc) {
+                a = d_acc_shared;
+                ap = acc_polys;
+                if (!acc_shared) {
+                    NTT_CUDA_CHECK(cudaMemcpyAsync(d_acc[i], static_cast<const char*>(acc) + b0 * pb, nb * pb,
+                                                   cudaMemcpyHostToDevice, st[i]));
+                    a = d_acc[i];
+                    ap = nb;
+                }
+            }
+            pl->fwd_mac_inv(d_io[i], d_io[i], r, rp, a, ap, nb, st[i]);
+            NTT_CUDA_CHECK(cudaMemcpyAsync(ho, d_io[i], nb * pb, cudaMemcpyDeviceToHost, st[i]));
+        }
+        cudaError_t first = cudaSuccess;
+        for (int i = 0; i < ns; ++i) {
+            cudaError_t e = cudaStreamSynchronize(st[i]);
+            if (first == cudaSuccess) first = e;
+        }
+        for (int i = 0; i < ns; ++i) {
+            cudaFreeAsync(d_io[i], st[i]);
+            if (d_rhs[i]) cudaFreeAsync(d_rhs[i], st[i]);
+            if (d_acc[i]) cudaFreeAsync(d_acc[i], st[i]);
+        }
+        if (d_rhs_shared) cudaFreeAsync(d_rhs_shared, st[0]);
+        if (d_acc_shared) cudaFreeAsync(d_acc_shared, st[0]);
+        for (int i = 0; i < ns; ++i) {
+            cudaStreamSynchronize(st[i]);
+            cudaStreamDestroy(st[i]);
+        }
+        if (shared_ready) cudaEventDestroy(shared_ready);
+        NTT_CUDA_CHECK(first);
         return NTT_B200_OK;
     });
 }
@@ -260,6 +362,21 @@ int dev_pointwise_check(size_t len, size_t sub_len) {
         });                                                                                        \
     }                                                                                              \
     }
+
+#define NTT_DEFINE_FMI_BATCH(SFX, ELEM)                                                            \
+    extern "C" int ntt_b200_plan##SFX##_fwd_mac_inv_batch(                                         \
+        const ntt_b200_plan##SFX* plan, ELEM* out, const ELEM* lhs, const ELEM* rhs,               \
+        size_t rhs_polys, const ELEM* acc, size_t acc_polys, size_t batch) {                       \
+        if (!plan) return NTT_B200_ERR_ARG;                                                        \
+        if (!batch) return NTT_B200_OK;                                                            \
+        if (!out || !lhs || !rhs) return NTT_B200_ERR_ARG;                                         \
+        if (rhs_polys == 0 || rhs_polys > batch || batch % rhs_polys) return NTT_B200_ERR_LEN;     \
+        if (acc && (acc_polys == 0 || acc_polys > batch || batch % acc_polys))                     \
+            return NTT_B200_ERR_LEN;                                                               \
+        return host_fwd_mac_inv(plan->impl.get(), out, lhs, rhs, rhs_polys, acc, acc_polys, batch);\
+    }
+NTT_DEFINE_FMI_BATCH(64, uint64_t)
+NTT_DEFINE_FMI_BATCH(32, uint32_t)
 
 NTT_DEFINE_PRIME_API(64, uint64_t, make_plan64)
 NTT_DEFINE_PRIME_API(32, uint32_t, make_plan32)

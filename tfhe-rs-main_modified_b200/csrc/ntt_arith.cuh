@@ -78,7 +78,7 @@ struct Shoup {
             b = z0 - t + c.p;
         }
     }
-    NTT_DEVINL static void inv_bf(const Ctx& c, T& a, T& b, TW w) {
+    NTT_DEVINL static void inv_bf(const Ctx& c, T& a, T& b, TW w, bool /*b_canonical*/ = false) {
         if (HARVEY) {  // [0,2p) -> [0,2p)
             T y0 = csub(a + b, c.two_p);
             T t = a - b + c.two_p;
@@ -96,6 +96,7 @@ struct Shoup {
         return csub(a, c.p);
     }
     NTT_DEVINL static T inv_fin(const Ctx& c, T a) { return HARVEY ? csub(a, c.p) : a; }
+    NTT_DEVINL static T inv_fin_prod(const Ctx& c, T a) { return inv_fin(c, a); }
     // multiply by a plan constant given as a Shoup pair, canonical result (used by normalize)
     NTT_DEVINL static T mul_const(const Ctx& c, T a, TW w) { return csub(mul_lazy(c, a, w), c.p); }
 
@@ -162,13 +163,14 @@ struct Wide32 {
         a = add_full(c, z0, t);
         b = sub_full(c, z0, t);
     }
-    NTT_DEVINL static void inv_bf(const Ctx& c, T& a, T& b, TW w) {
+    NTT_DEVINL static void inv_bf(const Ctx& c, T& a, T& b, TW w, bool /*b_canonical*/ = false) {
         T s = add_full(c, a, b), d = sub_full(c, a, b);
         a = s;
         b = mul_exact(c, d, w);
     }
     NTT_DEVINL static T fwd_fin(const Ctx&, T a) { return a; }
     NTT_DEVINL static T inv_fin(const Ctx&, T a) { return a; }
+    NTT_DEVINL static T inv_fin_prod(const Ctx&, T a) { return a; }
     NTT_DEVINL static T mul_const(const Ctx& c, T a, TW w) { return mul_exact(c, a, w); }
     NTT_DEVINL static T mul_full(const Ctx& c, T a, T b) {
         return barrett32((uint64_t)a * b, c.p, c.barrett64);
@@ -259,13 +261,15 @@ struct Solinas64 {
         b = sub_lazy(z0, t);
     }
     // Gentleman-Sande: both inputs may be arbitrary representatives, so bring b into [0,p) first
-    NTT_DEVINL static void inv_bf(const Ctx&, T& a, T& b, TW w) {
-        T bc = canon(b), z0 = a;
+    // unless the caller knows it already is (b is the product output of the previous stage).
+    NTT_DEVINL static void inv_bf(const Ctx&, T& a, T& b, TW w, bool b_canonical = false) {
+        T bc = b_canonical ? b : canon(b), z0 = a;
         a = add_lazy(z0, bc);
         b = mulm(sub_lazy(z0, bc), w);
     }
     NTT_DEVINL static T fwd_fin(const Ctx&, T a) { return canon(a); }
     NTT_DEVINL static T inv_fin(const Ctx&, T a) { return canon(a); }
+    NTT_DEVINL static T inv_fin_prod(const Ctx&, T a) { return a; }  // mulm output is canonical
     NTT_DEVINL static T mul_const(const Ctx&, T a, TW wm) { return mulm(a, wm); }
     NTT_DEVINL static T add_full(const Ctx&, T a, T b) { return canon(add_lazy(a, b)); }
     NTT_DEVINL static T mul_full(const Ctx&, T a, T b) { return mul_plain(a, b); }
@@ -295,13 +299,14 @@ struct Mont64 {
         a = add_full(c, z0, t);
         b = sub_full(c, z0, t);
     }
-    NTT_DEVINL static void inv_bf(const Ctx& c, T& a, T& b, TW w) {
+    NTT_DEVINL static void inv_bf(const Ctx& c, T& a, T& b, TW w, bool /*b_canonical*/ = false) {
         T s = add_full(c, a, b), d = sub_full(c, a, b);
         a = s;
         b = mul_exact(c, d, w);
     }
     NTT_DEVINL static T fwd_fin(const Ctx&, T a) { return a; }
     NTT_DEVINL static T inv_fin(const Ctx&, T a) { return a; }
+    NTT_DEVINL static T inv_fin_prod(const Ctx&, T a) { return a; }
     NTT_DEVINL static T mul_const(const Ctx& c, T a, TW wm) { return mul_exact(c, a, wm); }
     NTT_DEVINL static T mul_full(const Ctx& c, T a, T b) {
         uint64_t x = redc64(a * b, __umul64hi(a, b), c.p, c.pinv);

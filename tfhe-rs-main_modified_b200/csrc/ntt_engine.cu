@@ -197,35 +197,52 @@ struct PlanImpl final : PrimePlan {
         if (r == 1) launch_global<INV, 1>(data, batch, stage, finalize, st);
         if (r == 2) launch_global<INV, 2>(data, batch, stage, finalize, st);
         if (r == 3) launch_global<INV, 3>(data, batch, stage, finalize, st);
+        if (r == 4) launch_global<INV, 4>(data, batch, stage, finalize, st);
+    }
+
+    // Longest polynomial the fast single-CTA kernels take; longer ones first run their top
+    // `logn - kFastMaxLog` stages as strided global-memory passes (<= 4 stages per pass).
+    static constexpr int kFastMaxLog = 12, kFastMinLog = 8;
+    static std::vector<std::pair<int, int>> global_groups(int depth) {
+        std::vector<std::pair<int, int>> g;  // (first stage, number of stages)
+        for (int s = 0; s < depth;) {
+            int r = std::min(4, depth - s);
+            if (depth - s == 5) r = 3;  // 3+2 rather than 4+1
+            g.push_back({s, r});
+            s += r;
+        }
+        return g;
     }
 
     void fwd(void* data, size_t batch, cudaStream_t st) const override {
         if (!batch) return;
         DeviceGuard g(device);
         T* d = static_cast<T*>(data);
-        if (aligned16(d) && fast_fwd<A>(d, batch, logn, d_fwd.get(), ctx, st)) return;
-        int depth = std::max(0, logn - kMaxLogRow);
-        for (int s = 0; s < depth;) {  // top stages in global memory, 3 at a time
-            int r = std::min(3, depth - s);
-            launch_global_r<false>(r, d, batch, s, 0, st);
-            s += r;
+        const bool fast_ok = aligned16(d) && logn >= kFastMinLog;
+        if (fast_ok) {
+            int depth = std::max(0, logn - kFastMaxLog);
+            for (auto [s, r] : global_groups(depth)) launch_global_r<false>(r, d, batch, s, 0, st);
+            if (fast_fwd<A>(d, batch << depth, logn - depth, (unsigned)depth, d_fwd.get(), ctx, st)) return;
         }
+        // small or unaligned: generic rows kernel (n <= 2^14 / 2^15 in one CTA)
+        int depth = std::max(0, logn - kMaxLogRow);
+        for (auto [s, r] : global_groups(depth)) launch_global_r<false>(r, d, batch, s, 0, st);
         launch_rows<false>(d, batch << depth, logn - depth, depth, 1, st);
     }
     void inv(void* data, size_t batch, cudaStream_t st) const override {
         if (!batch) return;
         DeviceGuard g(device);
         T* d = static_cast<T*>(data);
-        if (aligned16(d) && fast_inv<A>(d, batch, logn, d_inv.get(), ctx, st)) return;
-        int depth = std::max(0, logn - kMaxLogRow);
-        launch_rows<true>(d, batch << depth, logn - depth, depth, depth == 0, st);
-        // mirror of fwd: the same stage groups in reverse order
-        std::vector<std::pair<int, int>> groups;
-        for (int s = 0; s < depth;) {
-            int r = std::min(3, depth - s);
-            groups.push_back({s, r});
-            s += r;
+        const bool fast_ok = aligned16(d) && logn >= kFastMinLog;
+        int depth = std::max(0, logn - (fast_ok ? kFastMaxLog : kMaxLogRow));
+        if (fast_ok) {
+            bool ok = fast_inv<A>(d, batch << depth, logn - depth, (unsigned)depth, d_inv.get(), ctx, st);
+            if (!ok) throw CudaError("no fast inverse kernel for this size");
+        } else {
+            launch_rows<true>(d, batch << depth, logn - depth, depth, depth == 0, st);
         }
+        // mirror of fwd: the same stage groups in reverse order, the last one canonicalises
+        auto groups = global_groups(depth);
         for (size_t k = groups.size(); k-- > 0;)
             launch_global_r<true>(groups[k].second, d, batch, groups[k].first, k == 0, st);
     }

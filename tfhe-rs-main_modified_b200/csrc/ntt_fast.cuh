@@ -1,6 +1,7 @@
 // Fast single-CTA NTT kernels with compile-time size (2^8 .. 2^12 coefficients).
 //
-// One thread owns 8 coefficients; a polynomial is N/8 threads.  The log2(N) radix-2 stages of
+// One thread owns 8 coefficients of each of PPT (1 or 2) polynomials; a polynomial is N/8 threads.
+// Two polynomials per thread share every twiddle load and all index arithmetic.  The log2(N) radix-2 stages of
 // the reference (generic_solinas.rs:449-514 / shoup.rs:544-615) are executed as
 //   [radix-8 register passes over strides N/8, N/64, ...]  +  [a last pass over 8 consecutive
 //   coefficients holding the remaining 1..3 stages]
@@ -15,6 +16,15 @@
 #include "ntt_kernels.cuh"
 
 namespace nttb200 {
+
+// A "row" handled by one thread group may be one of the 2^depth contiguous sub-blocks of a longer
+// polynomial whose first `depth` stages ran in global memory (the reference's depth-first
+// recursion, generic_solinas.rs:1338-1386): its stage with 2^s groups then reads
+// twid[(2^s << depth) + half * 2^s + i].  depth = 0 is the plain case.
+struct SubPoly {
+    unsigned depth, half;
+    NTT_DEVINL unsigned base(int stage) const { return ((1u << stage) << depth) + (half << stage); }
+};
 
 template <int LOGN>
 struct FastShape {
@@ -47,10 +57,15 @@ NTT_DEVINL ShoupTw<uint64_t> ldg_tw(const ShoupTw<uint64_t>* p) {
     return ShoupTw<uint64_t>{v.x, v.y};
 }
 
-// radix-2^R butterflies on x[OFF .. OFF + 2^R) with twiddles fetched through the read-only path
-template <class A, int R, int OFF, bool INV>
-NTT_DEVINL void tuple_ro(typename A::T (&x)[8], const typename A::TW* __restrict__ tw, unsigned w0,
-                         const typename A::Ctx& c) {
+// radix-2^R butterflies on x[.][OFF .. OFF + 2^R) with twiddles fetched through the read-only
+// path.  PPT polynomials per thread share every twiddle load and all index arithmetic.
+// ENTRY_CANON (inverse only): the tuple's inputs are known canonical.  Within the tuple the
+// Gentleman-Sande stage of distance d leaves sums at positions with bit d clear and canonical
+// products at positions with bit d set, so which inputs of the next stage are canonical is
+// static.
+template <class A, int R, int OFF, bool INV, bool ENTRY_CANON, int PPT>
+NTT_DEVINL void tuple_ro(typename A::T (&x)[PPT][8], const typename A::TW* __restrict__ tw,
+                         unsigned w0, const typename A::Ctx& c) {
     if (!INV) {
 #pragma unroll
         for (int q = 0; q < R; ++q) {
@@ -60,7 +75,9 @@ NTT_DEVINL void tuple_ro(typename A::T (&x)[8], const typename A::TW* __restrict
                 typename A::TW w = ldg_tw(tw + ((w0 << q) + h));
 #pragma unroll
                 for (int k = 0; k < d; ++k)
-                    A::fwd_bf(c, x[OFF + h * 2 * d + k], x[OFF + h * 2 * d + k + d], w);
+#pragma unroll
+                    for (int pp = 0; pp < PPT; ++pp)
+                        A::fwd_bf(c, x[pp][OFF + h * 2 * d + k], x[pp][OFF + h * 2 * d + k + d], w);
             }
         }
     } else {
@@ -71,8 +88,13 @@ NTT_DEVINL void tuple_ro(typename A::T (&x)[8], const typename A::TW* __restrict
             for (int h = 0; h < (1 << q); ++h) {
                 typename A::TW w = ldg_tw(tw + ((w0 << q) + h));
 #pragma unroll
-                for (int k = 0; k < d; ++k)
-                    A::inv_bf(c, x[OFF + h * 2 * d + k], x[OFF + h * 2 * d + k + d], w);
+                for (int k = 0; k < d; ++k) {
+                    const int jb = h * 2 * d + k + d;  // position of b inside the tuple
+                    const bool b_canon = (d == 1) ? ENTRY_CANON : ((jb & (d >> 1)) != 0);
+#pragma unroll
+                    for (int pp = 0; pp < PPT; ++pp)
+                        A::inv_bf(c, x[pp][OFF + h * 2 * d + k], x[pp][OFF + jb], w, b_canon);
+                }
             }
         }
     }
@@ -80,25 +102,26 @@ NTT_DEVINL void tuple_ro(typename A::T (&x)[8], const typename A::TW* __restrict
 
 // The "last" pass: 8 consecutive coefficients 8u .. 8u+7 of the polynomial, stages
 // [LOGN - S, LOGN).  S = 3: one radix-8 tuple; S = 2: two radix-4 tuples; S = 1: four radix-2.
-template <class A, int LOGN, bool INV>
-NTT_DEVINL void last_pass(typename A::T (&x)[8], const typename A::TW* __restrict__ tw, unsigned u,
-                          const typename A::Ctx& c) {
+// `sub` locates this polynomial inside a longer one (see SubPoly).
+template <class A, int LOGN, bool INV, bool ENTRY_CANON, int PPT>
+NTT_DEVINL void last_pass(typename A::T (&x)[PPT][8], const typename A::TW* __restrict__ tw,
+                          unsigned u, const typename A::Ctx& c, const SubPoly& sub) {
     constexpr int S = FastShape<LOGN>::kLastStages;
-    constexpr unsigned m = 1u << (LOGN - S);  // groups in the first fused stage
+    const unsigned m = sub.base(LOGN - S);  // table index of group 0 of the first fused stage
     if (S == 3) {
-        tuple_ro<A, 3, 0, INV>(x, tw, m + u, c);
+        tuple_ro<A, 3, 0, INV, ENTRY_CANON, PPT>(x, tw, m + u, c);
     } else if (S == 2) {
-        tuple_ro<A, 2, 0, INV>(x, tw, m + 2 * u, c);
-        tuple_ro<A, 2, 4, INV>(x, tw, m + 2 * u + 1, c);
+        tuple_ro<A, 2, 0, INV, ENTRY_CANON, PPT>(x, tw, m + 2 * u, c);
+        tuple_ro<A, 2, 4, INV, ENTRY_CANON, PPT>(x, tw, m + 2 * u + 1, c);
     } else {
-        tuple_ro<A, 1, 0, INV>(x, tw, m + 4 * u, c);
-        tuple_ro<A, 1, 2, INV>(x, tw, m + 4 * u + 1, c);
-        tuple_ro<A, 1, 4, INV>(x, tw, m + 4 * u + 2, c);
-        tuple_ro<A, 1, 6, INV>(x, tw, m + 4 * u + 3, c);
+        tuple_ro<A, 1, 0, INV, ENTRY_CANON, PPT>(x, tw, m + 4 * u, c);
+        tuple_ro<A, 1, 2, INV, ENTRY_CANON, PPT>(x, tw, m + 4 * u + 1, c);
+        tuple_ro<A, 1, 4, INV, ENTRY_CANON, PPT>(x, tw, m + 4 * u + 2, c);
+        tuple_ro<A, 1, 6, INV, ENTRY_CANON, PPT>(x, tw, m + 4 * u + 3, c);
     }
 }
 
-// 8 consecutive elements <-> global memory with 128-bit accesses
+// 8 consecutive elements <-> memory with 128-bit accesses
 template <class T>
 NTT_DEVINL void load8_consecutive(const T* __restrict__ g, T (&x)[8]) {
     if (sizeof(T) == 8) {
@@ -133,24 +156,17 @@ NTT_DEVINL void store8_consecutive(T* __restrict__ g, const T (&x)[8]) {
         for (int k = 0; k < 2; ++k) v[k] = make_uint4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
     }
 }
-// 8 consecutive elements <-> padded shared memory (never straddles a padding gap: 8 | 16)
-template <class T>
-NTT_DEVINL void lds8(const T* s, unsigned u, T (&x)[8]) {
-    load8_consecutive(s + pad_index<T>(8 * u), x);
-}
-template <class T>
-NTT_DEVINL void sts8(T* s, unsigned u, const T (&x)[8]) {
-    store8_consecutive(s + pad_index<T>(8 * u), x);
-}
 
-// Core transform of one polynomial by N/8 cooperating threads.  `t` = thread index within the
-// polynomial, `s` = this polynomial's padded shared-memory tile.  Within a pass every thread
-// loads and stores the same 8 positions, so one CTA barrier per pass is enough.
-template <class A, int LOGN>
-NTT_DEVINL void fwd_from_regs(typename A::T (&x)[8], typename A::T* s, unsigned t,
-                              const typename A::TW* __restrict__ tw, const typename A::Ctx& c) {
+// Core transform of PPT polynomials by N/8 cooperating threads.  `t` = thread index within the
+// polynomial, `s` = padded shared-memory tiles (PPT consecutive tiles of kPaddedElems).  Within a
+// pass every thread loads and stores the same 8 positions, so one CTA barrier per pass is enough.
+template <class A, int LOGN, int PPT>
+NTT_DEVINL void fwd_from_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsigned t,
+                              const typename A::TW* __restrict__ tw, const typename A::Ctx& c,
+                              const SubPoly& sub) {
     // on entry x holds elements t + k*(N/8): exactly the first radix-8 tuple (stages 0..2)
     using S = FastShape<LOGN>;
+    using T = typename A::T;
 #pragma unroll
     for (int pass = 0; pass < S::kRadix8Passes; ++pass) {
         const int stage = 3 * pass;
@@ -159,24 +175,37 @@ NTT_DEVINL void fwd_from_regs(typename A::T (&x)[8], typename A::T* s, unsigned 
         unsigned base = (i << (log_t2 + 3)) + j;
         if (pass > 0) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = s[pad_index<typename A::T>(base + ((unsigned)k << log_t2))];
-        }
-        tuple_ro<A, 3, 0, false>(x, tw, (1u << stage) + i, c);
+            for (int k = 0; k < 8; ++k) {
+                unsigned off = pad_index<T>(base + ((unsigned)k << log_t2));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s[pad_index<typename A::T>(base + ((unsigned)k << log_t2))] = x[k];
+                for (int pp = 0; pp < PPT; ++pp) x[pp][k] = s[pp * S::kPaddedElems + off];
+            }
+        }
+        tuple_ro<A, 3, 0, false, false, PPT>(x, tw, sub.base(stage) + i, c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            unsigned off = pad_index<T>(base + ((unsigned)k << log_t2));
+#pragma unroll
+            for (int pp = 0; pp < PPT; ++pp) s[pp * S::kPaddedElems + off] = x[pp][k];
+        }
         __syncthreads();
     }
-    lds8(s, t, x);
-    last_pass<A, LOGN, false>(x, tw, t, c);
+#pragma unroll
+    for (int pp = 0; pp < PPT; ++pp) load8_consecutive(s + pp * S::kPaddedElems + pad_index<T>(8 * t), x[pp]);
+    last_pass<A, LOGN, false, false, PPT>(x, tw, t, c, sub);
 }
 
-// inverse: x holds 8 consecutive elements 8t..8t+7 on entry, elements t + k*(N/8) on exit
-template <class A, int LOGN>
-NTT_DEVINL void inv_to_regs(typename A::T (&x)[8], typename A::T* s, unsigned t,
-                            const typename A::TW* __restrict__ tw, const typename A::Ctx& c) {
+// inverse: x holds 8 consecutive elements 8t..8t+7 on entry (canonical: fresh input or the
+// output of a pointwise product), elements t + k*(N/8) on exit
+template <class A, int LOGN, int PPT>
+NTT_DEVINL void inv_to_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsigned t,
+                            const typename A::TW* __restrict__ tw, const typename A::Ctx& c,
+                            const SubPoly& sub) {
     using S = FastShape<LOGN>;
-    last_pass<A, LOGN, true>(x, tw, t, c);
-    sts8(s, t, x);
+    using T = typename A::T;
+    last_pass<A, LOGN, true, true, PPT>(x, tw, t, c, sub);
+#pragma unroll
+    for (int pp = 0; pp < PPT; ++pp) store8_consecutive(s + pp * S::kPaddedElems + pad_index<T>(8 * t), x[pp]);
 #pragma unroll
     for (int pass = S::kRadix8Passes - 1; pass >= 0; --pass) {
         const int stage = 3 * pass;
@@ -185,65 +214,98 @@ NTT_DEVINL void inv_to_regs(typename A::T (&x)[8], typename A::T* s, unsigned t,
         unsigned base = (i << (log_t2 + 3)) + j;
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = s[pad_index<typename A::T>(base + ((unsigned)k << log_t2))];
-        tuple_ro<A, 3, 0, true>(x, tw, (1u << stage) + i, c);
+        for (int k = 0; k < 8; ++k) {
+            unsigned off = pad_index<T>(base + ((unsigned)k << log_t2));
+#pragma unroll
+            for (int pp = 0; pp < PPT; ++pp) x[pp][k] = s[pp * S::kPaddedElems + off];
+        }
+        tuple_ro<A, 3, 0, true, false, PPT>(x, tw, sub.base(stage) + i, c);
         if (pass > 0) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s[pad_index<typename A::T>(base + ((unsigned)k << log_t2))] = x[k];
+            for (int k = 0; k < 8; ++k) {
+                unsigned off = pad_index<T>(base + ((unsigned)k << log_t2));
+#pragma unroll
+                for (int pp = 0; pp < PPT; ++pp) s[pp * S::kPaddedElems + off] = x[pp][k];
+            }
         }
     }
 }
 
 // ---- kernels ------------------------------------------------------------------------------
-// blockDim = (N/8, POLYS): POLYS polynomials per CTA (more than one only for small N).
-template <class A, int LOGN, int POLYS>
+// blockDim = (N/8, POLYS); each thread group works on PPT rows at once, so a CTA covers
+// POLYS*PPT rows.  `rows` counts rows of length N; with depth > 0 row r is sub-block
+// (r mod 2^depth) of polynomial r >> depth (PPT must be 1 then: the rows of a group would need
+// different twiddles).  Out-of-range rows are clamped and not stored (whole-CTA barriers inside).
+template <class A, int LOGN, int POLYS, int PPT>
 __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS)
-    ntt_fast_fwd_kernel(typename A::T* __restrict__ data, size_t batch,
+    ntt_fast_fwd_kernel(typename A::T* __restrict__ data, size_t rows, unsigned depth,
                         const typename A::TW* __restrict__ tw, typename A::Ctx c) {
     using T = typename A::T;
     using S = FastShape<LOGN>;
-    __shared__ __align__(16) T smem[POLYS * S::kPaddedElems];
+    __shared__ __align__(16) T smem[POLYS * PPT * S::kPaddedElems];
     const unsigned t = threadIdx.x;
-    size_t poly = (size_t)blockIdx.x * POLYS + threadIdx.y;
-    // whole-CTA barriers below: out-of-range polynomials run on a clamped index and skip the store
-    const bool live = poly < batch;
-    if (!live) poly = batch - 1;
-    T* g = data + (poly << LOGN);
-    T* s = smem + threadIdx.y * S::kPaddedElems;
-    T x[8];
+    const size_t row0 = ((size_t)blockIdx.x * POLYS + threadIdx.y) * PPT;
+    const SubPoly sub{depth, (unsigned)row0 & ((1u << depth) - 1u)};
+    T* s = smem + threadIdx.y * PPT * S::kPaddedElems;
+    T x[PPT][8];
+    T* g[PPT];
+    bool live[PPT];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = g[t + k * S::kThreadsPerPoly];
-    fwd_from_regs<A, LOGN>(x, s, t, tw, c);
+    for (int pp = 0; pp < PPT; ++pp) {
+        size_t row = row0 + pp;
+        live[pp] = row < rows;
+        g[pp] = data + ((live[pp] ? row : rows - 1) << LOGN);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = A::fwd_fin(c, x[k]);
-    if (live) store8_consecutive(g + 8 * t, x);
+        for (int k = 0; k < 8; ++k) x[pp][k] = g[pp][t + k * S::kThreadsPerPoly];
+    }
+    fwd_from_regs<A, LOGN, PPT>(x, s, t, tw, c, sub);
+#pragma unroll
+    for (int pp = 0; pp < PPT; ++pp) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[pp][k] = A::fwd_fin(c, x[pp][k]);
+        if (live[pp]) store8_consecutive(g[pp] + 8 * t, x[pp]);
+    }
 }
 
-template <class A, int LOGN, int POLYS>
+template <class A, int LOGN, int POLYS, int PPT>
 __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS)
-    ntt_fast_inv_kernel(typename A::T* __restrict__ data, size_t batch,
+    ntt_fast_inv_kernel(typename A::T* __restrict__ data, size_t rows, unsigned depth,
                         const typename A::TW* __restrict__ tw, typename A::Ctx c) {
     using T = typename A::T;
     using S = FastShape<LOGN>;
-    __shared__ __align__(16) T smem[POLYS * S::kPaddedElems];
+    __shared__ __align__(16) T smem[POLYS * PPT * S::kPaddedElems];
     const unsigned t = threadIdx.x;
-    size_t poly = (size_t)blockIdx.x * POLYS + threadIdx.y;
-    const bool live = poly < batch;
-    if (!live) poly = batch - 1;
-    T* g = data + (poly << LOGN);
-    T* s = smem + threadIdx.y * S::kPaddedElems;
-    T x[8];
-    load8_consecutive(g + 8 * t, x);
-    inv_to_regs<A, LOGN>(x, s, t, tw, c);
-    if (live) {
+    const size_t row0 = ((size_t)blockIdx.x * POLYS + threadIdx.y) * PPT;
+    const SubPoly sub{depth, (unsigned)row0 & ((1u << depth) - 1u)};
+    T* s = smem + threadIdx.y * PPT * S::kPaddedElems;
+    T x[PPT][8];
+    T* g[PPT];
+    bool live[PPT];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) g[t + k * S::kThreadsPerPoly] = A::inv_fin(c, x[k]);
+    for (int pp = 0; pp < PPT; ++pp) {
+        size_t row = row0 + pp;
+        live[pp] = row < rows;
+        g[pp] = data + ((live[pp] ? row : rows - 1) << LOGN);
+        load8_consecutive(g[pp] + 8 * t, x[pp]);
+    }
+    inv_to_regs<A, LOGN, PPT>(x, s, t, tw, c, sub);
+    // after the last radix-8 pass positions 0..3 hold sums, 4..7 canonical-range products; with
+    // depth > 0 the lazy values feed the global passes, which canonicalise at the end
+#pragma unroll
+    for (int pp = 0; pp < PPT; ++pp) {
+        if (!live[pp]) continue;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            T v = x[pp][k];
+            if (depth == 0) v = (k < 4) ? A::inv_fin(c, v) : A::inv_fin_prod(c, v);
+            g[pp][t + k * S::kThreadsPerPoly] = v;
+        }
     }
 }
 
 // Fused fwd -> pointwise multiply(-accumulate) -> inv, one pass over HBM (BASELINE C2 / the
 // PBS external product shape):  out = inv(acc + fwd(lhs) * rhs).
-template <class A, int LOGN, int POLYS>
+template <class A, int LOGN, int POLYS, int PPT>
 __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS)
     ntt_fast_fwd_mac_inv_kernel(typename A::T* __restrict__ out,
                                 const typename A::T* __restrict__ lhs,
@@ -253,45 +315,56 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS)
                                 const typename A::TW* __restrict__ tw_inv, typename A::Ctx c) {
     using T = typename A::T;
     using S = FastShape<LOGN>;
-    __shared__ __align__(16) T smem[POLYS * S::kPaddedElems];
+    __shared__ __align__(16) T smem[POLYS * PPT * S::kPaddedElems];
     const unsigned t = threadIdx.x;
-    size_t poly = (size_t)blockIdx.x * POLYS + threadIdx.y;
-    const bool live = poly < batch;
-    if (!live) poly = batch - 1;
-    T* s = smem + threadIdx.y * S::kPaddedElems;
-    T x[8];
-    const T* gl = lhs + (poly << LOGN);
+    const size_t poly0 = ((size_t)blockIdx.x * POLYS + threadIdx.y) * PPT;
+    const SubPoly sub{0u, 0u};
+    T* s = smem + threadIdx.y * PPT * S::kPaddedElems;
+    T x[PPT][8];
+    size_t poly[PPT];
+    bool live[PPT];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = gl[t + k * S::kThreadsPerPoly];
-    fwd_from_regs<A, LOGN>(x, s, t, tw_fwd, c);
+    for (int pp = 0; pp < PPT; ++pp) {
+        live[pp] = poly0 + pp < batch;
+        poly[pp] = live[pp] ? poly0 + pp : batch - 1;
+        const T* gl = lhs + (poly[pp] << LOGN);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[pp][k] = gl[t + k * S::kThreadsPerPoly];
+    }
+    fwd_from_regs<A, LOGN, PPT>(x, s, t, tw_fwd, c, sub);
     // pointwise step on the 8 consecutive NTT-domain coefficients this thread holds
-    {
+#pragma unroll
+    for (int pp = 0; pp < PPT; ++pp) {
         T r[8];
-        load8_consecutive(rhs + ((poly % rhs_polys) << LOGN) + 8 * t, r);
+        load8_consecutive(rhs + ((poly[pp] % rhs_polys) << LOGN) + 8 * t, r);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = A::mul_full(c, A::fwd_fin(c, x[k]), r[k]);
+        for (int k = 0; k < 8; ++k) x[pp][k] = A::mul_full(c, A::fwd_fin(c, x[pp][k]), r[k]);
         if (acc) {
-            load8_consecutive(acc + ((poly % acc_polys) << LOGN) + 8 * t, r);
+            load8_consecutive(acc + ((poly[pp] % acc_polys) << LOGN) + 8 * t, r);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = A::add_full(c, x[k], r[k]);
+            for (int k = 0; k < 8; ++k) x[pp][k] = A::add_full(c, x[pp][k], r[k]);
         }
     }
     // no barrier needed: the inverse first writes the 8 positions this thread just read
-    inv_to_regs<A, LOGN>(x, s, t, tw_inv, c);
-    if (live) {
-        T* go = out + (poly << LOGN);
+    inv_to_regs<A, LOGN, PPT>(x, s, t, tw_inv, c, sub);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) go[t + k * S::kThreadsPerPoly] = A::inv_fin(c, x[k]);
+    for (int pp = 0; pp < PPT; ++pp) {
+        if (!live[pp]) continue;
+        T* go = out + (poly[pp] << LOGN);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            go[t + k * S::kThreadsPerPoly] = (k < 4) ? A::inv_fin(c, x[pp][k]) : A::inv_fin_prod(c, x[pp][k]);
     }
 }
 
 // Host-side dispatch (defined in ntt_fast_*.cu, one translation unit per modulus family).
 // Returns false when (A, logn) has no fast kernel; the caller then uses the generic path.
+// `rows` rows of 2^logn coefficients; depth as in SubPoly.
 template <class A>
-bool fast_fwd(typename A::T* data, size_t batch, int logn, const typename A::TW* tw,
+bool fast_fwd(typename A::T* data, size_t rows, int logn, unsigned depth, const typename A::TW* tw,
               const typename A::Ctx& c, cudaStream_t st);
 template <class A>
-bool fast_inv(typename A::T* data, size_t batch, int logn, const typename A::TW* tw,
+bool fast_inv(typename A::T* data, size_t rows, int logn, unsigned depth, const typename A::TW* tw,
               const typename A::Ctx& c, cudaStream_t st);
 template <class A>
 bool fast_fwd_mac_inv(typename A::T* out, const typename A::T* lhs, const typename A::T* rhs,

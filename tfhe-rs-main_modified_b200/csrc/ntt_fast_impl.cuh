@@ -11,21 +11,46 @@ struct FastPolys {  // polynomials per CTA: keep CTAs at >= 256 threads
     static constexpr int value = (1 << LOGN) >= 2048 ? 1 : 2048 / (1 << LOGN);
 };
 
+// Polynomials per thread: two when both tiles fit the 48 KiB static shared-memory window and the
+// polynomial is big enough for the shared index arithmetic to matter.
 template <class A, int LOGN>
-void launch_fast_fwd(typename A::T* data, size_t batch, const typename A::TW* tw,
-                     const typename A::Ctx& c, cudaStream_t st) {
+struct FastPPT {
+    static constexpr bool fits =
+        2 * FastPolys<LOGN>::value * FastShape<LOGN>::kPaddedElems * sizeof(typename A::T) <= 48 * 1024;
+    static constexpr int value = (LOGN >= 10 && fits) ? 2 : 1;
+};
+
+template <class A, int LOGN, int PPT>
+void launch_fast_fwd_p(typename A::T* data, size_t rows, unsigned depth, const typename A::TW* tw,
+                       const typename A::Ctx& c, cudaStream_t st) {
     constexpr int P = FastPolys<LOGN>::value;
     dim3 block(FastShape<LOGN>::kThreadsPerPoly, P);
-    unsigned grid = (unsigned)((batch + P - 1) / P);
-    ntt_fast_fwd_kernel<A, LOGN, P><<<grid, block, 0, st>>>(data, batch, tw, c);
+    unsigned grid = (unsigned)((rows + P * PPT - 1) / (P * PPT));
+    ntt_fast_fwd_kernel<A, LOGN, P, PPT><<<grid, block, 0, st>>>(data, rows, depth, tw, c);
 }
 template <class A, int LOGN>
-void launch_fast_inv(typename A::T* data, size_t batch, const typename A::TW* tw,
+void launch_fast_fwd(typename A::T* data, size_t rows, unsigned depth, const typename A::TW* tw,
                      const typename A::Ctx& c, cudaStream_t st) {
+    if (FastPPT<A, LOGN>::value == 2 && depth == 0 && rows > 1)
+        launch_fast_fwd_p<A, LOGN, FastPPT<A, LOGN>::value>(data, rows, depth, tw, c, st);
+    else
+        launch_fast_fwd_p<A, LOGN, 1>(data, rows, depth, tw, c, st);
+}
+template <class A, int LOGN, int PPT>
+void launch_fast_inv_p(typename A::T* data, size_t rows, unsigned depth, const typename A::TW* tw,
+                       const typename A::Ctx& c, cudaStream_t st) {
     constexpr int P = FastPolys<LOGN>::value;
     dim3 block(FastShape<LOGN>::kThreadsPerPoly, P);
-    unsigned grid = (unsigned)((batch + P - 1) / P);
-    ntt_fast_inv_kernel<A, LOGN, P><<<grid, block, 0, st>>>(data, batch, tw, c);
+    unsigned grid = (unsigned)((rows + P * PPT - 1) / (P * PPT));
+    ntt_fast_inv_kernel<A, LOGN, P, PPT><<<grid, block, 0, st>>>(data, rows, depth, tw, c);
+}
+template <class A, int LOGN>
+void launch_fast_inv(typename A::T* data, size_t rows, unsigned depth, const typename A::TW* tw,
+                     const typename A::Ctx& c, cudaStream_t st) {
+    if (FastPPT<A, LOGN>::value == 2 && depth == 0 && rows > 1)
+        launch_fast_inv_p<A, LOGN, FastPPT<A, LOGN>::value>(data, rows, depth, tw, c, st);
+    else
+        launch_fast_inv_p<A, LOGN, 1>(data, rows, depth, tw, c, st);
 }
 template <class A, int LOGN>
 void launch_fast_fmi(typename A::T* out, const typename A::T* lhs, const typename A::T* rhs,
@@ -33,9 +58,10 @@ void launch_fast_fmi(typename A::T* out, const typename A::T* lhs, const typenam
                      const typename A::TW* tw_fwd, const typename A::TW* tw_inv,
                      const typename A::Ctx& c, cudaStream_t st) {
     constexpr int P = FastPolys<LOGN>::value;
+    constexpr int PPT = FastPPT<A, LOGN>::value;
     dim3 block(FastShape<LOGN>::kThreadsPerPoly, P);
-    unsigned grid = (unsigned)((batch + P - 1) / P);
-    ntt_fast_fwd_mac_inv_kernel<A, LOGN, P><<<grid, block, 0, st>>>(
+    unsigned grid = (unsigned)((batch + P * PPT - 1) / (P * PPT));
+    ntt_fast_fwd_mac_inv_kernel<A, LOGN, P, PPT><<<grid, block, 0, st>>>(
         out, lhs, rhs, rhs_polys, acc, acc_polys ? acc_polys : 1, batch, tw_fwd, tw_inv, c);
 }
 
@@ -51,18 +77,18 @@ void launch_fast_fmi(typename A::T* out, const typename A::T* lhs, const typenam
 
 
 template <class A>
-bool fast_fwd_impl(typename A::T* data, size_t batch, int logn, const typename A::TW* tw,
-                   const typename A::Ctx& c, cudaStream_t st) {
-#define NTT_CALL(L) launch_fast_fwd<A, L>(data, batch, tw, c, st)
+bool fast_fwd_impl(typename A::T* data, size_t batch, int logn, unsigned depth,
+                   const typename A::TW* tw, const typename A::Ctx& c, cudaStream_t st) {
+#define NTT_CALL(L) launch_fast_fwd<A, L>(data, batch, depth, tw, c, st)
     NTT_FAST_SWITCH(NTT_CALL)
 #undef NTT_CALL
     NTT_CUDA_CHECK(cudaGetLastError());
     return true;
 }
 template <class A>
-bool fast_inv_impl(typename A::T* data, size_t batch, int logn, const typename A::TW* tw,
-                   const typename A::Ctx& c, cudaStream_t st) {
-#define NTT_CALL(L) launch_fast_inv<A, L>(data, batch, tw, c, st)
+bool fast_inv_impl(typename A::T* data, size_t batch, int logn, unsigned depth,
+                   const typename A::TW* tw, const typename A::Ctx& c, cudaStream_t st) {
+#define NTT_CALL(L) launch_fast_inv<A, L>(data, batch, depth, tw, c, st)
     NTT_FAST_SWITCH(NTT_CALL)
 #undef NTT_CALL
     NTT_CUDA_CHECK(cudaGetLastError());
@@ -84,14 +110,14 @@ bool fast_fmi_impl(typename A::T* out, const typename A::T* lhs, const typename 
 // explicit specialisations of the entry points declared in ntt_fast.cuh
 #define NTT_DEFINE_FAST(A)                                                                         \
     template <>                                                                                    \
-    bool fast_fwd<A>(A::T * data, size_t batch, int logn, const A::TW* tw, const A::Ctx& c,        \
-                     cudaStream_t st) {                                                            \
-        return fast_fwd_impl<A>(data, batch, logn, tw, c, st);                                     \
+    bool fast_fwd<A>(A::T * data, size_t batch, int logn, unsigned depth, const A::TW* tw,         \
+                     const A::Ctx& c, cudaStream_t st) {                                           \
+        return fast_fwd_impl<A>(data, batch, logn, depth, tw, c, st);                              \
     }                                                                                              \
     template <>                                                                                    \
-    bool fast_inv<A>(A::T * data, size_t batch, int logn, const A::TW* tw, const A::Ctx& c,        \
-                     cudaStream_t st) {                                                            \
-        return fast_inv_impl<A>(data, batch, logn, tw, c, st);                                     \
+    bool fast_inv<A>(A::T * data, size_t batch, int logn, unsigned depth, const A::TW* tw,         \
+                     const A::Ctx& c, cudaStream_t st) {                                           \
+        return fast_inv_impl<A>(data, batch, logn, depth, tw, c, st);                              \
     }                                                                                              \
     template <>                                                                                    \
     bool fast_fwd_mac_inv<A>(A::T * out, const A::T* lhs, const A::T* rhs, size_t rhs_polys,       \
