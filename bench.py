@@ -29,6 +29,7 @@ SOLINAS_P = (1 << 64) - (1 << 32) + 1
 BATCH_PER_GPU = 65536          # 65536 * 16 KiB = 1 GiB per GPU: far beyond the 126 MB L2
 ALG_BYTES_PER_NTT = 2 * N * 8  # one in-place NTT reads and writes each coefficient once
 E2E_BATCH = 16384              # host-buffer leg: 256 MiB in + 256 MiB out per step
+NCU_TRAFFIC_PER_LAUNCH = 2.097e9  # measured by ncu --set full for one launch of this workload (see profiles/)
 METRIC = "fwd+inv NTTs/sec, N=2048 u64 prime, batched"
 UNIT = "NTT/s"
 WORKLOAD = "prime64 Solinas p=2^64-2^32+1 N=2048, batch %d polynomials per GPU, fwd then inv (in place, HBM-resident)" % BATCH_PER_GPU
@@ -43,15 +44,44 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML every ~2 ms when
+    pynvml is importable (the timed region is tens of milliseconds), nvidia-smi otherwise."""
 
     def __init__(self, index):
         self.index = index
         self.samples, self.max_mhz, self.reasons = [], None, set()
         self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+        self._t = threading.Thread(target=self._run_nvml if self._nvml else self._run_smi, daemon=True)
 
-    def _run(self):
+    def _run_nvml(self):
+        nv = self._nvml
+        flags = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = get_reasons(self._h)
+                for name, bit in flags.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -81,7 +111,8 @@ class ClockSampler:
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+                "reasons": sorted(self.reasons), "samples": len(s),
+                "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 def synth(batch, seed):
@@ -247,7 +278,10 @@ def run_gpu(args):
                        "l2_policy": "inputs (1 GiB per GPU) far larger than the 126 MB L2",
                        "parallelism": "batch sharded over %d GPU(s), no collective" % world},
             "roofline": {"bound": "hbm", "kernel": "ntt %s (N=2048 Solinas)" % dom, "achieved": achieved, "peak": hbm,
-                         "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": which,
+                         "unit": "GB/s", "frac": achieved / hbm, "traffic": NCU_TRAFFIC_PER_LAUNCH, "peak_source": which,
+                         "traffic_source": "profiles/r01_ncu_full_solinas2048_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                         "limiter": "INT32 ALU pipe (ncu: sm__inst_executed_pipe_alu 76-80 % of peak, DRAM 23 %): "
+                                    "the Solinas butterfly is carry-chain adds, see DESIGN.md section 5",
                          "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                          "algorithmic_bytes_per_launch": batch * ALG_BYTES_PER_NTT},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,

@@ -193,19 +193,20 @@ struct Solinas64 {
 
     // Montgomery product b * wm * 2^-64 mod p, canonical, for any 64-bit b and wm < p.
     // With p = 2^64 - 2^32 + 1 the REDC needs no multiplication (p^-1 = 2^32 + 1 mod 2^64):
-    //   T = b*wm = (hi : x1 : x0);  m1 = (x0 + x1) mod 2^32, c = its carry
-    //   S = m1*(2^32-1) + x0 - c = ((m1 + c) << 32) - (x1 + c)        (0 <= S < 2^64)
-    //   r = hi - S  in (-p, p);  negative -> + p, i.e. - (2^32-1) in wrapping arithmetic
-    // Only carry chains of one family are combined (add.cc/addc, sub.cc/subc are never mixed).
+    //   T = b*wm = (h1 : h0 : x1 : x0);  m1 = (x0 + x1) mod 2^32, c = its carry
+    //   S = m1*(2^32-1) + x0 - c = ((m1 + c) << 32) - (x1 + c)          (0 <= S < 2^64)
+    //   r = (h1:h0) - S = ((h1 + k - (m1 + c)) : r0)  with (k : r0) = h0 + x1 + c
+    //   r in (-p, p); negative (borrow in the high word) -> + p, i.e. - (2^32-1) wrapping.
+    // h1 + k cannot overflow because the high half of b*wm is at most p - 2.  Eight carry-chain
+    // instructions; add.cc/addc and sub.cc/subc chains are never mixed.
     NTT_DEVINL static uint64_t mulm(uint64_t b, uint64_t wm) {
         unsigned __int128 t = (unsigned __int128)b * wm;  // 4 IMAD.WIDE.U32 + 3
         uint64_t lo = (uint64_t)t, hi = (uint64_t)(t >> 64), r;
-        asm("{ .reg .u32 x0,x1,h0,h1,m1,c,s0,s1,m;\n\t"
+        asm("{ .reg .u32 x0,x1,h0,h1,m1,tt,m;\n\t"
             "mov.b64 {x0,x1}, %1; mov.b64 {h0,h1}, %2;\n\t"
-            "add.cc.u32 m1,x0,x1; addc.u32 c,0,0;\n\t"
-            "sub.cc.u32 s0,0,x1; subc.u32 s1,m1,0;\n\t"
-            "sub.u32 s0,s0,c; add.u32 s1,s1,c;\n\t"
-            "sub.cc.u32 h0,h0,s0; subc.cc.u32 h1,h1,s1; subc.u32 m,0,0;\n\t"
+            "add.cc.u32 m1,x0,x1; addc.u32 tt,m1,0;\n\t"
+            "addc.cc.u32 h0,h0,x1; addc.u32 h1,h1,0;\n\t"
+            "sub.cc.u32 h1,h1,tt; subc.u32 m,0,0;\n\t"
             "sub.cc.u32 h0,h0,m; subc.u32 h1,h1,0;\n\t"
             "mov.b64 %0,{h0,h1}; }"
             : "=l"(r)
