@@ -6,6 +6,7 @@
 
 #include "capi_common.cuh"
 #include "ntt_arith.cuh"
+#include "ntt_fast.cuh"
 #include "plan_math.hpp"
 
 using namespace nttb200;
@@ -206,10 +207,10 @@ NTT_DEVINL uint64_t pair32(const CrtConsts& k, int a, int b, uint32_t inv, uint3
     return (uint64_t)ra + (uint64_t)vb * k.P[a];
 }
 
-template <int KIND>
-NTT_DEVINL void crt_one(const CrtConsts& k, const ResPtrs& res, size_t i, void* value) {
-    auto r32 = [&](int j) { return static_cast<const uint32_t*>(res.r[j])[i]; };
-    auto r64 = [&](int j) { return static_cast<const uint64_t*>(res.r[j])[i]; };
+// Recombination of one coefficient; r32(j) / r64(j) return the residue modulo prime j (from
+// memory in crt_merge_kernel, from registers in the fused polymul kernel).
+template <int KIND, class R32, class R64>
+NTT_DEVINL void crt_with(const CrtConsts& k, R32 r32, R64 r64, size_t i, void* value) {
     if constexpr (KIND == NTT_B200_NATIVE32_PLAN32 || KIND == NTT_B200_NATIVE_BINARY64_PLAN32) {
         // native32.rs:27-55 / native_binary64.rs:32-60 (same Garner chain, u32 vs u64 accumulation)
         uint32_t P0 = k.P[0], P1 = k.P[1], P2 = k.P[2];
@@ -315,10 +316,80 @@ NTT_DEVINL void crt_one(const CrtConsts& k, const ResPtrs& res, size_t i, void* 
 }
 
 template <int KIND>
+NTT_DEVINL void crt_one(const CrtConsts& k, const ResPtrs& res, size_t i, void* value) {
+    auto r32 = [&](int j) { return static_cast<const uint32_t*>(res.r[j])[i]; };
+    auto r64 = [&](int j) { return static_cast<const uint64_t*>(res.r[j])[i]; };
+    crt_with<KIND>(k, r32, r64, i, value);
+}
+
+template <int KIND>
 __global__ void crt_merge_kernel(void* value, ResPtrs res, size_t total, CrtConsts k) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (size_t)gridDim.x * blockDim.x)
         crt_one<KIND>(k, res, i, value);
+}
+
+// ---- fused negacyclic_polymul for the Plan32 kinds with <= 5 primes --------------------------
+// One CTA per product: the operands are read once (coalesced), every residue transform runs in
+// registers + one shared-memory tile, the residues of all primes stay in registers until the
+// Garner recombination, and only the product is written: 3*n*sizeof(value) bytes of HBM traffic
+// per product (BASELINE config C4: 96 KiB), where the reference heap-allocates ten scratch
+// vectors per call (native64.rs:1046-1056).
+using S32H = Shoup<uint32_t, true>;  // every CRT prime is < 2^30 (lib.rs:457-466)
+template <int NP>
+struct FusedPrimes {
+    const S32H::TW* fwd[NP];
+    const S32H::TW* inv[NP];
+    S32H::Ctx ctx[NP];
+    S32H::TW n_inv[NP];
+};
+
+template <int KIND, class VT, int NP, int LOGN, bool BINARY>
+__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly)
+    native_polymul_fused_kernel(VT* __restrict__ prod, const VT* __restrict__ lhs,
+                                const VT* __restrict__ rhs, FusedPrimes<NP> P, CrtConsts k) {
+    using S = FastShape<LOGN>;
+    constexpr int TPP = S::kThreadsPerPoly;
+    __shared__ __align__(16) uint32_t smem[S::kPaddedElems];
+    const unsigned t = threadIdx.x;
+    const size_t base = (size_t)blockIdx.x << LOGN;
+    const SubPoly sub{0u, 0u};
+    VT lv[8], rv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        lv[q] = lhs[base + t + q * TPP];
+        rv[q] = rhs[base + t + q * TPP];
+    }
+    uint32_t res[NP][8];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        uint32_t x[1][8], y[1][8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            x[0][q] = (uint32_t)rem64((uint64_t)lv[q], k.P[j], k.P_b64[j]);
+            y[0][q] = BINARY ? (uint32_t)rv[q] : (uint32_t)rem64((uint64_t)rv[q], k.P[j], k.P_b64[j]);
+        }
+        fwd_from_regs<S32H, LOGN, 1>(x, smem, t, P.fwd[j], P.ctx[j], sub);
+        __syncthreads();  // everyone has read its last-pass inputs before the tile is reused
+        fwd_from_regs<S32H, LOGN, 1>(y, smem, t, P.fwd[j], P.ctx[j], sub);
+        // mul_assign_normalize on the 8 consecutive NTT-domain coefficients of this thread
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            uint32_t a = S32H::fwd_fin(P.ctx[j], x[0][q]), b = S32H::fwd_fin(P.ctx[j], y[0][q]);
+            x[0][q] = S32H::mul_const(P.ctx[j], S32H::mul_full(P.ctx[j], a, b), P.n_inv[j]);
+        }
+        __syncthreads();
+        inv_to_regs<S32H, LOGN, 1>(x, smem, t, P.inv[j], P.ctx[j], sub);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) res[j][q] = S32H::inv_fin(P.ctx[j], x[0][q]);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        auto r32 = [&](int j) { return res[j][q]; };
+        auto r64 = [&](int) { return (uint64_t)0; };
+        crt_with<KIND>(k, r32, r64, base + t + q * TPP, prod);
+    }
 }
 
 }  // namespace
@@ -384,8 +455,52 @@ struct ntt_b200_native_plan {
     }
     // negacyclic_polymul over `batch` polynomial pairs; residues live in a scratch arena that is
     // sized to stay L2-resident (chunks of the batch), so they never travel to HBM and back.
+    template <int KIND, class VT, int NP, bool BINARY>
+    bool launch_fused(void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st) const {
+        FusedPrimes<NP> P{};
+        for (int j = 0; j < NP; ++j) {
+            RawShoup32H raw;
+            if (!p32[j].impl->raw_shoup32h(&raw)) return false;
+            P.fwd[j] = raw.fwd;
+            P.inv[j] = raw.inv;
+            P.ctx[j] = raw.ctx;
+            P.n_inv[j] = raw.n_inv;
+        }
+        auto aligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+        if (!aligned(prod) || !aligned(lhs) || !aligned(rhs)) return false;
+        unsigned grid = (unsigned)batch;
+#define NTT_FUSED_CASE(L)                                                                         \
+    case L:                                                                                       \
+        native_polymul_fused_kernel<KIND, VT, NP, L, BINARY>                                      \
+            <<<grid, FastShape<L>::kThreadsPerPoly, 0, st>>>((VT*)prod, (const VT*)lhs,           \
+                                                             (const VT*)rhs, P, consts);          \
+        break;
+        switch (__builtin_ctzll((unsigned long long)n)) {
+            NTT_FUSED_CASE(10)
+            NTT_FUSED_CASE(11)
+            NTT_FUSED_CASE(12)
+            default: return false;
+        }
+#undef NTT_FUSED_CASE
+        NTT_CUDA_CHECK(cudaGetLastError());
+        return true;
+    }
+    bool polymul_fused(void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st) const {
+        switch (kind) {
+            case NTT_B200_NATIVE32_PLAN32:
+                return launch_fused<NTT_B200_NATIVE32_PLAN32, uint32_t, 3, false>(prod, lhs, rhs, batch, st);
+            case NTT_B200_NATIVE64_PLAN32:
+                return launch_fused<NTT_B200_NATIVE64_PLAN32, uint64_t, 5, false>(prod, lhs, rhs, batch, st);
+            case NTT_B200_NATIVE_BINARY32_PLAN32:
+                return launch_fused<NTT_B200_NATIVE_BINARY32_PLAN32, uint32_t, 2, true>(prod, lhs, rhs, batch, st);
+            case NTT_B200_NATIVE_BINARY64_PLAN32:
+                return launch_fused<NTT_B200_NATIVE_BINARY64_PLAN32, uint64_t, 3, true>(prod, lhs, rhs, batch, st);
+            default: return false;
+        }
+    }
     void polymul_dev(void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st) const {
         if (!batch) return;
+        if (polymul_fused(prod, lhs, rhs, batch, st)) return;
         keep_pool_cached(device);
         const size_t rb = (size_t)info.residue_bytes, vb = (size_t)info.value_bytes;
         const int np = info.num_primes;

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <type_traits>
 
 #include "ntt_fast.cuh"
 #include "ntt_kernels.cuh"
@@ -157,6 +158,14 @@ struct PlanImpl final : PrimePlan {
     }
 
     std::shared_ptr<PrimePlan> clone() const override { return std::make_shared<PlanImpl>(*this); }
+    bool raw_shoup32h(RawShoup32H* out) const override {
+        if constexpr (std::is_same<A, Shoup<uint32_t, true>>::value) {
+            *out = RawShoup32H{d_fwd.get(), d_inv.get(), ctx, n_inv};
+            return true;
+        } else {
+            return false;
+        }
+    }
 
     template <bool INV>
     void launch_rows(T* data, size_t num_rows, int log_row, int depth, int finalize,

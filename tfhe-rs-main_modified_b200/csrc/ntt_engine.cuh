@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include "ntt_arith.cuh"
+
 namespace nttb200 {
 
 struct CudaError : std::runtime_error {
@@ -20,6 +22,15 @@ struct CudaError : std::runtime_error {
         if (e__ != cudaSuccess)                                                               \
             throw ::nttb200::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__));  \
     } while (0)
+
+// Raw device tables of a 30-bit-prime plan, for kernels that run several plans at once (the fused
+// CRT polymul).
+struct RawShoup32H {
+    const ShoupTw<uint32_t>* fwd;
+    const ShoupTw<uint32_t>* inv;
+    Shoup<uint32_t, true>::Ctx ctx;
+    ShoupTw<uint32_t> n_inv;
+};
 
 // Abstract prime plan (prime32::Plan / prime64::Plan); one concrete class per modulus family.
 struct PrimePlan {
@@ -46,6 +57,7 @@ struct PrimePlan {
                              const void* acc, size_t acc_polys, size_t batch,
                              cudaStream_t stream) const = 0;
     virtual std::shared_ptr<PrimePlan> clone() const = 0;
+    virtual bool raw_shoup32h(RawShoup32H*) const { return false; }
 };
 
 // nullptr <=> the reference's try_new returns None.  Throws CudaError on CUDA failures.
