@@ -204,8 +204,8 @@ struct Solinas64 {
         uint64_t lo = (uint64_t)t, hi = (uint64_t)(t >> 64), r;
         asm("{ .reg .u32 x0,x1,h0,h1,m1,tt,m;\n\t"
             "mov.b64 {x0,x1}, %1; mov.b64 {h0,h1}, %2;\n\t"
-            "add.cc.u32 m1,x0,x1; addc.u32 tt,m1,0;\n\t"
-            "addc.cc.u32 h0,h0,x1; addc.u32 h1,h1,0;\n\t"
+            "add.cc.u32 m1,x0,x1; madc.lo.u32 tt,m1,1,0;\n\t"
+            "addc.cc.u32 h0,h0,x1; madc.lo.u32 h1,h1,1,0;\n\t"
             "sub.cc.u32 h1,h1,tt; subc.u32 m,0,0;\n\t"
             "sub.cc.u32 h0,h0,m; subc.u32 h1,h1,0;\n\t"
             "mov.b64 %0,{h0,h1}; }"
@@ -219,7 +219,7 @@ struct Solinas64 {
         uint64_t r;
         asm("{ .reg .u32 a0,a1,b0,b1,c;\n\t"
             "mov.b64 {a0,a1}, %1; mov.b64 {b0,b1}, %2;\n\t"
-            "add.cc.u32 a0,a0,b0; addc.cc.u32 a1,a1,b1; addc.u32 c,0,0;\n\t"
+            "add.cc.u32 a0,a0,b0; addc.cc.u32 a1,a1,b1; madc.lo.u32 c,0,0,0;\n\t"
             "add.u32 a1,a1,c; sub.cc.u32 a0,a0,c; subc.u32 a1,a1,0;\n\t"
             "mov.b64 %0, {a0,a1}; }"
             : "=l"(r)

@@ -34,6 +34,14 @@ struct FastShape {
     static constexpr int kPaddedElems = (1 << LOGN) + ((1 << LOGN) >> 3);  // 16 B per 128 B
 };
 
+// Resident CTAs per SM the register allocator is asked to allow: 1024 threads per SM (64
+// registers per thread), which every family reaches without spilling except where noted in
+// FastMinBlocks specialisations.
+template <class A, int THREADS>
+struct FastMinBlocks {
+    static constexpr int value = 1024 / THREADS > 0 ? 1024 / THREADS : 1;
+};
+
 // 16 bytes of padding after every 128 bytes: u64 -> a + 2*(a>>4), u32 -> a + 4*(a>>5)
 template <class T>
 NTT_DEVINL constexpr unsigned pad_index(unsigned a) {
@@ -237,7 +245,8 @@ NTT_DEVINL void inv_to_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsign
 // (r mod 2^depth) of polynomial r >> depth (PPT must be 1 then: the rows of a group would need
 // different twiddles).  Out-of-range rows are clamped and not stored (whole-CTA barriers inside).
 template <class A, int LOGN, int POLYS, int PPT>
-__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS)
+__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
+                                  FastMinBlocks<A, FastShape<LOGN>::kThreadsPerPoly * POLYS>::value)
     ntt_fast_fwd_kernel(typename A::T* __restrict__ data, size_t rows, unsigned depth,
                         const typename A::TW* __restrict__ tw, typename A::Ctx c) {
     using T = typename A::T;
@@ -268,7 +277,8 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS)
 }
 
 template <class A, int LOGN, int POLYS, int PPT>
-__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS)
+__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
+                                  FastMinBlocks<A, FastShape<LOGN>::kThreadsPerPoly * POLYS>::value)
     ntt_fast_inv_kernel(typename A::T* __restrict__ data, size_t rows, unsigned depth,
                         const typename A::TW* __restrict__ tw, typename A::Ctx c) {
     using T = typename A::T;
