@@ -227,11 +227,11 @@ static inline uint64_t solinas_mul(uint64_t a, uint64_t b) {
     uint64_t mid = hi & 0x00000000FFFFFFFFull;
     hi = (hi & 0xFFFFFFFF00000000ull) >> 32;
     uint64_t low2 = lo - hi;
-    if (hi > lo) low2 += p;
+    low2 += (hi > lo) ? p : 0; /* `if hi > lo { low2 += p }`, as a select */
     uint64_t product = mid << 32;
     product -= mid;
     uint64_t result = low2 + product;
-    if (result < product || result >= p) result -= p;
+    result -= ((result < product) | (result >= p)) ? p : 0;
     return result;
 }
 /* generic_solinas.rs:72-74 */
@@ -333,15 +333,18 @@ void tfo_plan64_free(tfo_plan64 *pl) {
 
 /* generic_solinas.rs:449-481 at recursion depth 0.  The depth-first recursion
  * (generic_solinas.rs:1338-1386) performs the same butterflies with the same
- * twiddles in another order, so one breadth-first sweep gives the same values. */
-static void fwd64_exact(uint64_t *data, size_t n, uint64_t p, const uint64_t *twid, int solinas) {
+ * twiddles in another order, so one breadth-first sweep gives the same values.
+ * The Solinas and the generic-modulus instantiations are separate loops, as the
+ * reference monomorphises them (PrimeModulus for Solinas / for u64). */
+static void fwd64_solinas(uint64_t *data, size_t n, const uint64_t *twid) {
+    const uint64_t p = SOLINAS_P;
     size_t t = n / 2, m = 1;
     while (m < n) {
         for (size_t i = 0; i < m; i++) {
             uint64_t w1 = twid[m + i];
             uint64_t *z0 = data + 2 * i * t, *z1 = z0 + t;
             for (size_t j = 0; j < t; j++) {
-                uint64_t z1w = solinas ? solinas_mul(z1[j], w1) : generic_mul64(p, z1[j], w1);
+                uint64_t z1w = solinas_mul(z1[j], w1);
                 uint64_t a = z0[j];
                 z0[j] = add64(p, a, z1w);
                 z1[j] = sub64(p, a, z1w);
@@ -351,9 +354,32 @@ static void fwd64_exact(uint64_t *data, size_t n, uint64_t p, const uint64_t *tw
         m *= 2;
     }
 }
+static void fwd64_generic(uint64_t *data, size_t n, uint64_t p, const uint64_t *twid) {
+    size_t t = n / 2, m = 1;
+    while (m < n) {
+        for (size_t i = 0; i < m; i++) {
+            uint64_t w1 = twid[m + i];
+            uint64_t *z0 = data + 2 * i * t, *z1 = z0 + t;
+            for (size_t j = 0; j < t; j++) {
+                uint64_t z1w = generic_mul64(p, z1[j], w1);
+                uint64_t a = z0[j];
+                z0[j] = add64(p, a, z1w);
+                z1[j] = sub64(p, a, z1w);
+            }
+        }
+        t /= 2;
+        m *= 2;
+    }
+}
+static void fwd64_exact(uint64_t *data, size_t n, uint64_t p, const uint64_t *twid, int solinas) {
+    if (solinas)
+        fwd64_solinas(data, n, twid);
+    else
+        fwd64_generic(data, n, p, twid);
+}
 /* generic_solinas.rs:483-514 */
-static void inv64_exact(uint64_t *data, size_t n, uint64_t p, const uint64_t *inv_twid,
-                        int solinas) {
+static void inv64_solinas(uint64_t *data, size_t n, const uint64_t *inv_twid) {
+    const uint64_t p = SOLINAS_P;
     size_t t = 1, m = n;
     while (m > 1) {
         m /= 2;
@@ -363,12 +389,34 @@ static void inv64_exact(uint64_t *data, size_t n, uint64_t p, const uint64_t *in
             for (size_t j = 0; j < t; j++) {
                 uint64_t a = z0[j], b = z1[j];
                 z0[j] = add64(p, a, b);
-                uint64_t d = sub64(p, a, b);
-                z1[j] = solinas ? solinas_mul(d, w1) : generic_mul64(p, d, w1);
+                z1[j] = solinas_mul(sub64(p, a, b), w1);
             }
         }
         t *= 2;
     }
+}
+static void inv64_generic(uint64_t *data, size_t n, uint64_t p, const uint64_t *inv_twid) {
+    size_t t = 1, m = n;
+    while (m > 1) {
+        m /= 2;
+        for (size_t i = 0; i < m; i++) {
+            uint64_t w1 = inv_twid[m + i];
+            uint64_t *z0 = data + 2 * i * t, *z1 = z0 + t;
+            for (size_t j = 0; j < t; j++) {
+                uint64_t a = z0[j], b = z1[j];
+                z0[j] = add64(p, a, b);
+                z1[j] = generic_mul64(p, sub64(p, a, b), w1);
+            }
+        }
+        t *= 2;
+    }
+}
+static void inv64_exact(uint64_t *data, size_t n, uint64_t p, const uint64_t *inv_twid,
+                        int solinas) {
+    if (solinas)
+        inv64_solinas(data, n, inv_twid);
+    else
+        inv64_generic(data, n, p, inv_twid);
 }
 
 /* shoup.rs:544-615 driver with the less_than_62bit.rs:117-154 (lazy in [0,4p)) or
