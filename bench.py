@@ -126,18 +126,25 @@ def synth(batch, seed):
 # ---------------------------------------------------------------------------------------------
 # CPU legs (oracle port of tfhe-ntt's scalar path; the one place bench.py may execute oracle/)
 # ---------------------------------------------------------------------------------------------
+CPU_ISA = ["scalar"]
+CPU_NOTE = ("C port of tfhe-ntt's CPU path (oracle/): AVX-512 Solinas butterflies as in generic_solinas.rs:415-446 when the "
+            "host has AVX-512F+DQ, else the scalar path; batch split over all host threads in static contiguous chunks; "
+            "the Rust crate itself cannot be built in this image")
+
+
 def cpu_leg(sample_polys, repeats, threads):
     import oracle_lib
     lib = oracle_lib._load(native=True)   # rebuilt with -march=native on this host
     plan = oracle_lib.OraclePlan(64, N, SOLINAS_P, _lib=lib)
     buf = synth(sample_polys, 0xC0FFEE03)
-    plan.fwd_batch_inplace(buf, threads)  # warm
-    plan.inv_batch_inplace(buf, threads)
+    isa = plan.fwd_batch_inplace(buf, threads, simd=True)  # warm
+    plan.inv_batch_inplace(buf, threads, simd=True)
     t0 = time.perf_counter()
     for _ in range(repeats):
-        plan.fwd_batch_inplace(buf, threads)
-        plan.inv_batch_inplace(buf, threads)
+        plan.fwd_batch_inplace(buf, threads, simd=True)
+        plan.inv_batch_inplace(buf, threads, simd=True)
     dt = time.perf_counter() - t0
+    CPU_ISA[0] = isa
     return 2.0 * sample_polys * repeats / dt, dt
 
 
@@ -156,12 +163,12 @@ def run_reference(args):
     plan = oracle_lib.OraclePlan(64, N, SOLINAS_P, _lib=lib)
     buf = synth(per_step_polys, 0xC0FFEE03)
     for _ in range(warm):
-        plan.fwd_batch_inplace(buf, threads)
-        plan.inv_batch_inplace(buf, threads)
+        plan.fwd_batch_inplace(buf, threads, simd=True)
+        plan.inv_batch_inplace(buf, threads, simd=True)
     t0 = time.perf_counter()
     for _ in range(steps):
-        plan.fwd_batch_inplace(buf, threads)
-        plan.inv_batch_inplace(buf, threads)
+        plan.fwd_batch_inplace(buf, threads, simd=True)
+        plan.inv_batch_inplace(buf, threads, simd=True)
     dt = time.perf_counter() - t0
     value = 2.0 * per_step_polys * steps / dt
     sample_txt = "%d polynomials per step (fwd then inv), %d threads, static contiguous chunks" % (per_step_polys, threads)
@@ -171,7 +178,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "cpu_sample": sample_txt},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt,
-                         "note": "C restatement of tfhe-ntt's scalar CPU path (oracle/); the Rust crate cannot be built in this image"},
+                         "isa": CPU_ISA[0], "note": CPU_NOTE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -296,10 +303,10 @@ def run_gpu(args):
             threads = os.cpu_count() or 1
             try:
                 rate, dt = cpu_leg(2048, 1, threads)
-                reps = int(max(1, min(50, 12.0 / max(dt, 1e-3))))
+                reps = int(max(1, min(400, 12.0 / max(dt, 1e-3))))
                 rate, dt = cpu_leg(2048, reps, threads)
                 line["cpu_baseline"] = {
-                    "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                    "value": rate, "unit": UNIT, "cores": threads, "kind": "port", "isa": CPU_ISA[0], "note": CPU_NOTE,
                     "sample": "%d x (fwd+inv over 2048 polynomials), %.1f s of CPU work, %d threads" % (reps, dt, threads)}
             except Exception as e:  # the GPU numbers stand on their own
                 line["cpu_baseline"] = {"error": repr(e)}

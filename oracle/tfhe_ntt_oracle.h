@@ -168,6 +168,12 @@ void tfo_plan64_inv_batch(const tfo_plan64 *, uint64_t *buf, size_t batch, int t
 void tfo_plan32_fwd_batch(const tfo_plan32 *, uint32_t *buf, size_t batch, int threads);
 void tfo_plan32_inv_batch(const tfo_plan32 *, uint32_t *buf, size_t batch, int threads);
 
+/* AVX-512 port of the reference's vectorised Solinas path (tfhe_ntt_simd.c; bench.py only).
+ * Return 1 when the SIMD path ran, 0 when the CPU / build has no AVX-512F+DQ or p is not the
+ * Solinas prime (the caller then uses the scalar batch helpers). */
+int tfo_plan64_fwd_batch_simd(const tfo_plan64 *, uint64_t *buf, size_t batch, int threads);
+int tfo_plan64_inv_batch_simd(const tfo_plan64 *, uint64_t *buf, size_t batch, int threads);
+
 #ifdef __cplusplus
 }
 #endif

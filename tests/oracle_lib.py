@@ -25,15 +25,22 @@ NATIVE_KIND_NAMES = [
 ]
 
 
+_NATIVE_BUILT = [False]
+
+
 def build(native=False):
     """Compile the oracle with gcc (make); returns the path of the shared object."""
     target = "native" if native else "all"
     name = "libtfhe_ntt_oracle_native.so" if native else "libtfhe_ntt_oracle.so"
     so = os.path.join(_ORACLE_DIR, name)
-    src = [os.path.join(_ORACLE_DIR, f) for f in ("tfhe_ntt_oracle.c", "tfhe_ntt_oracle.h")]
+    src = [os.path.join(_ORACLE_DIR, f) for f in ("tfhe_ntt_oracle.c", "tfhe_ntt_simd.c", "tfhe_ntt_oracle.h")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src)
-    if stale or native:
+    # the -march=native build is redone once per process: the file may have travelled from a
+    # machine with a different CPU
+    if stale or (native and not _NATIVE_BUILT[0]):
         subprocess.run(["make", "-C", _ORACLE_DIR, target], check=True, capture_output=True)
+        if native:
+            _NATIVE_BUILT[0] = True
     return so
 
 
@@ -114,6 +121,8 @@ def _load(native=False):
         "tfo_plan64_inv_batch": (None, [P64, vp, sz, i]),
         "tfo_plan32_fwd_batch": (None, [P32, vp, sz, i]),
         "tfo_plan32_inv_batch": (None, [P32, vp, sz, i]),
+        "tfo_plan64_fwd_batch_simd": (i, [P64, vp, sz, i]),
+        "tfo_plan64_inv_batch_simd": (i, [P64, vp, sz, i]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -210,11 +219,18 @@ class OraclePlan:
                                                         min(a.size, l.size, r.size))
         return a
 
-    def fwd_batch_inplace(self, buf, threads):
+    def fwd_batch_inplace(self, buf, threads, simd=False):
+        """Returns "avx512" when the vectorised Solinas port ran, else "scalar"."""
+        if simd and self.bits == 64 and self.lib.tfo_plan64_fwd_batch_simd(self.h, _ptr(buf), buf.size // self.n, threads):
+            return "avx512"
         getattr(self.lib, self._pfx + "fwd_batch")(self.h, _ptr(buf), buf.size // self.n, threads)
+        return "scalar"
 
-    def inv_batch_inplace(self, buf, threads):
+    def inv_batch_inplace(self, buf, threads, simd=False):
+        if simd and self.bits == 64 and self.lib.tfo_plan64_inv_batch_simd(self.h, _ptr(buf), buf.size // self.n, threads):
+            return "avx512"
         getattr(self.lib, self._pfx + "inv_batch")(self.h, _ptr(buf), buf.size // self.n, threads)
+        return "scalar"
 
 
 def negacyclic_convolution_mod(bits, p, lhs, rhs):
