@@ -148,6 +148,19 @@ int ntt_b200_plan64_fwd_mac_inv_device(const ntt_b200_plan64 *plan, uint64_t *ou
                                        const uint64_t *acc, size_t acc_polys, size_t batch,
                                        void *stream);
 
+/* External-product core of the NTT-PBS (tfhe ntt64_pbs.rs:598-661), new:
+ *   out[b][c] = inv( sum_{r<rows} fwd(in[b][r]) (*) ggsw[r][c] )      c < cols
+ * in: batch x rows polynomials (e.g. the (k+1)*l decomposition digits of one GLWE per batch item),
+ * ggsw: rows x cols NTT-domain polynomials shared by the whole batch, out: batch x cols polynomials.
+ * Same result as Plan::fwd on every input, Plan::mul_accumulate for every (r, c), Plan::inv on
+ * every accumulator.  rows >= 1, 1 <= cols <= 4 use one fused kernel for n = 512..4096. */
+int ntt_b200_plan64_ext_product_device(const ntt_b200_plan64 *plan, uint64_t *out,
+                                       const uint64_t *in, const uint64_t *ggsw, size_t rows,
+                                       size_t cols, size_t batch, void *stream);
+int ntt_b200_plan32_ext_product_device(const ntt_b200_plan32 *plan, uint32_t *out,
+                                       const uint32_t *in, const uint32_t *ggsw, size_t rows,
+                                       size_t cols, size_t batch, void *stream);
+
 /* Host-memory form of the fused call: lhs/out hold `batch` polynomials in host memory (pinned
  * memory lets the copies overlap the kernels); rhs / acc hold rhs_polys / acc_polys polynomials
  * (== batch, or fewer and reused cyclically; acc may be NULL).  H2D, kernel and D2H of successive

@@ -138,6 +138,12 @@ struct Div64 {
                                                              rhs, rhs_len, stream),               \
                   "mul_accumulate_device");                                                       \
         }                                                                                         \
+        void ext_product_device(ELEM* out, const ELEM* in, const ELEM* ggsw, size_t rows,         \
+                                size_t cols, size_t batch, void* stream = nullptr) const {        \
+            check(ntt_b200_plan##SFX##_ext_product_device(h_.get(), out, in, ggsw, rows, cols,    \
+                                                          batch, stream),                         \
+                  "ext_product_device");                                                          \
+        }                                                                                         \
         void fwd_mac_inv_device(ELEM* out, const ELEM* lhs, const ELEM* rhs, size_t rhs_polys,    \
                                 const ELEM* acc, size_t acc_polys, size_t batch,                  \
                                 void* stream = nullptr) const {                                   \

@@ -203,6 +203,36 @@ def test_device_api_and_fused(T):
     assert (d_n.cpu().numpy().view(np.uint64).ravel() == op.normalize(want.ravel())).all()
 
 
+@pytest.mark.parametrize("bits,n,p,rows,cols", [
+    (64, 2048, SOLINAS_P, 4, 2),          # GLWE k=1, l=2 (BASELINE C3 shape): fused kernel
+    (64, 1024, 4611686018427322369, 3, 3),
+    (32, 4096, 1073479681, 2, 4),
+    (64, 256, SOLINAS_P, 4, 2),           # n outside the fused sizes: generic composition
+    (32, 512, 2147352577, 2, 5),          # cols > 4: generic composition
+])
+def test_ext_product(T, bits, n, p, rows, cols):
+    import torch
+    gp, op = plan_pair(T, bits, n, p)
+    dt = np.uint64 if bits == 64 else np.uint32
+    tdt = torch.int64 if bits == 64 else torch.int32
+    rng = np.random.default_rng(rows * 10 + cols)
+    batch = 5
+    x = rand_below(rng, p, (batch, rows, n), dt)
+    g = rand_below(rng, p, (rows, cols, n), dt)
+    d_x = torch.from_numpy(x.view(np.int64 if bits == 64 else np.int32)).cuda()
+    d_g = torch.from_numpy(g.view(np.int64 if bits == 64 else np.int32)).cuda()
+    d_o = torch.zeros((batch, cols, n), dtype=tdt, device="cuda")
+    gp.ext_product_device(d_o, d_x, d_g, rows, cols, stream=torch.cuda.current_stream())
+    got = d_o.cpu().numpy().view(dt)
+    for b in range(batch):
+        f = op.fwd(x[b])
+        for c in range(cols):
+            acc = np.zeros(n, dtype=dt)
+            for r in range(rows):
+                acc = op.mul_accumulate(acc, f[r], g[r, c])
+            assert (got[b, c] == op.inv(acc)).all(), (b, c)
+
+
 def test_fwd_mac_inv_batch_host(T):
     n, p = 1024, SOLINAS_P
     gp, op = plan_pair(T, 64, n, p)

@@ -49,6 +49,7 @@ def _prime_sigs(sfx, elem):
         p + "mul_accumulate_device": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
         p + "fwd_mac_inv_device": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _sz, _vp]),
         p + "fwd_mac_inv_batch": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _sz]),
+        p + "ext_product_device": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     }
 
 

@@ -135,6 +135,14 @@ class PrimePlanBase:
         B.check(self._f("mul_accumulate_device")(self._h, B.dev_ptr(acc), length, B.dev_ptr(lhs), lhs_len,
                                                  B.dev_ptr(rhs), rhs_len, B.stream_ptr(stream)))
 
+    def ext_product_device(self, out, inp, ggsw, rows, cols, batch=None, stream=None):
+        """out[b][c] = inv(sum_r fwd(inp[b][r]) * ggsw[r][c]) -- the NTT-PBS external-product core."""
+        n = self.ntt_size()
+        if batch is None:
+            batch = B.dev_numel(inp, self._eb()) // (n * rows)
+        B.check(self._f("ext_product_device")(self._h, B.dev_ptr(out), B.dev_ptr(inp), B.dev_ptr(ggsw), rows, cols,
+                                              batch, B.stream_ptr(stream)), "in ext_product_device")
+
     def fwd_mac_inv_device(self, out, lhs, rhs, acc=None, batch=None, rhs_polys=None, acc_polys=None,
                            stream=None):
         n = self.ntt_size()

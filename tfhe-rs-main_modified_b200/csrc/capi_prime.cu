@@ -375,6 +375,23 @@ int dev_pointwise_check(size_t len, size_t sub_len) {
             return NTT_B200_ERR_LEN;                                                               \
         return host_fwd_mac_inv(plan->impl.get(), out, lhs, rhs, rhs_polys, acc, acc_polys, batch);\
     }
+#define NTT_DEFINE_EXT(SFX, ELEM)                                                                  \
+    extern "C" int ntt_b200_plan##SFX##_ext_product_device(                                        \
+        const ntt_b200_plan##SFX* plan, ELEM* out, const ELEM* in, const ELEM* ggsw, size_t rows,  \
+        size_t cols, size_t batch, void* stream) {                                                 \
+        if (!plan) return NTT_B200_ERR_ARG;                                                        \
+        if (!batch) return NTT_B200_OK;                                                            \
+        if (!out || !in || !ggsw) return NTT_B200_ERR_ARG;                                         \
+        if (rows == 0 || cols == 0 || rows > 65535 || cols > 65535) return NTT_B200_ERR_LEN;       \
+        return guarded([&] {                                                                       \
+            plan->impl->ext_product(out, in, ggsw, (unsigned)rows, (unsigned)cols, batch,          \
+                                    (cudaStream_t)stream);                                         \
+            return NTT_B200_OK;                                                                    \
+        });                                                                                        \
+    }
+NTT_DEFINE_EXT(64, uint64_t)
+NTT_DEFINE_EXT(32, uint32_t)
+
 NTT_DEFINE_FMI_BATCH(64, uint64_t)
 NTT_DEFINE_FMI_BATCH(32, uint32_t)
 

@@ -101,6 +101,9 @@ struct Shoup {
     NTT_DEVINL static T mul_const(const Ctx& c, T a, TW w) { return csub(mul_lazy(c, a, w), c.p); }
 
     NTT_DEVINL static T add_full(const Ctx& c, T a, T b) { return csub(a + b, c.p); }  // p < 2^(W-1)
+    // running sum of canonical products: acc stays canonical
+    NTT_DEVINL static T acc_add(const Ctx& c, T acc, T prod) { return add_full(c, acc, prod); }
+    NTT_DEVINL static T acc_fin(const Ctx&, T acc) { return acc; }
     NTT_DEVINL static T mul_full(const Ctx& c, T a, T b);
 };
 
@@ -175,6 +178,8 @@ struct Wide32 {
     NTT_DEVINL static T mul_full(const Ctx& c, T a, T b) {
         return barrett32((uint64_t)a * b, c.p, c.barrett64);
     }
+    NTT_DEVINL static T acc_add(const Ctx& c, T acc, T prod) { return add_full(c, acc, prod); }
+    NTT_DEVINL static T acc_fin(const Ctx&, T acc) { return acc; }
 };
 
 // ------------------------------------------------------------------------------------
@@ -274,6 +279,9 @@ struct Solinas64 {
     NTT_DEVINL static T mul_const(const Ctx&, T a, TW wm) { return mulm(a, wm); }
     NTT_DEVINL static T add_full(const Ctx&, T a, T b) { return canon(add_lazy(a, b)); }
     NTT_DEVINL static T mul_full(const Ctx&, T a, T b) { return mul_plain(a, b); }
+    // running sum: arbitrary representative + canonical product, canonicalised once at the end
+    NTT_DEVINL static T acc_add(const Ctx&, T acc, T prod) { return add_lazy(acc, prod); }
+    NTT_DEVINL static T acc_fin(const Ctx&, T acc) { return canon(acc); }
 };
 
 // ------------------------------------------------------------------------------------
@@ -313,6 +321,8 @@ struct Mont64 {
         uint64_t x = redc64(a * b, __umul64hi(a, b), c.p, c.pinv);
         return redc64(x * c.r2, __umul64hi(x, c.r2), c.p, c.pinv);
     }
+    NTT_DEVINL static T acc_add(const Ctx& c, T acc, T prod) { return add_full(c, acc, prod); }
+    NTT_DEVINL static T acc_fin(const Ctx&, T acc) { return acc; }
 };
 
 }  // namespace nttb200

@@ -282,6 +282,40 @@ struct PlanImpl final : PrimePlan {
             lhs_period, rhs_period, ctx);
         NTT_CUDA_CHECK(cudaGetLastError());
     }
+    void ext_product(void* out, const void* in, const void* ggsw, unsigned rows, unsigned cols,
+                     size_t batch, cudaStream_t st) const override {
+        if (!batch || !rows || !cols) return;
+        DeviceGuard g(device);
+        if (aligned16(out) && aligned16(in) && aligned16(ggsw) &&
+            fast_ext_product<A>(static_cast<T*>(out), static_cast<const T*>(in),
+                                static_cast<const T*>(ggsw), rows, cols, batch, logn, d_fwd.get(),
+                                d_inv.get(), ctx, st))
+            return;
+        // generic composition: transform a copy of the inputs, accumulate row by row, invert
+        size_t in_total = batch * rows * n, out_total = batch * cols * n;
+        T *tmp = nullptr, *row = nullptr, *acc = nullptr;
+        NTT_CUDA_CHECK(cudaMallocAsync(&tmp, in_total * sizeof(T), st));
+        NTT_CUDA_CHECK(cudaMallocAsync(&row, batch * n * sizeof(T), st));
+        NTT_CUDA_CHECK(cudaMallocAsync(&acc, batch * n * sizeof(T), st));
+        NTT_CUDA_CHECK(cudaMemcpyAsync(tmp, in, in_total * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        fwd(tmp, batch * rows, st);
+        for (unsigned cc = 0; cc < cols; ++cc) {
+            NTT_CUDA_CHECK(cudaMemsetAsync(acc, 0, batch * n * sizeof(T), st));
+            for (unsigned r = 0; r < rows; ++r) {
+                NTT_CUDA_CHECK(cudaMemcpy2DAsync(row, n * sizeof(T), tmp + (size_t)r * n, rows * n * sizeof(T),
+                                                 n * sizeof(T), batch, cudaMemcpyDeviceToDevice, st));
+                mul_accumulate(acc, row, static_cast<const T*>(ggsw) + ((size_t)r * cols + cc) * n, batch * n,
+                               batch * n, n, st);
+            }
+            inv(acc, batch, st);
+            NTT_CUDA_CHECK(cudaMemcpy2DAsync(static_cast<T*>(out) + (size_t)cc * n, cols * n * sizeof(T), acc,
+                                             n * sizeof(T), n * sizeof(T), batch, cudaMemcpyDeviceToDevice, st));
+        }
+        (void)out_total;
+        NTT_CUDA_CHECK(cudaFreeAsync(tmp, st));
+        NTT_CUDA_CHECK(cudaFreeAsync(row, st));
+        NTT_CUDA_CHECK(cudaFreeAsync(acc, st));
+    }
     void fwd_mac_inv(void* out, const void* lhs, const void* rhs, size_t rhs_polys,
                      const void* acc, size_t acc_polys, size_t batch,
                      cudaStream_t st) const override {

@@ -56,6 +56,10 @@ struct PrimePlan {
     virtual void fwd_mac_inv(void* out, const void* lhs, const void* rhs, size_t rhs_polys,
                              const void* acc, size_t acc_polys, size_t batch,
                              cudaStream_t stream) const = 0;
+    // out[b][c] = inv(sum_r fwd(in[b][r]) * ggsw[r][c]); in: [batch][rows][n], ggsw: [rows][cols][n]
+    // (NTT domain, shared by the batch), out: [batch][cols][n]
+    virtual void ext_product(void* out, const void* in, const void* ggsw, unsigned rows,
+                             unsigned cols, size_t batch, cudaStream_t stream) const = 0;
     virtual std::shared_ptr<PrimePlan> clone() const = 0;
     virtual bool raw_shoup32h(RawShoup32H*) const { return false; }
 };

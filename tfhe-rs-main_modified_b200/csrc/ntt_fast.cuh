@@ -367,6 +367,60 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS)
     }
 }
 
+// External-product core (the NTT-PBS shape, tfhe ntt64_pbs.rs:598-661): for every batch item b
+//   out[b][c] = inv( sum_r fwd(in[b][r]) (*) ggsw[r][c] ),   r < rows, c < COLS
+// `ggsw` (rows x COLS NTT-domain polynomials) is shared by the whole batch and stays in L2.
+// One CTA per batch item: rows forward transforms, rows*COLS pointwise multiply-accumulates
+// into register accumulators, COLS inverse transforms; HBM traffic is rows*n*w in, COLS*n*w out.
+// Equivalent to the reference's sequence Plan::fwd / Plan::mul_accumulate / Plan::inv.
+template <class A, int LOGN, int COLS>
+__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly)
+    ntt_fast_ext_product_kernel(typename A::T* __restrict__ out, const typename A::T* __restrict__ in,
+                                const typename A::T* __restrict__ ggsw, unsigned rows,
+                                const typename A::TW* __restrict__ tw_fwd,
+                                const typename A::TW* __restrict__ tw_inv, typename A::Ctx c) {
+    using T = typename A::T;
+    using S = FastShape<LOGN>;
+    __shared__ __align__(16) T smem[S::kPaddedElems];
+    const unsigned t = threadIdx.x;
+    const size_t b = blockIdx.x;
+    const SubPoly sub{0u, 0u};
+    T acc[COLS][8];
+#pragma unroll
+    for (int cc = 0; cc < COLS; ++cc)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[cc][k] = 0;
+    for (unsigned r = 0; r < rows; ++r) {
+        T x[1][8];
+        const T* gi = in + ((b * rows + r) << LOGN);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[0][k] = gi[t + k * S::kThreadsPerPoly];
+        fwd_from_regs<A, LOGN, 1>(x, smem, t, tw_fwd, c, sub);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[0][k] = A::fwd_fin(c, x[0][k]);
+#pragma unroll
+        for (int cc = 0; cc < COLS; ++cc) {
+            T g[8];
+            load8_consecutive(ggsw + (((size_t)r * COLS + cc) << LOGN) + 8 * t, g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[cc][k] = A::acc_add(c, acc[cc][k], A::mul_full(c, x[0][k], g[k]));
+        }
+        __syncthreads();  // the tile is reused by the next transform
+    }
+#pragma unroll
+    for (int cc = 0; cc < COLS; ++cc) {
+        T x[1][8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[0][k] = A::acc_fin(c, acc[cc][k]);
+        inv_to_regs<A, LOGN, 1>(x, smem, t, tw_inv, c, sub);
+        T* go = out + ((b * COLS + cc) << LOGN);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            go[t + k * S::kThreadsPerPoly] = (k < 4) ? A::inv_fin(c, x[0][k]) : A::inv_fin_prod(c, x[0][k]);
+        __syncthreads();
+    }
+}
+
 // Host-side dispatch (defined in ntt_fast_*.cu, one translation unit per modulus family).
 // Returns false when (A, logn) has no fast kernel; the caller then uses the generic path.
 // `rows` rows of 2^logn coefficients; depth as in SubPoly.
@@ -376,6 +430,11 @@ bool fast_fwd(typename A::T* data, size_t rows, int logn, unsigned depth, const 
 template <class A>
 bool fast_inv(typename A::T* data, size_t rows, int logn, unsigned depth, const typename A::TW* tw,
               const typename A::Ctx& c, cudaStream_t st);
+template <class A>
+bool fast_ext_product(typename A::T* out, const typename A::T* in, const typename A::T* ggsw,
+                      unsigned rows, unsigned cols, size_t batch, int logn,
+                      const typename A::TW* tw_fwd, const typename A::TW* tw_inv,
+                      const typename A::Ctx& c, cudaStream_t st);
 template <class A>
 bool fast_fwd_mac_inv(typename A::T* out, const typename A::T* lhs, const typename A::T* rhs,
                       size_t rhs_polys, const typename A::T* acc, size_t acc_polys, size_t batch,

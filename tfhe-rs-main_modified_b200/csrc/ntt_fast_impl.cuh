@@ -107,6 +107,38 @@ bool fast_fmi_impl(typename A::T* out, const typename A::T* lhs, const typename 
     return true;
 }
 
+template <class A, int LOGN>
+bool launch_fast_ext(typename A::T* out, const typename A::T* in, const typename A::T* ggsw,
+                     unsigned rows, unsigned cols, size_t batch, const typename A::TW* tw_fwd,
+                     const typename A::TW* tw_inv, const typename A::Ctx& c, cudaStream_t st) {
+    dim3 block(FastShape<LOGN>::kThreadsPerPoly);
+    unsigned grid = (unsigned)batch;
+    switch (cols) {
+        case 1: ntt_fast_ext_product_kernel<A, LOGN, 1><<<grid, block, 0, st>>>(out, in, ggsw, rows, tw_fwd, tw_inv, c); break;
+        case 2: ntt_fast_ext_product_kernel<A, LOGN, 2><<<grid, block, 0, st>>>(out, in, ggsw, rows, tw_fwd, tw_inv, c); break;
+        case 3: ntt_fast_ext_product_kernel<A, LOGN, 3><<<grid, block, 0, st>>>(out, in, ggsw, rows, tw_fwd, tw_inv, c); break;
+        case 4: ntt_fast_ext_product_kernel<A, LOGN, 4><<<grid, block, 0, st>>>(out, in, ggsw, rows, tw_fwd, tw_inv, c); break;
+        default: return false;
+    }
+    return true;
+}
+template <class A>
+bool fast_ext_impl(typename A::T* out, const typename A::T* in, const typename A::T* ggsw,
+                   unsigned rows, unsigned cols, size_t batch, int logn,
+                   const typename A::TW* tw_fwd, const typename A::TW* tw_inv,
+                   const typename A::Ctx& c, cudaStream_t st) {
+    bool ok = false;
+    switch (logn) {  // the PBS polynomial sizes
+        case 9: ok = launch_fast_ext<A, 9>(out, in, ggsw, rows, cols, batch, tw_fwd, tw_inv, c, st); break;
+        case 10: ok = launch_fast_ext<A, 10>(out, in, ggsw, rows, cols, batch, tw_fwd, tw_inv, c, st); break;
+        case 11: ok = launch_fast_ext<A, 11>(out, in, ggsw, rows, cols, batch, tw_fwd, tw_inv, c, st); break;
+        case 12: ok = launch_fast_ext<A, 12>(out, in, ggsw, rows, cols, batch, tw_fwd, tw_inv, c, st); break;
+        default: return false;
+    }
+    if (ok) NTT_CUDA_CHECK(cudaGetLastError());
+    return ok;
+}
+
 // explicit specialisations of the entry points declared in ntt_fast.cuh
 #define NTT_DEFINE_FAST(A)                                                                         \
     template <>                                                                                    \
@@ -118,6 +150,12 @@ bool fast_fmi_impl(typename A::T* out, const typename A::T* lhs, const typename 
     bool fast_inv<A>(A::T * data, size_t batch, int logn, unsigned depth, const A::TW* tw,         \
                      const A::Ctx& c, cudaStream_t st) {                                           \
         return fast_inv_impl<A>(data, batch, logn, depth, tw, c, st);                              \
+    }                                                                                              \
+    template <>                                                                                    \
+    bool fast_ext_product<A>(A::T * out, const A::T* in, const A::T* ggsw, unsigned rows,          \
+                             unsigned cols, size_t batch, int logn, const A::TW* tw_fwd,           \
+                             const A::TW* tw_inv, const A::Ctx& c, cudaStream_t st) {              \
+        return fast_ext_impl<A>(out, in, ggsw, rows, cols, batch, logn, tw_fwd, tw_inv, c, st);    \
     }                                                                                              \
     template <>                                                                                    \
     bool fast_fwd_mac_inv<A>(A::T * out, const A::T* lhs, const A::T* rhs, size_t rhs_polys,       \

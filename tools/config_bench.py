@@ -65,6 +65,12 @@ def main():
     t = timeit(c3_step)
     out["C3"] = {"external_products_per_s": lwes / t, "ms": t * 1e3, "ntt_per_s": (lwes * 6) / t,
                  "note": "unfused: copy + 16384 fwd + 8 shared-GGSW mul_accumulate passes + 8192 inv"}
+    outp = torch.empty((lwes, 2, n), dtype=torch.int64, device="cuda")
+    t_e = timeit(lambda: plan.ext_product_device(outp, dig, ggsw, 4, 2, stream=st))
+    out["C3"]["fused_ext_product_ms"] = t_e * 1e3
+    out["C3"]["fused_external_products_per_s"] = lwes / t_e
+    out["C3"]["fused_ntt_per_s"] = lwes * 6 / t_e
+    out["C3"]["fused_hbm_frac"] = lwes * 6 * n * 8 / t_e / HBM
     t_f = timeit(lambda: plan.fwd_device(work, lwes * 4, stream=st))
     t_i = timeit(lambda: plan.inv_device(accs, lwes * 2, stream=st))
     out["C3"]["fwd_only_ms"] = t_f * 1e3
