@@ -34,6 +34,12 @@ extern "C" {
     pub fn ntt_b200_plan64_fwd_device(plan: *const ntt_b200_plan64, dev: *mut u64, batch: usize, stream: *mut c_void) -> c_int;
     pub fn ntt_b200_plan64_inv_device(plan: *const ntt_b200_plan64, dev: *mut u64, batch: usize, stream: *mut c_void) -> c_int;
 
+    pub fn ntt_b200_plan64_normalize_device(plan: *const ntt_b200_plan64, dev: *mut u64, len: usize, stream: *mut c_void) -> c_int;
+    pub fn ntt_b200_plan64_mul_accumulate_device(plan: *const ntt_b200_plan64, acc: *mut u64, len: usize, lhs: *const u64, lhs_len: usize, rhs: *const u64, rhs_len: usize, stream: *mut c_void) -> c_int;
+    pub fn ntt_b200_plan64_fwd_mac_inv_device(plan: *const ntt_b200_plan64, out: *mut u64, lhs: *const u64, rhs: *const u64, rhs_polys: usize, acc: *const u64, acc_polys: usize, batch: usize, stream: *mut c_void) -> c_int;
+    pub fn ntt_b200_plan64_fwd_mac_inv_batch(plan: *const ntt_b200_plan64, out: *mut u64, lhs: *const u64, rhs: *const u64, rhs_polys: usize, acc: *const u64, acc_polys: usize, batch: usize) -> c_int;
+    pub fn ntt_b200_plan64_ext_product_device(plan: *const ntt_b200_plan64, out: *mut u64, input: *const u64, ggsw: *const u64, rows: usize, cols: usize, batch: usize, stream: *mut c_void) -> c_int;
+
     pub fn ntt_b200_plan32_try_new(n: usize, p: u32, out: *mut *mut ntt_b200_plan32) -> c_int;
     pub fn ntt_b200_plan32_clone(plan: *const ntt_b200_plan32, out: *mut *mut ntt_b200_plan32) -> c_int;
     pub fn ntt_b200_plan32_free(plan: *mut ntt_b200_plan32);

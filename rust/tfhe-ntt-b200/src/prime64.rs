@@ -69,6 +69,22 @@ impl Plan {
     pub unsafe fn inv_device(&self, dev: *mut u64, batch: usize, stream: *mut core::ffi::c_void) {
         check(ffi::ntt_b200_plan64_inv_device(self.raw, dev, batch, stream), "inv_device")
     }
+    /// New: `out = inv(acc + fwd(lhs) * rhs)` on host slices in one pipelined call; `rhs` / `acc` may
+    /// hold fewer polynomials than `lhs` (reused cyclically).
+    pub fn fwd_mac_inv_batch(&self, out: &mut [u64], lhs: &[u64], rhs: &[u64], acc: Option<&[u64]>) {
+        let n = self.ntt_size();
+        assert_eq!(out.len(), lhs.len());
+        assert_eq!(lhs.len() % n, 0);
+        let (ap, al) = acc.map_or((core::ptr::null(), 0), |a| (a.as_ptr(), a.len() / n));
+        check(unsafe { ffi::ntt_b200_plan64_fwd_mac_inv_batch(self.raw, out.as_mut_ptr(), lhs.as_ptr(), rhs.as_ptr(), rhs.len() / n, ap, al, lhs.len() / n) }, "fwd_mac_inv_batch")
+    }
+    /// New: the NTT core of the PBS external product on device memory:
+    /// `out[b][c] = inv(sum_r fwd(input[b][r]) * ggsw[r][c])`.
+    /// # Safety
+    /// device pointers on the plan's GPU with `batch*rows*n`, `rows*cols*n`, `batch*cols*n` elements.
+    pub unsafe fn ext_product_device(&self, out: *mut u64, input: *const u64, ggsw: *const u64, rows: usize, cols: usize, batch: usize, stream: *mut core::ffi::c_void) {
+        check(ffi::ntt_b200_plan64_ext_product_device(self.raw, out, input, ggsw, rows, cols, batch, stream), "ext_product_device")
+    }
     pub(crate) unsafe fn borrowed(raw: *const ffi::ntt_b200_plan64) -> core::mem::ManuallyDrop<Self> {
         core::mem::ManuallyDrop::new(Self { raw: raw as *mut _ })
     }
