@@ -238,6 +238,45 @@ int ntt_b200_native_inv_device(const ntt_b200_native_plan *plan, void *value,
                                void *const *residues, size_t batch, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * product::Plan   (tfhe-ntt/src/product.rs:139-967): negacyclic NTT modulo a product of distinct
+ * primes (each < 2^32 prime runs as a prime32 plan, the others as prime64 plans).
+ * NTT-domain layout of ONE polynomial = the reference's (product.rs:261-283): the u32 residue
+ * arrays (n/2 words each) followed by the u64 residue arrays; ntt_domain_len() words in total.
+ * The *_device forms take `batch` polynomials with the residue arrays prime-major (prime j owns
+ * batch*n contiguous residues); batch = 1 is the reference layout.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ntt_b200_product_plan ntt_b200_product_plan;
+/* Plan::try_new(polynomial_size, modulus, factors) -> Option<Plan>     product.rs:153-246
+ * NONE: odd size, a zero / duplicate factor, product(factors) != modulus (or overflow), or any
+ * per-prime try_new is None. */
+int ntt_b200_product_try_new(size_t n, uint64_t modulus, const uint64_t *factors, size_t nfactors,
+                             ntt_b200_product_plan **out);
+void ntt_b200_product_free(ntt_b200_product_plan *plan);
+size_t ntt_b200_product_ntt_size(const ntt_b200_product_plan *plan);       /* product.rs:251 */
+uint64_t ntt_b200_product_modulus(const ntt_b200_product_plan *plan);      /* product.rs:257 */
+size_t ntt_b200_product_ntt_domain_len(const ntt_b200_product_plan *plan); /* product.rs:268 */
+/* Plan::fwd(ntt, standard, mode)   product.rs:273-357.  FwdMode::Bounded(b) produces the residues
+ * of FwdMode::Generic for every input that honours the bound, so there is one exact entry point. */
+int ntt_b200_product_fwd(const ntt_b200_product_plan *plan, uint64_t *ntt, size_t ntt_len,
+                         const uint64_t *standard, size_t standard_len);
+/* Plan::inv(standard, ntt, mode)   product.rs:360-880; accumulate != 0 = InvMode::Accumulate
+ * (standard += value, modulo the product).  ntt is transformed in place, as in the reference. */
+int ntt_b200_product_inv(const ntt_b200_product_plan *plan, uint64_t *standard, size_t standard_len,
+                         uint64_t *ntt, size_t ntt_len, int accumulate);
+int ntt_b200_product_normalize(const ntt_b200_product_plan *plan, uint64_t *values,
+                               size_t len); /* product.rs:917-932 */
+int ntt_b200_product_mul_assign_normalize(const ntt_b200_product_plan *plan, uint64_t *lhs,
+                                          size_t lhs_len, const uint64_t *rhs,
+                                          size_t rhs_len); /* product.rs:885-913 */
+int ntt_b200_product_mul_accumulate(const ntt_b200_product_plan *plan, uint64_t *acc, size_t acc_len,
+                                    const uint64_t *lhs, size_t lhs_len, const uint64_t *rhs,
+                                    size_t rhs_len); /* product.rs:935-967 */
+int ntt_b200_product_fwd_device(const ntt_b200_product_plan *plan, uint64_t *ntt,
+                                const uint64_t *standard, size_t batch, void *stream);
+int ntt_b200_product_inv_device(const ntt_b200_product_plan *plan, uint64_t *standard, uint64_t *ntt,
+                                size_t batch, int accumulate, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * plan-build helpers that are public in the reference crate
  * ------------------------------------------------------------------------------------------ */
 /* prime::is_prime64                                    prime.rs:76-126 */

@@ -1509,3 +1509,226 @@ void tfo_plan32_fwd_batch(const tfo_plan32 *pl, uint32_t *buf, size_t batch, int
 void tfo_plan32_inv_batch(const tfo_plan32 *pl, uint32_t *buf, size_t batch, int threads) {
     run_batch(pl, buf, batch, threads, 3);
 }
+
+/* ------------------------------------------------------------------ */
+/* product.rs -- plan over a product of distinct primes                */
+/* ------------------------------------------------------------------ */
+
+/* product.rs:22-64 (extended Euclid exactly as the reference iterates it) */
+static uint64_t modular_inv_u64(uint64_t modulus, uint64_t n) {
+    uint64_t old_r = n % modulus, r = modulus, old_s = 1, s = 0;
+    while (r != 0) {
+        uint64_t q = old_r / r;
+        uint64_t nr = old_r - q * r;
+        old_r = r;
+        r = nr;
+        uint64_t qs = (uint64_t)(((u128)q * s) % modulus);
+        uint64_t ns = old_s >= qs ? old_s - qs : old_s - qs + modulus; /* sub_mod, product.rs:67-73 */
+        old_s = s;
+        s = ns;
+    }
+    return old_s;
+}
+/* product.rs:85-93 */
+static inline uint64_t add_mod_u64(uint64_t modulus, uint64_t a, uint64_t b) {
+    uint64_t sum = a + b;
+    int overflow = sum < a;
+    return (sum >= modulus || overflow) ? sum - modulus : sum;
+}
+static inline uint64_t sub_mod_u64(uint64_t modulus, uint64_t a, uint64_t b) {
+    return a >= b ? a - b : a - b + modulus;
+}
+
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+
+/* product.rs:153-246 */
+tfo_product_plan *tfo_product_try_new(size_t n, uint64_t modulus, const uint64_t *factors,
+                                      size_t nfactors) {
+    if (n % 2 != 0 || nfactors > 64) return NULL;
+    uint64_t sorted[64];
+    memcpy(sorted, factors, nfactors * sizeof(uint64_t));
+    qsort(sorted, nfactors, sizeof(uint64_t), cmp_u64);
+    uint64_t prev = 0;
+    for (size_t i = 0; i < nfactors; i++) { /* zeros / duplicates */
+        if (sorted[i] == prev) return NULL;
+        prev = sorted[i];
+    }
+    size_t start = 0;
+    while (start < nfactors && sorted[start] == 1) start++;
+    const uint64_t *primes = sorted + start;
+    size_t len = nfactors - start;
+    u128 prod = 1;
+    for (size_t i = 0; i < len; i++) { /* checked_mul */
+        prod *= primes[i];
+        if (prod >> 64) return NULL;
+    }
+    if ((uint64_t)prod != modulus) return NULL;
+    tfo_product_plan *pl = (tfo_product_plan *)calloc(1, sizeof(*pl));
+    pl->n = n;
+    pl->modulus = modulus;
+    for (size_t i = 0; i < len; i++) {
+        if (primes[i] < ((uint64_t)1 << 32)) {
+            pl->p32[pl->n32] = tfo_plan32_try_new(n, (uint32_t)primes[i]);
+            if (!pl->p32[pl->n32]) {
+                tfo_product_free(pl);
+                return NULL;
+            }
+            pl->n32++;
+        }
+    }
+    for (size_t i = 0; i < len; i++) {
+        if (primes[i] >= ((uint64_t)1 << 32)) {
+            pl->p64[pl->n64] = tfo_plan64_try_new(n, primes[i]);
+            if (!pl->p64[pl->n64]) {
+                tfo_product_free(pl);
+                return NULL;
+            }
+            pl->n64++;
+        }
+    }
+    for (size_t i = 0; i < len; i++) pl->primes[i] = primes[i];
+    /* modular_inverses[offset(j) + i] = p_i^-1 mod p_j for i < j (product.rs:203-225) */
+    size_t offset = 0;
+    for (size_t j = 0; j < len; j++) {
+        for (size_t i = 0; i < j; i++) pl->inverses[offset + i] = modular_inv_u64(primes[j], primes[i]);
+        offset += j;
+    }
+    return pl;
+}
+
+void tfo_product_free(tfo_product_plan *pl) {
+    if (!pl) return;
+    for (int i = 0; i < 16; i++) tfo_plan32_free(pl->p32[i]);
+    for (int i = 0; i < 16; i++) tfo_plan64_free(pl->p64[i]);
+    free(pl);
+}
+
+/* product.rs:261-270 */
+size_t tfo_product_ntt_domain_len(const tfo_product_plan *pl) {
+    return (pl->n / 2) * (size_t)pl->n32 + pl->n * (size_t)pl->n64;
+}
+
+/* product.rs:273-357.  FwdMode::Bounded (the 2 x u32 arm, :304-325) is restated too: for inputs
+ * that honour its precondition it produces the same residues as Generic. */
+void tfo_product_fwd(const tfo_product_plan *pl, uint64_t *ntt, const uint64_t *standard,
+                     int bounded, uint64_t bound) {
+    size_t n = pl->n;
+    uint32_t *ntt_32 = (uint32_t *)ntt;
+    uint64_t *ntt_64 = ntt + (n / 2) * (size_t)pl->n32;
+    if (pl->n32 == 0 && pl->n64 == 1) {
+        memcpy(ntt_64, standard, n * sizeof(uint64_t));
+        tfo_plan64_fwd(pl->p64[0], ntt_64);
+        return;
+    }
+    if (pl->n32 == 1 && pl->n64 == 0) {
+        for (size_t i = 0; i < n; i++) ntt_32[i] = (uint32_t)standard[i];
+        tfo_plan32_fwd(pl->p32[0], ntt_32);
+        return;
+    }
+    if (pl->n32 == 2 && pl->n64 == 0) {
+        uint32_t *ntt0 = ntt_32, *ntt1 = ntt_32 + n;
+        uint32_t p0 = pl->p32[0]->p, p1 = pl->p32[1]->p;
+        uint64_t p = pl->modulus;
+        uint32_t p_u32 = (uint32_t)p;
+        if (bounded && bound < p0 && bound < p1) {
+            for (size_t i = 0; i < n; i++) {
+                int positive = standard[i] < p / 2;
+                uint32_t st = (uint32_t)standard[i];
+                uint32_t complement = p_u32 - st;
+                ntt0[i] = positive ? st : p0 - complement;
+                ntt1[i] = positive ? st : p1 - complement;
+            }
+        } else {
+            for (size_t i = 0; i < n; i++) {
+                ntt0[i] = (uint32_t)(standard[i] % p0);
+                ntt1[i] = (uint32_t)(standard[i] % p1);
+            }
+        }
+        tfo_plan32_fwd(pl->p32[0], ntt0);
+        tfo_plan32_fwd(pl->p32[1], ntt1);
+        return;
+    }
+    for (int j = 0; j < pl->n32; j++) {
+        uint32_t *r = ntt_32 + (size_t)j * n;
+        for (size_t i = 0; i < n; i++) r[i] = (uint32_t)(standard[i] % pl->p32[j]->p);
+        tfo_plan32_fwd(pl->p32[j], r);
+    }
+    for (int j = 0; j < pl->n64; j++) {
+        uint64_t *r = ntt_64 + (size_t)j * n;
+        for (size_t i = 0; i < n; i++) r[i] = standard[i] % pl->p64[j]->p;
+        tfo_plan64_fwd(pl->p64[j], r);
+    }
+}
+
+/* product.rs:360-880: per-prime inverse transforms, then Knuth 4.3.2 mixed-radix recombination.
+ * The special-cased arms (u64x1 :386-398, u32x1 :399-415, u32x2 :420-790) compute the same
+ * values as the general loop (:792-879) for canonical residues; the general loop is restated and
+ * the single-prime arms, which skip the recombination, explicitly. */
+void tfo_product_inv(const tfo_product_plan *pl, uint64_t *standard, uint64_t *ntt, int accumulate) {
+    size_t n = pl->n;
+    uint32_t *ntt_32 = (uint32_t *)ntt;
+    uint64_t *ntt_64 = ntt + (n / 2) * (size_t)pl->n32;
+    for (int j = 0; j < pl->n32; j++) tfo_plan32_inv(pl->p32[j], ntt_32 + (size_t)j * n);
+    for (int j = 0; j < pl->n64; j++) tfo_plan64_inv(pl->p64[j], ntt_64 + (size_t)j * n);
+    uint64_t p = pl->modulus;
+    if (pl->n32 == 0 && pl->n64 == 0) {
+        if (!accumulate) memset(standard, 0, n * sizeof(uint64_t));
+        return;
+    }
+    if (pl->n32 == 1 && pl->n64 == 0 && accumulate) { /* add_mod_u32 on the truncated word, :406-413 */
+        uint32_t q = pl->p32[0]->p;
+        for (size_t i = 0; i < n; i++) {
+            uint32_t a = (uint32_t)standard[i], b = ntt_32[i];
+            uint32_t sum = a + b;
+            int overflow = sum < a;
+            standard[i] = (sum >= q || overflow) ? (uint32_t)(sum - q) : sum;
+        }
+        return;
+    }
+    int c32 = pl->n32, c64 = pl->n64;
+    for (size_t idx = 0; idx < n; idx++) {
+        uint64_t v[32];
+        size_t offset = 0;
+        for (int j = 0; j < c32 + c64; j++) {
+            uint64_t pj = pl->primes[j];
+            uint64_t x = j < c32 ? ntt_32[(size_t)j * n + idx] : ntt_64[(size_t)(j - c32) * n + idx];
+            for (int i = 0; i < j; i++) {
+                uint64_t diff = sub_mod_u64(pj, x, v[i]);
+                x = (uint64_t)(((u128)diff * pl->inverses[offset + (size_t)i]) % pj);
+            }
+            offset += (size_t)j;
+            v[j] = x;
+        }
+        uint64_t acc = 0;
+        for (int j = c32 + c64 - 1; j >= 0; j--) acc = acc * pl->primes[j] + v[j];
+        standard[idx] = accumulate ? add_mod_u64(p, standard[idx], acc) : acc;
+    }
+}
+
+/* product.rs:885-967 */
+void tfo_product_mul_assign_normalize(const tfo_product_plan *pl, uint64_t *lhs, const uint64_t *rhs) {
+    size_t n = pl->n, off64 = (n / 2) * (size_t)pl->n32;
+    for (int j = 0; j < pl->n32; j++)
+        tfo_plan32_mul_assign_normalize(pl->p32[j], (uint32_t *)lhs + (size_t)j * n,
+                                        (const uint32_t *)rhs + (size_t)j * n, n);
+    for (int j = 0; j < pl->n64; j++)
+        tfo_plan64_mul_assign_normalize(pl->p64[j], lhs + off64 + (size_t)j * n, rhs + off64 + (size_t)j * n, n);
+}
+void tfo_product_normalize(const tfo_product_plan *pl, uint64_t *values) {
+    size_t n = pl->n, off64 = (n / 2) * (size_t)pl->n32;
+    for (int j = 0; j < pl->n32; j++) tfo_plan32_normalize(pl->p32[j], (uint32_t *)values + (size_t)j * n, n);
+    for (int j = 0; j < pl->n64; j++) tfo_plan64_normalize(pl->p64[j], values + off64 + (size_t)j * n, n);
+}
+void tfo_product_mul_accumulate(const tfo_product_plan *pl, uint64_t *acc, const uint64_t *lhs,
+                                const uint64_t *rhs) {
+    size_t n = pl->n, off64 = (n / 2) * (size_t)pl->n32;
+    for (int j = 0; j < pl->n32; j++)
+        tfo_plan32_mul_accumulate(pl->p32[j], (uint32_t *)acc + (size_t)j * n,
+                                  (const uint32_t *)lhs + (size_t)j * n, (const uint32_t *)rhs + (size_t)j * n, n);
+    for (int j = 0; j < pl->n64; j++)
+        tfo_plan64_mul_accumulate(pl->p64[j], acc + off64 + (size_t)j * n, lhs + off64 + (size_t)j * n,
+                                  rhs + off64 + (size_t)j * n, n);
+}

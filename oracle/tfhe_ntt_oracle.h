@@ -168,6 +168,32 @@ void tfo_plan64_inv_batch(const tfo_plan64 *, uint64_t *buf, size_t batch, int t
 void tfo_plan32_fwd_batch(const tfo_plan32 *, uint32_t *buf, size_t batch, int threads);
 void tfo_plan32_inv_batch(const tfo_plan32 *, uint32_t *buf, size_t batch, int threads);
 
+/* ---- product::Plan (product.rs:139-967): NTT over a product of distinct primes ----
+ * NTT-domain layout of one polynomial (product.rs:261-283): n32 arrays of n u32 (packed two per
+ * u64 word) followed by n64 arrays of n u64; ntt_domain_len() = n/2 * n32 + n * n64 words. */
+typedef struct tfo_product_plan {
+    size_t n;
+    uint64_t modulus;
+    int n32, n64;
+    tfo_plan32 *p32[16];
+    tfo_plan64 *p64[16];
+    uint64_t primes[32];     /* sorted: the u32 primes, then the u64 primes */
+    uint64_t inverses[512];  /* modular_inverses, product.rs:203-225 */
+} tfo_product_plan;
+tfo_product_plan *tfo_product_try_new(size_t n, uint64_t modulus, const uint64_t *factors,
+                                      size_t nfactors); /* NULL <=> None */
+void tfo_product_free(tfo_product_plan *);
+size_t tfo_product_ntt_domain_len(const tfo_product_plan *);
+/* bounded != 0 selects FwdMode::Bounded(bound) */
+void tfo_product_fwd(const tfo_product_plan *, uint64_t *ntt, const uint64_t *standard, int bounded,
+                     uint64_t bound);
+/* accumulate != 0 selects InvMode::Accumulate; ntt is transformed in place like the reference */
+void tfo_product_inv(const tfo_product_plan *, uint64_t *standard, uint64_t *ntt, int accumulate);
+void tfo_product_mul_assign_normalize(const tfo_product_plan *, uint64_t *lhs, const uint64_t *rhs);
+void tfo_product_normalize(const tfo_product_plan *, uint64_t *values);
+void tfo_product_mul_accumulate(const tfo_product_plan *, uint64_t *acc, const uint64_t *lhs,
+                                const uint64_t *rhs);
+
 /* AVX-512 port of the reference's vectorised Solinas path (tfhe_ntt_simd.c; bench.py only).
  * Return 1 when the SIMD path ran, 0 when the CPU / build has no AVX-512F+DQ or p is not the
  * Solinas prime (the caller then uses the scalar batch helpers). */

@@ -10,6 +10,7 @@ pub const ERR_CUDA: c_int = 3;
 #[repr(C)] pub struct ntt_b200_plan64 { _p: [u8; 0] }
 #[repr(C)] pub struct ntt_b200_plan32 { _p: [u8; 0] }
 #[repr(C)] pub struct ntt_b200_native_plan { _p: [u8; 0] }
+#[repr(C)] pub struct ntt_b200_product_plan { _p: [u8; 0] }
 
 extern "C" {
     pub fn ntt_b200_last_error() -> *const c_char;
@@ -56,6 +57,17 @@ extern "C" {
 
     pub fn ntt_b200_plan32_fwd_device(plan: *const ntt_b200_plan32, dev: *mut u32, batch: usize, stream: *mut c_void) -> c_int;
     pub fn ntt_b200_plan32_inv_device(plan: *const ntt_b200_plan32, dev: *mut u32, batch: usize, stream: *mut c_void) -> c_int;
+
+    pub fn ntt_b200_product_try_new(n: usize, modulus: u64, factors: *const u64, nfactors: usize, out: *mut *mut ntt_b200_product_plan) -> c_int;
+    pub fn ntt_b200_product_free(plan: *mut ntt_b200_product_plan);
+    pub fn ntt_b200_product_ntt_size(plan: *const ntt_b200_product_plan) -> usize;
+    pub fn ntt_b200_product_modulus(plan: *const ntt_b200_product_plan) -> u64;
+    pub fn ntt_b200_product_ntt_domain_len(plan: *const ntt_b200_product_plan) -> usize;
+    pub fn ntt_b200_product_fwd(plan: *const ntt_b200_product_plan, ntt: *mut u64, ntt_len: usize, standard: *const u64, standard_len: usize) -> c_int;
+    pub fn ntt_b200_product_inv(plan: *const ntt_b200_product_plan, standard: *mut u64, standard_len: usize, ntt: *mut u64, ntt_len: usize, accumulate: c_int) -> c_int;
+    pub fn ntt_b200_product_normalize(plan: *const ntt_b200_product_plan, values: *mut u64, len: usize) -> c_int;
+    pub fn ntt_b200_product_mul_assign_normalize(plan: *const ntt_b200_product_plan, lhs: *mut u64, lhs_len: usize, rhs: *const u64, rhs_len: usize) -> c_int;
+    pub fn ntt_b200_product_mul_accumulate(plan: *const ntt_b200_product_plan, acc: *mut u64, acc_len: usize, lhs: *const u64, lhs_len: usize, rhs: *const u64, rhs_len: usize) -> c_int;
 
     pub fn ntt_b200_native_try_new(kind: c_int, n: usize, out: *mut *mut ntt_b200_native_plan) -> c_int;
     pub fn ntt_b200_native_free(plan: *mut ntt_b200_native_plan);

@@ -5,5 +5,6 @@ pub mod ffi;
 pub mod prime;
 pub mod prime32;
 pub mod prime64;
+pub mod product;
 mod native;
 pub use native::{native128, native32, native64, native_binary128, native_binary32, native_binary64};

@@ -121,6 +121,14 @@ def _load(native=False):
         "tfo_plan64_inv_batch": (None, [P64, vp, sz, i]),
         "tfo_plan32_fwd_batch": (None, [P32, vp, sz, i]),
         "tfo_plan32_inv_batch": (None, [P32, vp, sz, i]),
+        "tfo_product_try_new": (vp, [sz, u64, C.POINTER(u64), sz]),
+        "tfo_product_free": (None, [vp]),
+        "tfo_product_ntt_domain_len": (sz, [vp]),
+        "tfo_product_fwd": (None, [vp, vp, vp, i, u64]),
+        "tfo_product_inv": (None, [vp, vp, vp, i]),
+        "tfo_product_mul_assign_normalize": (None, [vp, vp, vp]),
+        "tfo_product_normalize": (None, [vp, vp]),
+        "tfo_product_mul_accumulate": (None, [vp, vp, vp, vp]),
         "tfo_plan64_fwd_batch_simd": (i, [P64, vp, sz, i]),
         "tfo_plan64_inv_batch_simd": (i, [P64, vp, sz, i]),
     }
@@ -312,3 +320,56 @@ class OracleNativePlan:
         prod = self.value_array()
         self.lib.tfo_native_negacyclic_polymul(self.h, _ptr(prod), _ptr(lhs), _ptr(rhs))
         return prod
+
+
+class OracleProductPlan:
+    """product::Plan restated (product.rs:139-967)."""
+
+    def __init__(self, n, modulus, factors):
+        self.lib = lib()
+        self.n, self.modulus = n, modulus
+        f = (C.c_uint64 * len(factors))(*factors)
+        self.h = self.lib.tfo_product_try_new(n, modulus, f, len(factors))
+        if not self.h:
+            raise ValueError("try_new returned None")
+        self.domain_len = self.lib.tfo_product_ntt_domain_len(self.h)
+
+    @staticmethod
+    def try_new(n, modulus, factors):
+        try:
+            return OracleProductPlan(n, modulus, factors)
+        except ValueError:
+            return None
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.tfo_product_free(self.h)
+            self.h = None
+
+    def fwd(self, standard, bounded=None):
+        st = np.ascontiguousarray(standard, dtype=np.uint64)
+        ntt = np.zeros(self.domain_len, dtype=np.uint64)
+        self.lib.tfo_product_fwd(self.h, _ptr(ntt), _ptr(st), 0 if bounded is None else 1, bounded or 0)
+        return ntt
+
+    def inv(self, ntt, standard=None, accumulate=False):
+        ntt = np.ascontiguousarray(ntt, dtype=np.uint64).copy()
+        st = np.zeros(self.n, dtype=np.uint64) if standard is None else np.ascontiguousarray(standard, dtype=np.uint64).copy()
+        self.lib.tfo_product_inv(self.h, _ptr(st), _ptr(ntt), int(accumulate))
+        return st, ntt
+
+    def mul_assign_normalize(self, lhs, rhs):
+        l = np.ascontiguousarray(lhs, dtype=np.uint64).copy()
+        self.lib.tfo_product_mul_assign_normalize(self.h, _ptr(l), _ptr(np.ascontiguousarray(rhs, dtype=np.uint64)))
+        return l
+
+    def normalize(self, values):
+        v = np.ascontiguousarray(values, dtype=np.uint64).copy()
+        self.lib.tfo_product_normalize(self.h, _ptr(v))
+        return v
+
+    def mul_accumulate(self, acc, lhs, rhs):
+        a = np.ascontiguousarray(acc, dtype=np.uint64).copy()
+        self.lib.tfo_product_mul_accumulate(self.h, _ptr(a), _ptr(np.ascontiguousarray(lhs, dtype=np.uint64)),
+                                            _ptr(np.ascontiguousarray(rhs, dtype=np.uint64)))
+        return a

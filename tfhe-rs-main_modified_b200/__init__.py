@@ -11,6 +11,8 @@ Module, type and method names follow the reference:
     native32 / native64 / native128 / native_binary32 / native_binary64 / native_binary128
                                    Plan32 / Plan52: try_new, ntt_size, ntt_0().., fwd, fwd_binary,
                                    inv, negacyclic_polymul
+    product.Plan (FwdMode, InvMode)   try_new, ntt_size, modulus, ntt_domain_len, fwd, inv,
+                                   normalize, mul_assign_normalize, mul_accumulate
     prime.is_prime64, prime.largest_prime_in_arithmetic_progression64
 
 Host calls take numpy arrays and work in place exactly like the reference's `&mut [T]` slices.
@@ -28,4 +30,5 @@ from ._binding import (  # noqa: F401
 from . import prime32, prime64, prime  # noqa: F401
 from . import native32, native64, native128  # noqa: F401
 from . import native_binary32, native_binary64, native_binary128  # noqa: F401
+from . import product  # noqa: F401
 from . import sharding  # noqa: F401

@@ -73,6 +73,18 @@ SIGNATURES = {
     "ntt_b200_native_negacyclic_polymul_device": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "ntt_b200_native_fwd_device": (_i, [_vp, _vp, _pp, _sz, _i, _vp]),
     "ntt_b200_native_inv_device": (_i, [_vp, _vp, _pp, _sz, _vp]),
+    "ntt_b200_product_try_new": (_i, [_sz, _u64, C.POINTER(_u64), _sz, _pp]),
+    "ntt_b200_product_free": (None, [_vp]),
+    "ntt_b200_product_ntt_size": (_sz, [_vp]),
+    "ntt_b200_product_modulus": (_u64, [_vp]),
+    "ntt_b200_product_ntt_domain_len": (_sz, [_vp]),
+    "ntt_b200_product_fwd": (_i, [_vp, _vp, _sz, _vp, _sz]),
+    "ntt_b200_product_inv": (_i, [_vp, _vp, _sz, _vp, _sz, _i]),
+    "ntt_b200_product_normalize": (_i, [_vp, _vp, _sz]),
+    "ntt_b200_product_mul_assign_normalize": (_i, [_vp, _vp, _sz, _vp, _sz]),
+    "ntt_b200_product_mul_accumulate": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "ntt_b200_product_fwd_device": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "ntt_b200_product_inv_device": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "ntt_b200_is_prime64": (_i, [_u64]),
     "ntt_b200_largest_prime_in_arithmetic_progression64": (_i, [_u64, _u64, _u64, _u64, C.POINTER(_u64)]),
 }
