@@ -238,6 +238,27 @@ int ntt_b200_native_inv_device(const ntt_b200_native_plan *plan, void *value,
                                void *const *residues, size_t batch, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * tfhe's Ntt64View (tfhe/src/core_crypto/commons/math/ntt/ntt64.rs:89-266): the wrapper through
+ * which the NTT-PBS calls prime64::Plan.  `len` = batch * ntt_size() coefficients.
+ *   forward mode 0 forward (:89-95)            1 forward_normalized (:97-108)
+ *                2 forward_from_decomp (:218-238)
+ *                3 forward_from_power_of_two_modulus(width) (:201-214)
+ *   add_backward mode 0 add_backward (:110-131: standard += inv(ntt) modulo p)
+ *                     1 add_backward_on_power_of_two_modulus(width) (:242-266)
+ * `ntt` is left as the reference leaves it (inverse-transformed, and modswitched in mode 1).
+ * ------------------------------------------------------------------------------------------ */
+int ntt_b200_ntt64_forward(const ntt_b200_plan64 *plan, uint64_t *ntt, const uint64_t *standard,
+                           size_t len, int mode, uint32_t width);
+int ntt_b200_ntt64_add_backward(const ntt_b200_plan64 *plan, uint64_t *standard, uint64_t *ntt,
+                                size_t len, int mode, uint32_t width);
+int ntt_b200_ntt64_forward_device(const ntt_b200_plan64 *plan, uint64_t *ntt,
+                                  const uint64_t *standard, size_t batch, int mode, uint32_t width,
+                                  void *stream);
+int ntt_b200_ntt64_add_backward_device(const ntt_b200_plan64 *plan, uint64_t *standard,
+                                       uint64_t *ntt, size_t batch, int mode, uint32_t width,
+                                       void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * product::Plan   (tfhe-ntt/src/product.rs:139-967): negacyclic NTT modulo a product of distinct
  * primes (each < 2^32 prime runs as a prime32 plan, the others as prime64 plans).
  * NTT-domain layout of ONE polynomial = the reference's (product.rs:261-283): the u32 residue

@@ -1732,3 +1732,53 @@ void tfo_product_mul_accumulate(const tfo_product_plan *pl, uint64_t *acc, const
         tfo_plan64_mul_accumulate(pl->p64[j], acc + off64 + (size_t)j * n, lhs + off64 + (size_t)j * n,
                                   rhs + off64 + (size_t)j * n, n);
 }
+
+/* ------------------------------------------------------------------ */
+/* tfhe::core_crypto::commons::math::ntt::ntt64::Ntt64View             */
+/* (tfhe/src/core_crypto/commons/math/ntt/ntt64.rs:89-266): the thin   */
+/* wrapper through which the NTT-PBS calls prime64::Plan               */
+/* ------------------------------------------------------------------ */
+
+/* mode 0: forward (:89-95); 1: forward_normalized (:97-108); 2: forward_from_decomp (:218-238);
+ * 3: forward_from_power_of_two_modulus(width) (:201-214 with the modswitch :165-177) */
+void tfo_ntt64_forward(const tfo_plan64 *pl, uint64_t *ntt, const uint64_t *standard, int mode,
+                       uint32_t width) {
+    size_t n = pl->n;
+    uint64_t p = pl->p;
+    memcpy(ntt, standard, n * sizeof(uint64_t));
+    if (mode == 2) {
+        for (size_t i = 0; i < n; i++)
+            if ((int64_t)ntt[i] < 0) ntt[i] = ntt[i] + p;
+    } else if (mode == 3) {
+        for (size_t i = 0; i < n; i++) {
+            u128 v = (u128)ntt[i] >> (64 - width);
+            ntt[i] = (uint64_t)(((v * (u128)p) + ((u128)1 << (width - 1))) >> width);
+        }
+    }
+    tfo_plan64_fwd(pl, ntt);
+    if (mode == 1) tfo_plan64_normalize(pl, ntt, n);
+}
+
+/* mode 0: add_backward (:110-131, wrapping_add_custom_mod); 1: add_backward_on_power_of_two_modulus
+ * (:242-266 with the modswitch :184-196).  ntt is transformed (and, in mode 1, modswitched) in
+ * place exactly as the reference leaves it. */
+void tfo_ntt64_add_backward(const tfo_plan64 *pl, uint64_t *standard, uint64_t *ntt, int mode,
+                            uint32_t width) {
+    size_t n = pl->n;
+    uint64_t p = pl->p;
+    tfo_plan64_inv(pl, ntt);
+    if (mode == 0) {
+        for (size_t i = 0; i < n; i++) {
+            /* wrapping_add_custom_mod = a - neg(b) (mod p), tfhe .../numeric/unsigned.rs:174-190, :219-225 */
+            uint64_t a = standard[i], b = ntt[i];
+            uint64_t nb = b == 0 ? 0 : p - b;
+            standard[i] = a >= nb ? a - nb : a - nb + p;
+        }
+    } else {
+        for (size_t i = 0; i < n; i++) {
+            u128 x = (((u128)ntt[i]) << width) | ((u128)p >> 1);
+            ntt[i] = (uint64_t)(x / p) << (64 - width);
+            standard[i] = standard[i] + ntt[i];
+        }
+    }
+}

@@ -194,6 +194,15 @@ void tfo_product_normalize(const tfo_product_plan *, uint64_t *values);
 void tfo_product_mul_accumulate(const tfo_product_plan *, uint64_t *acc, const uint64_t *lhs,
                                 const uint64_t *rhs);
 
+/* ---- tfhe Ntt64View (tfhe/src/core_crypto/commons/math/ntt/ntt64.rs:89-266) ----
+ * forward modes: 0 forward, 1 forward_normalized, 2 forward_from_decomp,
+ * 3 forward_from_power_of_two_modulus(width); add_backward modes: 0 add_backward,
+ * 1 add_backward_on_power_of_two_modulus(width) */
+void tfo_ntt64_forward(const tfo_plan64 *, uint64_t *ntt, const uint64_t *standard, int mode,
+                       uint32_t width);
+void tfo_ntt64_add_backward(const tfo_plan64 *, uint64_t *standard, uint64_t *ntt, int mode,
+                            uint32_t width);
+
 /* AVX-512 port of the reference's vectorised Solinas path (tfhe_ntt_simd.c; bench.py only).
  * Return 1 when the SIMD path ran, 0 when the CPU / build has no AVX-512F+DQ or p is not the
  * Solinas prime (the caller then uses the scalar batch helpers). */

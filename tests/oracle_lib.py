@@ -121,6 +121,8 @@ def _load(native=False):
         "tfo_plan64_inv_batch": (None, [P64, vp, sz, i]),
         "tfo_plan32_fwd_batch": (None, [P32, vp, sz, i]),
         "tfo_plan32_inv_batch": (None, [P32, vp, sz, i]),
+        "tfo_ntt64_forward": (None, [P64, vp, vp, i, u32]),
+        "tfo_ntt64_add_backward": (None, [P64, vp, vp, i, u32]),
         "tfo_product_try_new": (vp, [sz, u64, C.POINTER(u64), sz]),
         "tfo_product_free": (None, [vp]),
         "tfo_product_ntt_domain_len": (sz, [vp]),
@@ -226,6 +228,21 @@ class OraclePlan:
         getattr(self.lib, self._pfx + "mul_accumulate")(self.h, _ptr(a), _ptr(l), _ptr(r),
                                                         min(a.size, l.size, r.size))
         return a
+
+    # tfhe Ntt64View wrappers (ntt64.rs:89-266), u64 plans only
+    def ntt64_forward(self, standard, mode=0, width=64):
+        st = np.ascontiguousarray(standard, dtype=np.uint64)
+        out = np.zeros_like(st)
+        for a, b in zip(out.reshape(-1, self.n), st.reshape(-1, self.n)):
+            self.lib.tfo_ntt64_forward(self.h, _ptr(a), _ptr(b), mode, width)
+        return out
+
+    def ntt64_add_backward(self, standard, ntt, mode=0, width=64):
+        st = np.ascontiguousarray(standard, dtype=np.uint64).copy()
+        nt = np.ascontiguousarray(ntt, dtype=np.uint64).copy()
+        for a, b in zip(st.reshape(-1, self.n), nt.reshape(-1, self.n)):
+            self.lib.tfo_ntt64_add_backward(self.h, _ptr(a), _ptr(b), mode, width)
+        return st, nt
 
     def fwd_batch_inplace(self, buf, threads, simd=False):
         """Returns "avx512" when the vectorised Solinas port ran, else "scalar"."""

@@ -31,4 +31,5 @@ from . import prime32, prime64, prime  # noqa: F401
 from . import native32, native64, native128  # noqa: F401
 from . import native_binary32, native_binary64, native_binary128  # noqa: F401
 from . import product  # noqa: F401
+from . import ntt64  # noqa: F401
 from . import sharding  # noqa: F401

@@ -73,6 +73,10 @@ SIGNATURES = {
     "ntt_b200_native_negacyclic_polymul_device": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "ntt_b200_native_fwd_device": (_i, [_vp, _vp, _pp, _sz, _i, _vp]),
     "ntt_b200_native_inv_device": (_i, [_vp, _vp, _pp, _sz, _vp]),
+    "ntt_b200_ntt64_forward": (_i, [_vp, _vp, _vp, _sz, _i, _u32]),
+    "ntt_b200_ntt64_add_backward": (_i, [_vp, _vp, _vp, _sz, _i, _u32]),
+    "ntt_b200_ntt64_forward_device": (_i, [_vp, _vp, _vp, _sz, _i, _u32, _vp]),
+    "ntt_b200_ntt64_add_backward_device": (_i, [_vp, _vp, _vp, _sz, _i, _u32, _vp]),
     "ntt_b200_product_try_new": (_i, [_sz, _u64, C.POINTER(_u64), _sz, _pp]),
     "ntt_b200_product_free": (None, [_vp]),
     "ntt_b200_product_ntt_size": (_sz, [_vp]),

@@ -230,6 +230,80 @@ int dev_pointwise_check(size_t len, size_t sub_len) {
 
 }  // namespace
 
+// ---- tfhe Ntt64View on top of a prime64 plan (tfhe .../math/ntt/ntt64.rs:89-266) ------------
+// Element-wise pre / post maps around the batched transforms.
+// forward modes: 0 forward, 1 forward_normalized, 2 forward_from_decomp,
+//                3 forward_from_power_of_two_modulus(width)
+__global__ void ntt64_premap_kernel(uint64_t* __restrict__ ntt, const uint64_t* __restrict__ standard,
+                                    size_t total, int mode, unsigned width, uint64_t p) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t v = standard[i];
+        if (mode == 2) {  // small signed digits -> [0,p)   (ntt64.rs:229-236)
+            if ((int64_t)v < 0) v += p;
+        } else if (mode == 3) {  // modswitch 2^width -> p, rounded   (ntt64.rs:165-177)
+            unsigned __int128 x = (unsigned __int128)(v >> (64 - width)) * p +
+                                  ((unsigned __int128)1 << (width - 1));
+            v = (uint64_t)(x >> width);
+        }
+        ntt[i] = v;
+    }
+}
+// add_backward modes: 0 add modulo p (ntt64.rs:110-131), 1 modswitch p -> 2^width, then wrapping
+// add (ntt64.rs:184-196, :242-266; the modswitched values are left in `ntt` like the reference)
+__global__ void ntt64_postmap_kernel(uint64_t* __restrict__ standard, uint64_t* __restrict__ ntt,
+                                     size_t total, int mode, unsigned width, uint64_t p) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t a = standard[i], b = ntt[i];
+        if (mode == 0) {
+            // wrapping_add_custom_mod: a - neg(b) mod p (tfhe .../numeric/unsigned.rs:174-190)
+            uint64_t nb = b == 0 ? 0 : p - b;
+            standard[i] = a >= nb ? a - nb : a - nb + p;
+        } else {
+            unsigned __int128 x = ((unsigned __int128)b << width) | ((unsigned __int128)p >> 1);
+            uint64_t m = (uint64_t)(x / p) << (64 - width);
+            ntt[i] = m;
+            standard[i] = a + m;
+        }
+    }
+}
+
+int ntt64_forward_dev(const PrimePlan* pl, uint64_t* ntt, const uint64_t* standard, size_t batch, int mode,
+                      unsigned width, cudaStream_t st) {
+    if (mode < 0 || mode > 3 || (mode == 3 && (width == 0 || width > 64))) return NTT_B200_ERR_ARG;
+    return guarded([&] {
+        if (!batch) return NTT_B200_OK;
+        DeviceGuard g(pl->device);
+        size_t total = batch * pl->n;
+        if (mode <= 1) {
+            if (ntt != standard)
+                NTT_CUDA_CHECK(cudaMemcpyAsync(ntt, standard, total * 8, cudaMemcpyDeviceToDevice, st));
+        } else {
+            unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+            ntt64_premap_kernel<<<blocks, 256, 0, st>>>(ntt, standard, total, mode, width, pl->p);
+            NTT_CUDA_CHECK(cudaGetLastError());
+        }
+        pl->fwd(ntt, batch, st);
+        if (mode == 1) pl->normalize(ntt, total, st);
+        return NTT_B200_OK;
+    });
+}
+int ntt64_add_backward_dev(const PrimePlan* pl, uint64_t* standard, uint64_t* ntt, size_t batch, int mode,
+                           unsigned width, cudaStream_t st) {
+    if (mode < 0 || mode > 1 || (mode == 1 && (width == 0 || width > 64))) return NTT_B200_ERR_ARG;
+    return guarded([&] {
+        if (!batch) return NTT_B200_OK;
+        DeviceGuard g(pl->device);
+        size_t total = batch * pl->n;
+        pl->inv(ntt, batch, st);
+        unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+        ntt64_postmap_kernel<<<blocks, 256, 0, st>>>(standard, ntt, total, mode, width, pl->p);
+        NTT_CUDA_CHECK(cudaGetLastError());
+        return NTT_B200_OK;
+    });
+}
+
 // The 32- and 64-bit families share every code path; only the handle and element types differ.
 #define NTT_DEFINE_PRIME_API(SFX, ELEM, MAKE)                                                      \
     extern "C" {                                                                                   \
@@ -389,6 +463,74 @@ int dev_pointwise_check(size_t len, size_t sub_len) {
             return NTT_B200_OK;                                                                    \
         });                                                                                        \
     }
+extern "C" {
+int ntt_b200_ntt64_forward_device(const ntt_b200_plan64* plan, uint64_t* ntt, const uint64_t* standard,
+                                  size_t batch, int mode, uint32_t width, void* stream) {
+    if (!plan || (batch && (!ntt || !standard))) return NTT_B200_ERR_ARG;
+    return ntt64_forward_dev(plan->impl.get(), ntt, standard, batch, mode, width, (cudaStream_t)stream);
+}
+int ntt_b200_ntt64_add_backward_device(const ntt_b200_plan64* plan, uint64_t* standard, uint64_t* ntt,
+                                       size_t batch, int mode, uint32_t width, void* stream) {
+    if (!plan || (batch && (!ntt || !standard))) return NTT_B200_ERR_ARG;
+    return ntt64_add_backward_dev(plan->impl.get(), standard, ntt, batch, mode, width, (cudaStream_t)stream);
+}
+// host forms: `batch` polynomials each
+int ntt_b200_ntt64_forward(const ntt_b200_plan64* plan, uint64_t* ntt, const uint64_t* standard, size_t len,
+                           int mode, uint32_t width) {
+    if (!plan || !ntt || !standard) return NTT_B200_ERR_ARG;
+    size_t n = plan->impl->n;
+    if (len == 0 || len % n) return NTT_B200_ERR_LEN;  // izip_eq! / copy_from_slice panic on a mismatch
+    int rc = NTT_B200_OK;
+    int g = guarded([&] {
+        DeviceGuard dg(plan->impl->device);
+        keep_pool_cached(plan->impl->device);
+        cudaStream_t st;
+        NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        uint64_t *ds = nullptr, *dn = nullptr;
+        NTT_CUDA_CHECK(cudaMallocAsync(&ds, len * 8, st));
+        NTT_CUDA_CHECK(cudaMallocAsync(&dn, len * 8, st));
+        NTT_CUDA_CHECK(cudaMemcpyAsync(ds, standard, len * 8, cudaMemcpyHostToDevice, st));
+        rc = ntt64_forward_dev(plan->impl.get(), dn, ds, len / n, mode, width, st);
+        NTT_CUDA_CHECK(cudaMemcpyAsync(ntt, dn, len * 8, cudaMemcpyDeviceToHost, st));
+        cudaFreeAsync(ds, st);
+        cudaFreeAsync(dn, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+        NTT_CUDA_CHECK(e);
+        return NTT_B200_OK;
+    });
+    return g != NTT_B200_OK ? g : rc;
+}
+int ntt_b200_ntt64_add_backward(const ntt_b200_plan64* plan, uint64_t* standard, uint64_t* ntt, size_t len,
+                                int mode, uint32_t width) {
+    if (!plan || !ntt || !standard) return NTT_B200_ERR_ARG;
+    size_t n = plan->impl->n;
+    if (len == 0 || len % n) return NTT_B200_ERR_LEN;
+    int rc = NTT_B200_OK;
+    int g = guarded([&] {
+        DeviceGuard dg(plan->impl->device);
+        keep_pool_cached(plan->impl->device);
+        cudaStream_t st;
+        NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        uint64_t *ds = nullptr, *dn = nullptr;
+        NTT_CUDA_CHECK(cudaMallocAsync(&ds, len * 8, st));
+        NTT_CUDA_CHECK(cudaMallocAsync(&dn, len * 8, st));
+        NTT_CUDA_CHECK(cudaMemcpyAsync(ds, standard, len * 8, cudaMemcpyHostToDevice, st));
+        NTT_CUDA_CHECK(cudaMemcpyAsync(dn, ntt, len * 8, cudaMemcpyHostToDevice, st));
+        rc = ntt64_add_backward_dev(plan->impl.get(), ds, dn, len / n, mode, width, st);
+        NTT_CUDA_CHECK(cudaMemcpyAsync(standard, ds, len * 8, cudaMemcpyDeviceToHost, st));
+        NTT_CUDA_CHECK(cudaMemcpyAsync(ntt, dn, len * 8, cudaMemcpyDeviceToHost, st));
+        cudaFreeAsync(ds, st);
+        cudaFreeAsync(dn, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+        NTT_CUDA_CHECK(e);
+        return NTT_B200_OK;
+    });
+    return g != NTT_B200_OK ? g : rc;
+}
+}
+
 NTT_DEFINE_EXT(64, uint64_t)
 NTT_DEFINE_EXT(32, uint32_t)
 
