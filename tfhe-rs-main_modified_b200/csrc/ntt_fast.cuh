@@ -48,6 +48,11 @@ NTT_DEVINL constexpr unsigned pad_index(unsigned a) {
     return sizeof(T) == 8 ? a + 2u * (a >> 4) : a + 4u * (a >> 5);
 }
 
+// Tuple addressing.  A radix-8 tuple's base is i*(8*t2) + j with j < t2; when 8*t2 is a multiple of
+// the padding period (16 u64 / 32 u32 elements) the padding of base + k*t2 splits into pad(base)
+// plus a compile-time constant, so the eight accesses of a pass use immediate offsets instead of
+// per-element index arithmetic (`const_off` in the pass loops below).
+
 template <class T>
 NTT_DEVINL T ldg_tw(const T* p) {
     return __ldg(p);
@@ -181,10 +186,14 @@ NTT_DEVINL void fwd_from_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsi
         const int log_t2 = LOGN - stage - 3;
         unsigned i = t >> log_t2, j = t & ((1u << log_t2) - 1u);
         unsigned base = (i << (log_t2 + 3)) + j;
+        // (pass and k are unrolled, so these fold to constants)
+        const bool const_off = ((8u << log_t2) % (128u / sizeof(T))) == 0;
+        const unsigned pbase = pad_index<T>(base);
         if (pass > 0) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                unsigned off = pad_index<T>(base + ((unsigned)k << log_t2));
+                unsigned off = const_off ? pbase + pad_index<T>((unsigned)k << log_t2)
+                                         : pad_index<T>(base + ((unsigned)k << log_t2));
 #pragma unroll
                 for (int pp = 0; pp < PPT; ++pp) x[pp][k] = s[pp * S::kPaddedElems + off];
             }
@@ -192,7 +201,8 @@ NTT_DEVINL void fwd_from_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsi
         tuple_ro<A, 3, 0, false, false, PPT>(x, tw, sub.base(stage) + i, c);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            unsigned off = pad_index<T>(base + ((unsigned)k << log_t2));
+            unsigned off = const_off ? pbase + pad_index<T>((unsigned)k << log_t2)
+                                         : pad_index<T>(base + ((unsigned)k << log_t2));
 #pragma unroll
             for (int pp = 0; pp < PPT; ++pp) s[pp * S::kPaddedElems + off] = x[pp][k];
         }
@@ -220,10 +230,14 @@ NTT_DEVINL void inv_to_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsign
         const int log_t2 = LOGN - stage - 3;
         unsigned i = t >> log_t2, j = t & ((1u << log_t2) - 1u);
         unsigned base = (i << (log_t2 + 3)) + j;
+        // (pass and k are unrolled, so these fold to constants)
+        const bool const_off = ((8u << log_t2) % (128u / sizeof(T))) == 0;
+        const unsigned pbase = pad_index<T>(base);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            unsigned off = pad_index<T>(base + ((unsigned)k << log_t2));
+            unsigned off = const_off ? pbase + pad_index<T>((unsigned)k << log_t2)
+                                         : pad_index<T>(base + ((unsigned)k << log_t2));
 #pragma unroll
             for (int pp = 0; pp < PPT; ++pp) x[pp][k] = s[pp * S::kPaddedElems + off];
         }
@@ -231,7 +245,8 @@ NTT_DEVINL void inv_to_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsign
         if (pass > 0) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                unsigned off = pad_index<T>(base + ((unsigned)k << log_t2));
+                unsigned off = const_off ? pbase + pad_index<T>((unsigned)k << log_t2)
+                                         : pad_index<T>(base + ((unsigned)k << log_t2));
 #pragma unroll
                 for (int pp = 0; pp < PPT; ++pp) s[pp * S::kPaddedElems + off] = x[pp][k];
             }
