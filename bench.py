@@ -28,7 +28,7 @@ N = 2048
 SOLINAS_P = (1 << 64) - (1 << 32) + 1
 BATCH_PER_GPU = 65536          # 65536 * 16 KiB = 1 GiB per GPU: far beyond the 126 MB L2
 ALG_BYTES_PER_NTT = 2 * N * 8  # one in-place NTT reads and writes each coefficient once
-E2E_BATCH = 16384              # host-buffer leg: 256 MiB in + 256 MiB out per step
+E2E_BATCH = 32768              # host-buffer leg: 512 MiB in + 512 MiB out per step
 NCU_TRAFFIC_PER_LAUNCH = 2.097e9  # measured by ncu --set full for one launch of this workload (see profiles/)
 METRIC = "fwd+inv NTTs/sec, N=2048 u64 prime, batched"
 UNIT = "NTT/s"
@@ -269,7 +269,7 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = 2.0 * eb * world * e2e_steps / float(te.item())
     e2e_bytes = eb * N * 8  # per step and direction
-    e2e_launches = e2e_steps * ((eb * N * 8 + (32 << 20) - 1) // (32 << 20))
+    e2e_launches = e2e_steps * ((eb * N * 8 + (16 << 20) - 1) // (16 << 20))
 
     if rank == 0:
         peaks, which = measured_peaks()
@@ -303,7 +303,7 @@ def run_gpu(args):
             threads = os.cpu_count() or 1
             try:
                 rate, dt = cpu_leg(2048, 1, threads)
-                reps = int(max(1, min(400, 12.0 / max(dt, 1e-3))))
+                reps = int(max(1, min(4000, 12.0 / max(dt, 1e-3))))
                 rate, dt = cpu_leg(2048, reps, threads)
                 line["cpu_baseline"] = {
                     "value": rate, "unit": UNIT, "cores": threads, "kind": "port", "isa": CPU_ISA[0], "note": CPU_NOTE,

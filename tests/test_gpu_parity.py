@@ -237,13 +237,13 @@ def test_fwd_mac_inv_batch_host(T):
     n, p = 1024, SOLINAS_P
     gp, op = plan_pair(T, 64, n, p)
     rng = np.random.default_rng(9)
-    batch = 9000  # > one staging chunk (32 MiB / 8 KiB = 4096 polynomials), ragged tail
+    batch = 9000  # several staging chunks (16 MiB / 8 KiB = 2048 polynomials each), ragged tail
     lhs = rand_below(rng, p, (batch, n), np.uint64)
     ggsw = rand_below(rng, p, (4, n), np.uint64)
     acc = rand_below(rng, p, (2, n), np.uint64)
     out = np.zeros_like(lhs)
     gp.fwd_mac_inv_batch(out, lhs, ggsw, acc)
-    for b in (0, 1, 4095, 4096, 4097, 8999):
+    for b in (0, 1, 2047, 2048, 4095, 4096, 4097, 8191, 8192, 8999):
         want = op.inv(op.mul_accumulate(acc[b % 2], op.fwd(lhs[b]), ggsw[b % 4]))
         assert (out[b] == want).all(), b
     # full-size operands, in place

@@ -46,7 +46,8 @@ int ntt_b200_largest_prime_in_arithmetic_progression64(uint64_t factor, uint64_t
 namespace {
 
 // ---- host-pointer paths: stage through device memory, chunked and double-buffered ---------
-constexpr size_t kChunkBytes = size_t(32) << 20;
+constexpr size_t kChunkBytes = size_t(16) << 20;
+constexpr int kStreams = 4;  // H2D, kernel and D2H of successive chunks overlap across these
 
 struct Stage {
     cudaStream_t st = nullptr;
@@ -62,8 +63,8 @@ int host_transform(const PrimePlan* pl, void* host, size_t batch, bool inverse) 
         size_t chunk_polys = std::max<size_t>(1, kChunkBytes / poly_bytes);
         chunk_polys = std::min(chunk_polys, batch);
         size_t nchunks = (batch + chunk_polys - 1) / chunk_polys;
-        int ns = (int)std::min<size_t>(3, nchunks);
-        Stage sg[3];
+        int ns = (int)std::min<size_t>(kStreams, nchunks);
+        Stage sg[kStreams];
         for (int i = 0; i < ns; ++i) {
             NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&sg[i].st, cudaStreamNonBlocking));
             NTT_CUDA_CHECK(cudaMallocAsync(&sg[i].d, chunk_polys * poly_bytes, sg[i].st));
@@ -148,9 +149,9 @@ int host_fwd_mac_inv(const PrimePlan* pl, void* out, const void* lhs, const void
         chunk = std::max(period, chunk / period * period);
         chunk = std::min(chunk, batch);
         size_t nchunks = (batch + chunk - 1) / chunk;
-        int ns = (int)std::min<size_t>(3, nchunks);
-        cudaStream_t st[3] = {};
-        void *d_io[3] = {}, *d_rhs[3] = {}, *d_acc[3] = {};
+        int ns = (int)std::min<size_t>(kStreams, nchunks);
+        cudaStream_t st[kStreams] = {};
+        void *d_io[kStreams] = {}, *d_rhs[kStreams] = {}, *d_acc[kStreams] = {};
         void *d_rhs_shared = nullptr, *d_acc_shared = nullptr;
         cudaEvent_t shared_ready = nullptr;
         for (int i = 0; i < ns; ++i) {
