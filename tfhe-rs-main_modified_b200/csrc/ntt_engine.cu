@@ -177,13 +177,9 @@ struct PlanImpl final : PrimePlan {
         unsigned threads = (unsigned)std::min<size_t>(512, std::max<size_t>(64, elems / 8));
         size_t smem = elems * sizeof(T);
         auto kern = ntt_rows_kernel<A, INV>;
-        if (smem > 48 * 1024) {
-            static std::once_flag once[2];
-            // the attribute is per function per device; set it every time on a cheap path
+        if (smem > 48 * 1024)  // the attribute is per function and per device; setting it is cheap
             NTT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(size_t(1) << kMaxLogRow) * (int)sizeof(T)));
-            (void)once;
-        }
         size_t ctas = (num_rows + rows_per_cta - 1) / rows_per_cta;
         kern<<<(unsigned)ctas, threads, smem, st>>>(data, num_rows, log_row, depth,
                                                     INV ? d_inv.get() : d_fwd.get(), ctx,
@@ -292,7 +288,7 @@ struct PlanImpl final : PrimePlan {
                                 d_inv.get(), ctx, st))
             return;
         // generic composition: transform a copy of the inputs, accumulate row by row, invert
-        size_t in_total = batch * rows * n, out_total = batch * cols * n;
+        size_t in_total = batch * rows * n;
         T *tmp = nullptr, *row = nullptr, *acc = nullptr;
         NTT_CUDA_CHECK(cudaMallocAsync(&tmp, in_total * sizeof(T), st));
         NTT_CUDA_CHECK(cudaMallocAsync(&row, batch * n * sizeof(T), st));
@@ -311,7 +307,6 @@ struct PlanImpl final : PrimePlan {
             NTT_CUDA_CHECK(cudaMemcpy2DAsync(static_cast<T*>(out) + (size_t)cc * n, cols * n * sizeof(T), acc,
                                              n * sizeof(T), n * sizeof(T), batch, cudaMemcpyDeviceToDevice, st));
         }
-        (void)out_total;
         NTT_CUDA_CHECK(cudaFreeAsync(tmp, st));
         NTT_CUDA_CHECK(cudaFreeAsync(row, st));
         NTT_CUDA_CHECK(cudaFreeAsync(acc, st));

@@ -34,9 +34,9 @@ struct FastShape {
     static constexpr int kPaddedElems = (1 << LOGN) + ((1 << LOGN) >> 3);  // 16 B per 128 B
 };
 
-// Resident CTAs per SM the register allocator is asked to allow: 1024 threads per SM (64
-// registers per thread), which every family reaches without spilling except where noted in
-// FastMinBlocks specialisations.
+// Resident CTAs per SM the register allocator is asked to allow: 1024 threads per SM, i.e. 64
+// registers per thread.  Every family fits (the 64-bit ones with at most a few spilled words);
+// four 256-thread CTAs per SM hide the load phase of one CTA behind the butterflies of the others.
 template <class A, int THREADS>
 struct FastMinBlocks {
     static constexpr int value = 1024 / THREADS > 0 ? 1024 / THREADS : 1;
