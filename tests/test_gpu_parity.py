@@ -337,3 +337,35 @@ def test_native_batch(T):
     gp.negacyclic_polymul_batch(prod, lhs, rhs)
     for b in range(batch):
         assert (prod[b] == op.negacyclic_polymul(lhs[b], rhs[b])).all()
+
+
+def test_shared_plan_is_reentrant(T):
+    """Plans are Send + Sync in the reference (one Arc<Plan> shared by rayon workers,
+    tfhe ntt64.rs:26-31): concurrent calls on one plan must not interfere."""
+    import threading
+    n, p = 1024, SOLINAS_P
+    gp, op = plan_pair(T, 64, n, p)
+    rng = np.random.default_rng(11)
+    xs = [rand_below(rng, p, (17, n), np.uint64) for _ in range(8)]
+    wants = [op.inv(op.fwd(x)) for x in xs]
+    errors = []
+
+    def worker(i):
+        try:
+            for _ in range(5):
+                y = xs[i].copy()
+                gp.fwd_batch(y)
+                one = xs[i][0].copy()
+                gp.fwd(one)
+                assert (one == y[0]).all()
+                gp.inv_batch(y)
+                assert (y == wants[i]).all()
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
