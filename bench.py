@@ -286,8 +286,8 @@ def run_gpu(args):
                        "parallelism": "batch sharded over %d GPU(s), no collective" % world},
             "roofline": {"bound": "hbm", "kernel": "ntt %s (N=2048 Solinas)" % dom, "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm, "traffic": NCU_TRAFFIC_PER_LAUNCH, "peak_source": which,
-                         "traffic_source": "profiles/r01_ncu_full_solinas2048_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
-                         "limiter": "INT32 ALU pipe (ncu: sm__inst_executed_pipe_alu 76-80 % of peak, DRAM 23 %): "
+                         "traffic_source": "profiles/r01_ncu_full_solinas2048_v3_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                         "limiter": "integer instruction throughput (ncu: ALU pipe 68-73 %, FMA-heavy pipe 68-71 %, DRAM 24 %): "
                                     "the Solinas butterfly is carry-chain adds, see DESIGN.md section 5",
                          "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                          "algorithmic_bytes_per_launch": batch * ALG_BYTES_PER_NTT},
