@@ -259,6 +259,76 @@ int ntt_b200_ntt64_add_backward_device(const ntt_b200_plan64 *plan, uint64_t *st
                                        void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * NTT programmable bootstrap, the caller of the hot path:
+ *   tfhe/src/core_crypto/algorithms/lwe_programmable_bootstrapping/ntt64_pbs.rs       "classic":
+ *       the ciphertext modulus is the NTT prime (SignedDecomposerNonNative, custom-mod rotations)
+ *   tfhe/src/core_crypto/algorithms/lwe_programmable_bootstrapping/ntt64_bnf_pbs.rs   "bnf":
+ *       ciphertexts live modulo 2^width (MSB aligned), modswitched around each NTT
+ * Containers are the reference's flat ones: lwe [n_lwe+1] (mask, body), glwe / lut / accumulator
+ * [(k+1)*N], NTT bootstrap key [n_lwe][level][k+1][k+1][N] with the first level slice = level l
+ * (entities/ntt_ggsw_ciphertext.rs:176-190).  New: every call takes `batch` ciphertexts.
+ * `path`: 0 = fused kernel when the shape has one, else composed; 1 = fused only (ERR_CUDA when
+ * there is none); 2 = composed only.  All paths give identical bits.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ntt_b200_bsk ntt_b200_bsk;
+/* NttLweBootstrapKey::from_container   entities/ntt_lwe_bootstrap_key.rs:68-110; copies the
+ * NTT-domain container to the plan's device.  base_log * level must be < 64. */
+int ntt_b200_bsk_new(const ntt_b200_plan64 *plan, const uint64_t *ntt_bsk, size_t n_lwe,
+                     size_t glwe_size, uint32_t base_log, uint32_t level, ntt_b200_bsk **out);
+/* convert_standard_lwe_bootstrap_key_to_ntt64   lwe_bootstrap_key_conversion.rs:294-363, into a
+ * device-resident key.  input_width = 0: the standard key is modulo the NTT prime (ntt.forward);
+ * else log2 of its power-of-two modulus (forward_from_power_of_two_modulus).  normalize != 0 =
+ * NttLweBootstrapKeyOption::Normalize. */
+int ntt_b200_bsk_convert_new(const ntt_b200_plan64 *plan, const uint64_t *standard_bsk, size_t n_lwe,
+                             size_t glwe_size, uint32_t base_log, uint32_t level,
+                             uint32_t input_width, int normalize, ntt_b200_bsk **out);
+/* the same conversion host to host (`len` coefficients, a multiple of ntt_size()) */
+int ntt_b200_convert_standard_lwe_bootstrap_key_to_ntt64(const ntt_b200_plan64 *plan,
+                                                         const uint64_t *input, uint64_t *output,
+                                                         size_t len, uint32_t input_width,
+                                                         int normalize);
+void ntt_b200_bsk_free(ntt_b200_bsk *key);
+size_t ntt_b200_bsk_input_lwe_dimension(const ntt_b200_bsk *key);         /* ntt_lwe_bootstrap_key.rs:113 */
+size_t ntt_b200_bsk_glwe_size(const ntt_b200_bsk *key);                   /* :123 */
+size_t ntt_b200_bsk_polynomial_size(const ntt_b200_bsk *key);             /* :118 */
+uint32_t ntt_b200_bsk_decomposition_base_log(const ntt_b200_bsk *key);    /* :128 */
+uint32_t ntt_b200_bsk_decomposition_level_count(const ntt_b200_bsk *key); /* :133 */
+const uint64_t *ntt_b200_bsk_device_data(const ntt_b200_bsk *key);        /* device pointer */
+/* copies the NTT-domain key back (len = n_lwe * level * (k+1)^2 * N) */
+int ntt_b200_bsk_read(const ntt_b200_bsk *key, uint64_t *out, size_t len);
+/* blind_rotate_ntt64_assign(input, lut, bsk)   ntt64_pbs.rs:175-286
+ * lwe [batch][n_lwe+1]; lut [batch][(k+1)N] is rotated in place */
+int ntt_b200_blind_rotate_ntt64_assign(const ntt_b200_bsk *key, const uint64_t *lwe, uint64_t *lut,
+                                       size_t batch, int path);
+/* blind_rotate_ntt64_bnf_assign(msed_input, lut, bsk)   ntt64_bnf_pbs.rs:174-276
+ * msed [batch][n_lwe+1]: the modulus-switched mask and body (each in [0, 2N)) */
+int ntt_b200_blind_rotate_ntt64_bnf_assign(const ntt_b200_bsk *key, uint32_t width,
+                                           const uint64_t *msed, uint64_t *lut, size_t batch,
+                                           int path);
+/* programmable_bootstrap_ntt64_lwe_ciphertext(input, output, accumulator, bsk)  ntt64_pbs.rs:439-538
+ * lwe_in [batch][n_lwe+1], lwe_out [batch][k*N+1], accumulator [acc_count][(k+1)N] with
+ * acc_count = 1 (one LUT for the whole batch) or batch (ERR_LEN otherwise) */
+int ntt_b200_programmable_bootstrap_ntt64(const ntt_b200_bsk *key, const uint64_t *lwe_in,
+                                          uint64_t *lwe_out, const uint64_t *accumulator,
+                                          size_t acc_count, size_t batch, int path);
+/* programmable_bootstrap_ntt64_bnf_lwe_ciphertext   ntt64_bnf_pbs.rs:428-539 */
+int ntt_b200_programmable_bootstrap_ntt64_bnf(const ntt_b200_bsk *key, uint32_t width,
+                                              const uint64_t *lwe_in, uint64_t *lwe_out,
+                                              const uint64_t *accumulator, size_t acc_count,
+                                              size_t batch, int path);
+/* device-resident forms (pointers on the key's device, asynchronous on `stream`).
+ * lwe_is_switched: bnf only, `lwe` already holds modulus-switched values.
+ * acc_out [batch][(k+1)N] must not alias lut. */
+int ntt_b200_blind_rotate_ntt64_device(const ntt_b200_bsk *key, int bnf, uint32_t width,
+                                       const uint64_t *lwe, int lwe_is_switched, const uint64_t *lut,
+                                       size_t lut_count, uint64_t *acc_out, size_t batch, int path,
+                                       void *stream);
+/* extract_lwe_sample_from_glwe_ciphertext(glwe, lwe, MonomialDegree(0))
+ * glwe_sample_extraction.rs:89-164; glwe [batch][(k+1)N] -> lwe_out [batch][k*N+1] */
+int ntt_b200_extract_lwe_sample_device(const ntt_b200_bsk *key, int bnf, const uint64_t *glwe,
+                                       uint64_t *lwe_out, size_t batch, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * product::Plan   (tfhe-ntt/src/product.rs:139-967): negacyclic NTT modulo a product of distinct
  * primes (each < 2^32 prime runs as a prime32 plan, the others as prime64 plans).
  * NTT-domain layout of ONE polynomial = the reference's (product.rs:261-283): the u32 residue

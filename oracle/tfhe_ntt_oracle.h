@@ -203,6 +203,48 @@ void tfo_ntt64_forward(const tfo_plan64 *, uint64_t *ntt, const uint64_t *standa
 void tfo_ntt64_add_backward(const tfo_plan64 *, uint64_t *standard, uint64_t *ntt, int mode,
                             uint32_t width);
 
+/* ---- NTT programmable bootstrap (tfhe_ntt_pbs_oracle.c): tfhe ntt64_pbs.rs / ntt64_bnf_pbs.rs ----
+ * lwe [n_lwe+1]; glwe / lut / accumulator [(k+1)*N]; bsk [n_lwe][l][k+1][k+1][N] (NTT domain).
+ * "modulus == 0" selects the native 2^64 wrapping arithmetic. */
+uint64_t tfo_pbs_modulus_switch_non_native(uint64_t input, uint32_t log2_poly_size, uint64_t modulus);
+uint64_t tfo_modulus_switch(uint64_t input, uint32_t log_modulus);
+void tfo_monomial_mul_assign(uint64_t *poly, size_t n, size_t degree, uint64_t modulus);
+void tfo_monomial_div_assign(uint64_t *poly, size_t n, size_t degree, uint64_t modulus);
+uint64_t tfo_closest_representable_non_native(uint64_t input, uint32_t base_log, uint32_t level,
+                                              uint64_t modulus);
+uint64_t tfo_init_decomposer_state_native(uint64_t input, uint32_t base_log, uint32_t level);
+void tfo_decomp_non_native_init(const uint64_t *input, size_t len, uint32_t base_log, uint32_t level,
+                                uint64_t modulus, uint64_t *states, uint8_t *signs);
+void tfo_decomp_non_native_next(uint64_t *states, const uint8_t *signs, size_t len, uint32_t base_log,
+                                uint64_t modulus, uint64_t *term);
+void tfo_decomp_native_init(const uint64_t *input, size_t len, uint32_t base_log, uint32_t level,
+                            uint64_t *states);
+void tfo_decomp_native_next(uint64_t *states, size_t len, uint32_t base_log, uint64_t *term);
+void tfo_add_external_product_ntt64_assign(const tfo_plan64 *, uint64_t *out, const uint64_t *ggsw,
+                                           const uint64_t *glwe, size_t glwe_size, uint32_t base_log,
+                                           uint32_t level, int bnf, uint32_t width);
+void tfo_cmux_ntt64_assign(const tfo_plan64 *, uint64_t *ct0, uint64_t *ct1, const uint64_t *ggsw,
+                           size_t glwe_size, uint32_t base_log, uint32_t level, int bnf, uint32_t width);
+void tfo_blind_rotate_ntt64_assign(const tfo_plan64 *, const uint64_t *bsk, size_t n_lwe,
+                                   size_t glwe_size, uint32_t base_log, uint32_t level,
+                                   const uint64_t *lwe, uint64_t *lut);
+void tfo_blind_rotate_ntt64_bnf_assign(const tfo_plan64 *, const uint64_t *bsk, size_t n_lwe,
+                                       size_t glwe_size, uint32_t base_log, uint32_t level,
+                                       uint32_t width, const uint64_t *msed, uint64_t *lut);
+void tfo_extract_lwe_sample(const uint64_t *glwe, size_t glwe_size, size_t n, size_t nth,
+                            uint64_t modulus, uint64_t *lwe_out);
+void tfo_programmable_bootstrap_ntt64(const tfo_plan64 *, const uint64_t *bsk, size_t n_lwe,
+                                      size_t glwe_size, uint32_t base_log, uint32_t level,
+                                      const uint64_t *lwe_in, uint64_t *lwe_out,
+                                      const uint64_t *accumulator);
+void tfo_programmable_bootstrap_ntt64_bnf(const tfo_plan64 *, const uint64_t *bsk, size_t n_lwe,
+                                          size_t glwe_size, uint32_t base_log, uint32_t level,
+                                          uint32_t width, const uint64_t *lwe_in, uint64_t *lwe_out,
+                                          const uint64_t *accumulator);
+void tfo_convert_standard_lwe_bootstrap_key_to_ntt64(const tfo_plan64 *, const uint64_t *input,
+                                                     uint64_t *output, size_t poly_count,
+                                                     uint32_t input_width, int normalize);
+
 /* AVX-512 port of the reference's vectorised Solinas path (tfhe_ntt_simd.c; bench.py only).
  * Return 1 when the SIMD path ran, 0 when the CPU / build has no AVX-512F+DQ or p is not the
  * Solinas prime (the caller then uses the scalar batch helpers). */

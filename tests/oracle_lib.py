@@ -33,7 +33,8 @@ def build(native=False):
     target = "native" if native else "all"
     name = "libtfhe_ntt_oracle_native.so" if native else "libtfhe_ntt_oracle.so"
     so = os.path.join(_ORACLE_DIR, name)
-    src = [os.path.join(_ORACLE_DIR, f) for f in ("tfhe_ntt_oracle.c", "tfhe_ntt_simd.c", "tfhe_ntt_oracle.h")]
+    src = [os.path.join(_ORACLE_DIR, f) for f in ("tfhe_ntt_oracle.c", "tfhe_ntt_simd.c", "tfhe_ntt_pbs_oracle.c",
+                                                 "tfhe_ntt_oracle.h")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src)
     # the -march=native build is redone once per process: the file may have travelled from a
     # machine with a different CPU
@@ -131,6 +132,24 @@ def _load(native=False):
         "tfo_product_mul_assign_normalize": (None, [vp, vp, vp]),
         "tfo_product_normalize": (None, [vp, vp]),
         "tfo_product_mul_accumulate": (None, [vp, vp, vp, vp]),
+        "tfo_pbs_modulus_switch_non_native": (u64, [u64, u32, u64]),
+        "tfo_modulus_switch": (u64, [u64, u32]),
+        "tfo_monomial_mul_assign": (None, [vp, sz, sz, u64]),
+        "tfo_monomial_div_assign": (None, [vp, sz, sz, u64]),
+        "tfo_closest_representable_non_native": (u64, [u64, u32, u32, u64]),
+        "tfo_init_decomposer_state_native": (u64, [u64, u32, u32]),
+        "tfo_decomp_non_native_init": (None, [vp, sz, u32, u32, u64, vp, vp]),
+        "tfo_decomp_non_native_next": (None, [vp, vp, sz, u32, u64, vp]),
+        "tfo_decomp_native_init": (None, [vp, sz, u32, u32, vp]),
+        "tfo_decomp_native_next": (None, [vp, sz, u32, vp]),
+        "tfo_add_external_product_ntt64_assign": (None, [P64, vp, vp, vp, sz, u32, u32, i, u32]),
+        "tfo_cmux_ntt64_assign": (None, [P64, vp, vp, vp, sz, u32, u32, i, u32]),
+        "tfo_blind_rotate_ntt64_assign": (None, [P64, vp, sz, sz, u32, u32, vp, vp]),
+        "tfo_blind_rotate_ntt64_bnf_assign": (None, [P64, vp, sz, sz, u32, u32, u32, vp, vp]),
+        "tfo_extract_lwe_sample": (None, [vp, sz, sz, sz, u64, vp]),
+        "tfo_programmable_bootstrap_ntt64": (None, [P64, vp, sz, sz, u32, u32, vp, vp, vp]),
+        "tfo_programmable_bootstrap_ntt64_bnf": (None, [P64, vp, sz, sz, u32, u32, u32, vp, vp, vp]),
+        "tfo_convert_standard_lwe_bootstrap_key_to_ntt64": (None, [P64, vp, vp, sz, u32, i]),
         "tfo_plan64_fwd_batch_simd": (i, [P64, vp, sz, i]),
         "tfo_plan64_inv_batch_simd": (i, [P64, vp, sz, i]),
     }
@@ -390,3 +409,56 @@ class OracleProductPlan:
         self.lib.tfo_product_mul_accumulate(self.h, _ptr(a), _ptr(np.ascontiguousarray(lhs, dtype=np.uint64)),
                                             _ptr(np.ascontiguousarray(rhs, dtype=np.uint64)))
         return a
+
+
+class OraclePbs:
+    """NTT-PBS restated (oracle/tfhe_ntt_pbs_oracle.c): tfhe ntt64_pbs.rs / ntt64_bnf_pbs.rs.
+    bsk: NTT-domain container [n_lwe][level][k+1][k+1][N]."""
+
+    def __init__(self, plan, bsk, n_lwe, glwe_size, base_log, level):
+        assert plan.bits == 64
+        self.plan, self.lib = plan, plan.lib
+        self.bsk = np.ascontiguousarray(bsk, dtype=np.uint64)
+        self.n_lwe, self.glwe_size, self.base_log, self.level = n_lwe, glwe_size, base_log, level
+        self.n = plan.n
+        assert self.bsk.size == n_lwe * level * glwe_size * glwe_size * self.n
+
+    def blind_rotate(self, lwe, lut):
+        """classic; returns the rotated copy of lut"""
+        out = np.array(lut, dtype=np.uint64)
+        lwe = np.ascontiguousarray(lwe, dtype=np.uint64)
+        self.lib.tfo_blind_rotate_ntt64_assign(self.plan.h, _ptr(self.bsk), self.n_lwe, self.glwe_size, self.base_log,
+                                               self.level, _ptr(lwe), _ptr(out))
+        return out
+
+    def blind_rotate_bnf(self, msed, lut, width=64):
+        out = np.array(lut, dtype=np.uint64)
+        msed = np.ascontiguousarray(msed, dtype=np.uint64)
+        self.lib.tfo_blind_rotate_ntt64_bnf_assign(self.plan.h, _ptr(self.bsk), self.n_lwe, self.glwe_size,
+                                                   self.base_log, self.level, width, _ptr(msed), _ptr(out))
+        return out
+
+    def pbs(self, lwe_in, accumulator):
+        lwe_in = np.ascontiguousarray(lwe_in, dtype=np.uint64)
+        acc = np.ascontiguousarray(accumulator, dtype=np.uint64)
+        out = np.zeros((self.glwe_size - 1) * self.n + 1, dtype=np.uint64)
+        self.lib.tfo_programmable_bootstrap_ntt64(self.plan.h, _ptr(self.bsk), self.n_lwe, self.glwe_size,
+                                                  self.base_log, self.level, _ptr(lwe_in), _ptr(out), _ptr(acc))
+        return out
+
+    def pbs_bnf(self, lwe_in, accumulator, width=64):
+        lwe_in = np.ascontiguousarray(lwe_in, dtype=np.uint64)
+        acc = np.ascontiguousarray(accumulator, dtype=np.uint64)
+        out = np.zeros((self.glwe_size - 1) * self.n + 1, dtype=np.uint64)
+        self.lib.tfo_programmable_bootstrap_ntt64_bnf(self.plan.h, _ptr(self.bsk), self.n_lwe, self.glwe_size,
+                                                      self.base_log, self.level, width, _ptr(lwe_in), _ptr(out),
+                                                      _ptr(acc))
+        return out
+
+
+def convert_standard_bsk(plan, standard, input_width=0, normalize=False):
+    standard = np.ascontiguousarray(standard, dtype=np.uint64)
+    out = np.empty_like(standard)
+    plan.lib.tfo_convert_standard_lwe_bootstrap_key_to_ntt64(plan.h, _ptr(standard), _ptr(out), standard.size // plan.n,
+                                                             input_width, int(normalize))
+    return out

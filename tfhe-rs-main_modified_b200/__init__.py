@@ -14,6 +14,10 @@ Module, type and method names follow the reference:
     product.Plan (FwdMode, InvMode)   try_new, ntt_size, modulus, ntt_domain_len, fwd, inv,
                                    normalize, mul_assign_normalize, mul_accumulate
     prime.is_prime64, prime.largest_prime_in_arithmetic_progression64
+    ntt64.Ntt64View                tfhe's wrapper over prime64.Plan (forward*, add_backward*)
+    ntt64_pbs                      NttLweBootstrapKey, convert_standard_lwe_bootstrap_key_to_ntt64,
+                                   blind_rotate_ntt64[_bnf]_assign,
+                                   programmable_bootstrap_ntt64[_bnf]_lwe_ciphertext
 
 Host calls take numpy arrays and work in place exactly like the reference's `&mut [T]` slices.
 New, alongside: `*_batch` (host arrays holding many polynomials) and `*_device` (device pointers
@@ -32,4 +36,5 @@ from . import native32, native64, native128  # noqa: F401
 from . import native_binary32, native_binary64, native_binary128  # noqa: F401
 from . import product  # noqa: F401
 from . import ntt64  # noqa: F401
+from . import ntt64_pbs  # noqa: F401
 from . import sharding  # noqa: F401

@@ -82,6 +82,23 @@ SIGNATURES = {
     "ntt_b200_product_ntt_size": (_sz, [_vp]),
     "ntt_b200_product_modulus": (_u64, [_vp]),
     "ntt_b200_product_ntt_domain_len": (_sz, [_vp]),
+    "ntt_b200_bsk_new": (_i, [_vp, _vp, _sz, _sz, _u32, _u32, _pp]),
+    "ntt_b200_bsk_convert_new": (_i, [_vp, _vp, _sz, _sz, _u32, _u32, _u32, _i, _pp]),
+    "ntt_b200_convert_standard_lwe_bootstrap_key_to_ntt64": (_i, [_vp, _vp, _vp, _sz, _u32, _i]),
+    "ntt_b200_bsk_free": (None, [_vp]),
+    "ntt_b200_bsk_input_lwe_dimension": (_sz, [_vp]),
+    "ntt_b200_bsk_glwe_size": (_sz, [_vp]),
+    "ntt_b200_bsk_polynomial_size": (_sz, [_vp]),
+    "ntt_b200_bsk_decomposition_base_log": (_u32, [_vp]),
+    "ntt_b200_bsk_decomposition_level_count": (_u32, [_vp]),
+    "ntt_b200_bsk_device_data": (_vp, [_vp]),
+    "ntt_b200_bsk_read": (_i, [_vp, _vp, _sz]),
+    "ntt_b200_blind_rotate_ntt64_assign": (_i, [_vp, _vp, _vp, _sz, _i]),
+    "ntt_b200_blind_rotate_ntt64_bnf_assign": (_i, [_vp, _u32, _vp, _vp, _sz, _i]),
+    "ntt_b200_programmable_bootstrap_ntt64": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _i]),
+    "ntt_b200_programmable_bootstrap_ntt64_bnf": (_i, [_vp, _u32, _vp, _vp, _vp, _sz, _sz, _i]),
+    "ntt_b200_blind_rotate_ntt64_device": (_i, [_vp, _i, _u32, _vp, _i, _vp, _sz, _vp, _sz, _i, _vp]),
+    "ntt_b200_extract_lwe_sample_device": (_i, [_vp, _i, _vp, _vp, _sz, _vp]),
     "ntt_b200_product_fwd": (_i, [_vp, _vp, _sz, _vp, _sz]),
     "ntt_b200_product_inv": (_i, [_vp, _vp, _sz, _vp, _sz, _i]),
     "ntt_b200_product_normalize": (_i, [_vp, _vp, _sz]),

@@ -60,6 +60,18 @@ struct PrimePlan {
     // (NTT domain, shared by the batch), out: [batch][cols][n]
     virtual void ext_product(void* out, const void* in, const void* ggsw, unsigned rows,
                              unsigned cols, size_t batch, cudaStream_t stream) const = 0;
+    // Fused blind rotation of the NTT-PBS (u64 plans, tfhe ntt64_pbs.rs:213-286 / ntt64_bnf_pbs.rs:
+    // 208-276): acc_out[b] = blind rotation of lut[b % lut_count] by the switched ciphertext
+    // switched[b][n_lwe+1] under the NTT-domain key bsk.  Returns false when this plan / shape has
+    // no fused kernel (the caller then composes ext_product with elementwise kernels).
+    virtual bool blind_rotate(uint64_t* acc_out, const uint64_t* lut, size_t lut_count,
+                              const unsigned* switched, const uint64_t* bsk, size_t n_lwe,
+                              size_t glwe_size, unsigned base_log, unsigned level, size_t batch, int bnf,
+                              unsigned width, cudaStream_t stream) const {
+        (void)acc_out, (void)lut, (void)lut_count, (void)switched, (void)bsk, (void)n_lwe, (void)glwe_size;
+        (void)base_log, (void)level, (void)batch, (void)bnf, (void)width, (void)stream;
+        return false;
+    }
     virtual std::shared_ptr<PrimePlan> clone() const = 0;
     virtual bool raw_shoup32h(RawShoup32H*) const { return false; }
 };
