@@ -188,3 +188,23 @@ def test_pbs_other_prime_family_composed():
     got = lut.copy()
     G.blind_rotate_ntt64_assign(lwe.reshape(-1), got.reshape(-1), key)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_fused_only_path_and_its_limits():
+    import tfhe_ntt_b200 as T
+    rng = np.random.default_rng(9)
+    # fused kernel exists for Solinas, N = 256 .. 4096, glwe_size 2 .. 4
+    shape = (4, 1, 1024, 12, 2)
+    G, key, opbs = _setup(rng, *shape)
+    lwe = _rand_mod(rng, (2, 5), P)
+    lut = _rand_mod(rng, (2, 2 * 1024), P)
+    got = lut.copy()
+    G.blind_rotate_ntt64_assign(lwe.reshape(-1), got.reshape(-1), key, path=G.PATH_FUSED)
+    assert np.array_equal(got, np.stack([opbs.blind_rotate(lwe[b], lut[b]) for b in range(2)]))
+    # none for N = 64: PATH_FUSED fails loudly, PATH_AUTO composes
+    G, key, opbs = _setup(rng, 3, 1, 64, 12, 2)
+    lwe = _rand_mod(rng, 4, P)
+    lut = _rand_mod(rng, 128, P)
+    with pytest.raises(T.NttB200Error):
+        G.blind_rotate_ntt64_assign(lwe, lut.copy(), key, path=G.PATH_FUSED)

@@ -6,6 +6,7 @@
 #include <type_traits>
 
 #include "ntt_fast.cuh"
+#include "ntt_pbs_fused.cuh"
 #include "ntt_kernels.cuh"
 #include "plan_math.hpp"
 
@@ -158,6 +159,17 @@ struct PlanImpl final : PrimePlan {
     }
 
     std::shared_ptr<PrimePlan> clone() const override { return std::make_shared<PlanImpl>(*this); }
+    bool blind_rotate(uint64_t* acc_out, const uint64_t* lut, size_t lut_count, const unsigned* switched,
+                      const uint64_t* bsk, size_t n_lwe, size_t glwe_size, unsigned base_log, unsigned level,
+                      size_t batch, int bnf, unsigned width, cudaStream_t st) const override {
+        if constexpr (std::is_same<A, Solinas64>::value) {
+            DeviceGuard g(device);
+            return fast_blind_rotate<A>(acc_out, lut, lut_count, switched, bsk, n_lwe, glwe_size, base_log,
+                                        level, batch, bnf, width, logn, d_fwd.get(), d_inv.get(), ctx, n_inv, st);
+        } else {
+            return false;
+        }
+    }
     bool raw_shoup32h(RawShoup32H* out) const override {
         if constexpr (std::is_same<A, Shoup<uint32_t, true>>::value) {
             *out = RawShoup32H{d_fwd.get(), d_inv.get(), ctx, n_inv};
