@@ -7,6 +7,7 @@
 //   tfhe_ntt::prime32::Plan   <- tfhe-ntt/src/prime32.rs:632-1016
 //   tfhe_ntt::native64::Plan32 ... <- tfhe-ntt/src/native{32,64,128}.rs, native_binary*.rs
 //   tfhe_ntt::fastdiv::{Div32,Div64} <- tfhe-ntt/src/fastdiv.rs:29-150
+//   tfhe_ntt::ntt64_pbs::*         <- tfhe/src/core_crypto/algorithms/lwe_programmable_bootstrapping/ntt64_{,bnf_}pbs.rs
 // `try_new` returns std::optional (Rust Option); length assertions throw std::logic_error where
 // the reference panics; CUDA failures throw std::runtime_error.
 #pragma once
@@ -244,5 +245,129 @@ using Plan52 = NativePlan<NTT_B200_NATIVE_BINARY64_PLAN52, uint64_t, uint64_t, 2
 namespace native_binary128 {
 using Plan32 = NativePlan<NTT_B200_NATIVE_BINARY128_PLAN32, u128, uint32_t, 5, true>;
 }
+
+// NTT programmable bootstrap on top of prime64::Plan (the caller of the hot path):
+//   tfhe::core_crypto::algorithms::lwe_programmable_bootstrapping::ntt64_pbs / ntt64_bnf_pbs,
+//   tfhe::core_crypto::entities::NttLweBootstrapKey, convert_standard_lwe_bootstrap_key_to_ntt64.
+// Containers are the reference's flat ones; every call takes `batch` ciphertexts.
+namespace ntt64_pbs {
+enum class NttLweBootstrapKeyOption { Raw = 0, Normalize = 1 };  // lwe_bootstrap_key_conversion.rs:283-288
+enum class Path { Auto = 0, Fused = 1, Composed = 2 };
+
+class NttLweBootstrapKey {
+    struct Del {
+        void operator()(ntt_b200_bsk* p) const { ntt_b200_bsk_free(p); }
+    };
+    std::unique_ptr<ntt_b200_bsk, Del> h_;
+    explicit NttLweBootstrapKey(ntt_b200_bsk* h) : h_(h) {}
+
+   public:
+    // NttLweBootstrapKey::from_container, entities/ntt_lwe_bootstrap_key.rs:68-110
+    static NttLweBootstrapKey from_container(const prime64::Plan& plan, const std::vector<uint64_t>& container,
+                                             size_t input_lwe_dimension, size_t glwe_size,
+                                             uint32_t decomposition_base_log, uint32_t decomposition_level_count) {
+        if (container.size() != input_lwe_dimension * decomposition_level_count * glwe_size * glwe_size * plan.ntt_size())
+            throw std::logic_error("assertion failed: NttLweBootstrapKey container length");
+        ntt_b200_bsk* h = nullptr;
+        check(ntt_b200_bsk_new(plan.raw(), container.data(), input_lwe_dimension, glwe_size, decomposition_base_log,
+                               decomposition_level_count, &h),
+              "NttLweBootstrapKey::from_container");
+        return NttLweBootstrapKey(h);
+    }
+    // convert_standard_lwe_bootstrap_key_to_ntt64 (:294-363) straight into device memory
+    static NttLweBootstrapKey from_standard(const prime64::Plan& plan, const std::vector<uint64_t>& standard_bsk,
+                                            size_t input_lwe_dimension, size_t glwe_size,
+                                            uint32_t decomposition_base_log, uint32_t decomposition_level_count,
+                                            uint32_t input_modulus_width, NttLweBootstrapKeyOption option) {
+        if (standard_bsk.size() !=
+            input_lwe_dimension * decomposition_level_count * glwe_size * glwe_size * plan.ntt_size())
+            throw std::logic_error("assertion failed: LweBootstrapKey container length");
+        ntt_b200_bsk* h = nullptr;
+        check(ntt_b200_bsk_convert_new(plan.raw(), standard_bsk.data(), input_lwe_dimension, glwe_size,
+                                       decomposition_base_log, decomposition_level_count, input_modulus_width,
+                                       (int)option, &h),
+              "NttLweBootstrapKey::from_standard");
+        return NttLweBootstrapKey(h);
+    }
+    size_t input_lwe_dimension() const { return ntt_b200_bsk_input_lwe_dimension(h_.get()); }
+    size_t glwe_size() const { return ntt_b200_bsk_glwe_size(h_.get()); }
+    size_t polynomial_size() const { return ntt_b200_bsk_polynomial_size(h_.get()); }
+    uint32_t decomposition_base_log() const { return ntt_b200_bsk_decomposition_base_log(h_.get()); }
+    uint32_t decomposition_level_count() const { return ntt_b200_bsk_decomposition_level_count(h_.get()); }
+    size_t output_lwe_dimension() const { return (glwe_size() - 1) * polynomial_size(); }
+    std::vector<uint64_t> as_container() const {
+        std::vector<uint64_t> out(input_lwe_dimension() * decomposition_level_count() * glwe_size() * glwe_size() *
+                                  polynomial_size());
+        check(ntt_b200_bsk_read(h_.get(), out.data(), out.size()), "NttLweBootstrapKey::as_container");
+        return out;
+    }
+    const ntt_b200_bsk* raw() const { return h_.get(); }
+};
+
+// lwe_bootstrap_key_conversion.rs:294-363, host to host
+inline void convert_standard_lwe_bootstrap_key_to_ntt64(const prime64::Plan& plan,
+                                                        const std::vector<uint64_t>& input_bsk,
+                                                        std::vector<uint64_t>& output_bsk,
+                                                        NttLweBootstrapKeyOption option,
+                                                        uint32_t input_modulus_width = 0) {
+    if (input_bsk.size() != output_bsk.size()) throw std::logic_error("assertion failed: mismatched key sizes");
+    check(ntt_b200_convert_standard_lwe_bootstrap_key_to_ntt64(plan.raw(), input_bsk.data(), output_bsk.data(),
+                                                               input_bsk.size(), input_modulus_width, (int)option),
+          "convert_standard_lwe_bootstrap_key_to_ntt64");
+}
+
+inline size_t batch_of(size_t len, size_t row, const char* what) {
+    if (row == 0 || len % row) throw std::logic_error(std::string("assertion failed: container length in ") + what);
+    return len / row;
+}
+// blind_rotate_ntt64_assign, ntt64_pbs.rs:175-286
+inline void blind_rotate_ntt64_assign(const std::vector<uint64_t>& input, std::vector<uint64_t>& lut,
+                                      const NttLweBootstrapKey& bsk, Path path = Path::Auto) {
+    size_t batch = batch_of(input.size(), bsk.input_lwe_dimension() + 1, "blind_rotate_ntt64_assign");
+    if (lut.size() != batch * bsk.glwe_size() * bsk.polynomial_size())
+        throw std::logic_error("assertion failed: lut size");
+    check(ntt_b200_blind_rotate_ntt64_assign(bsk.raw(), input.data(), lut.data(), batch, (int)path),
+          "blind_rotate_ntt64_assign");
+}
+// blind_rotate_ntt64_bnf_assign, ntt64_bnf_pbs.rs:174-276
+inline void blind_rotate_ntt64_bnf_assign(const std::vector<uint64_t>& msed_input, std::vector<uint64_t>& lut,
+                                          const NttLweBootstrapKey& bsk, uint32_t ciphertext_modulus_width = 64,
+                                          Path path = Path::Auto) {
+    size_t batch = batch_of(msed_input.size(), bsk.input_lwe_dimension() + 1, "blind_rotate_ntt64_bnf_assign");
+    if (lut.size() != batch * bsk.glwe_size() * bsk.polynomial_size())
+        throw std::logic_error("assertion failed: lut size");
+    check(ntt_b200_blind_rotate_ntt64_bnf_assign(bsk.raw(), ciphertext_modulus_width, msed_input.data(), lut.data(),
+                                                 batch, (int)path),
+          "blind_rotate_ntt64_bnf_assign");
+}
+// programmable_bootstrap_ntt64_lwe_ciphertext, ntt64_pbs.rs:439-538
+inline void programmable_bootstrap_ntt64_lwe_ciphertext(const std::vector<uint64_t>& input,
+                                                        std::vector<uint64_t>& output,
+                                                        const std::vector<uint64_t>& accumulator,
+                                                        const NttLweBootstrapKey& bsk, Path path = Path::Auto) {
+    size_t batch = batch_of(input.size(), bsk.input_lwe_dimension() + 1, "programmable_bootstrap_ntt64");
+    if (output.size() != batch * (bsk.output_lwe_dimension() + 1))
+        throw std::logic_error("assertion failed: output size");
+    size_t acc_count = batch_of(accumulator.size(), bsk.glwe_size() * bsk.polynomial_size(), "accumulator");
+    check(ntt_b200_programmable_bootstrap_ntt64(bsk.raw(), input.data(), output.data(), accumulator.data(), acc_count,
+                                                batch, (int)path),
+          "programmable_bootstrap_ntt64_lwe_ciphertext");
+}
+// programmable_bootstrap_ntt64_bnf_lwe_ciphertext, ntt64_bnf_pbs.rs:428-539
+inline void programmable_bootstrap_ntt64_bnf_lwe_ciphertext(const std::vector<uint64_t>& input,
+                                                            std::vector<uint64_t>& output,
+                                                            const std::vector<uint64_t>& accumulator,
+                                                            const NttLweBootstrapKey& bsk,
+                                                            uint32_t ciphertext_modulus_width = 64,
+                                                            Path path = Path::Auto) {
+    size_t batch = batch_of(input.size(), bsk.input_lwe_dimension() + 1, "programmable_bootstrap_ntt64_bnf");
+    if (output.size() != batch * (bsk.output_lwe_dimension() + 1))
+        throw std::logic_error("assertion failed: output size");
+    size_t acc_count = batch_of(accumulator.size(), bsk.glwe_size() * bsk.polynomial_size(), "accumulator");
+    check(ntt_b200_programmable_bootstrap_ntt64_bnf(bsk.raw(), ciphertext_modulus_width, input.data(), output.data(),
+                                                    accumulator.data(), acc_count, batch, (int)path),
+          "programmable_bootstrap_ntt64_bnf_lwe_ciphertext");
+}
+}  // namespace ntt64_pbs
 
 }  // namespace tfhe_ntt

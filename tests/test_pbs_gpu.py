@@ -5,6 +5,9 @@ ntt64_bnf_pbs.rs), the fused and the composed device paths, and the reference's 
 tests (algorithms/test/lwe_programmable_bootstrapping.rs:708-870, :1002-1163) at the reference's
 parameters TEST_PARAMS_3_BITS_SOLINAS_U64 (test/mod.rs:106-130): encrypt, bootstrap, decrypt.
 """
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
@@ -208,3 +211,17 @@ def test_fused_only_path_and_its_limits():
     lut = _rand_mod(rng, 128, P)
     with pytest.raises(T.NttB200Error):
         G.blind_rotate_ntt64_assign(lwe, lut.copy(), key, path=G.PATH_FUSED)
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_pbs_example(tmp_path):
+    import tfhe_ntt_b200 as T
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "example_pbs"
+    libdir = os.path.dirname(T.library_path())
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cpp", "example_pbs.cpp"), "-o", str(exe),
+                    "-L", libdir, "-ltfhe_ntt_b200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "cpp pbs example ok" in r.stdout

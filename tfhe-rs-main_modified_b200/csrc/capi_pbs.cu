@@ -22,12 +22,14 @@ struct ntt_b200_bsk {
     size_t n_lwe = 0, glwe_size = 0;
     unsigned base_log = 0, level = 0;
     uint64_t* d_bsk = nullptr;  // [n_lwe][level][glwe_size][glwe_size][n], NTT domain
+    uint64_t* d_bsk_tw = nullptr;  // the same key in the plan's twiddle form (fused kernels), or null
     size_t ggsw_len() const { return (size_t)level * glwe_size * glwe_size * plan->n; }
     size_t total_len() const { return n_lwe * ggsw_len(); }
     ~ntt_b200_bsk() {
-        if (d_bsk) {
+        if (d_bsk || d_bsk_tw) {
             DeviceGuard g(plan->device);
             cudaFree(d_bsk);
+            cudaFree(d_bsk_tw);
         }
     }
 };
@@ -193,8 +195,8 @@ void blind_rotate_dev(const ntt_b200_bsk* key, const uint64_t* lwe, const uint64
                                                                  log2n, p, bnf, raw_bnf_input);
     NTT_CUDA_CHECK(cudaGetLastError());
     if (path != 2 &&
-        pl->blind_rotate(acc_out, lut, lut_count, switched, key->d_bsk, key->n_lwe, gs, key->base_log,
-                         key->level, batch, bnf, width, st))
+        pl->blind_rotate(acc_out, lut, lut_count, switched, key->d_bsk, key->d_bsk_tw, key->n_lwe, gs,
+                         key->base_log, key->level, batch, bnf, width, st))
         return;
     if (path == 1) throw std::runtime_error("no fused blind-rotation kernel for this shape");
     uint64_t* acc = bnf ? sc.get<uint64_t>(batch * per) : acc_out;
@@ -218,6 +220,18 @@ void blind_rotate_dev(const ntt_b200_bsk* key, const uint64_t* lwe, const uint64
         pbs_final_rotate_kernel<<<grid_for(batch * per), 256, 0, st>>>(acc_out, acc, switched, batch, lwe_size,
                                                                       gs, log2n);
         NTT_CUDA_CHECK(cudaGetLastError());
+    }
+}
+
+// second copy of the key in the form the fused kernels multiply by (when the family has one)
+void make_twiddle_form(ntt_b200_bsk* key) {
+    size_t total = key->total_len();
+    NTT_CUDA_CHECK(cudaMalloc(&key->d_bsk_tw, total * 8));
+    bool ok = key->plan->key_to_twiddle_form(key->d_bsk_tw, key->d_bsk, total, nullptr);
+    NTT_CUDA_CHECK(cudaDeviceSynchronize());
+    if (!ok) {
+        cudaFree(key->d_bsk_tw);
+        key->d_bsk_tw = nullptr;
     }
 }
 
@@ -325,6 +339,7 @@ int ntt_b200_bsk_new(const ntt_b200_plan64* plan, const uint64_t* ntt_bsk, size_
         DeviceGuard g(key->plan->device);
         NTT_CUDA_CHECK(cudaMalloc(&key->d_bsk, key->total_len() * 8));
         NTT_CUDA_CHECK(cudaMemcpy(key->d_bsk, ntt_bsk, key->total_len() * 8, cudaMemcpyHostToDevice));
+        make_twiddle_form(key.get());
         *out = key.release();
         return NTT_B200_OK;
     });
@@ -365,6 +380,7 @@ int ntt_b200_bsk_convert_new(const ntt_b200_plan64* plan, const uint64_t* standa
         cudaFree(staging);
         NTT_CUDA_CHECK(e);
         if (rc != NTT_B200_OK) return rc;
+        make_twiddle_form(key.get());
         *out = key.release();
         return NTT_B200_OK;
     });

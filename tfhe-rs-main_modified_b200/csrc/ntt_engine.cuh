@@ -64,12 +64,19 @@ struct PrimePlan {
     // 208-276): acc_out[b] = blind rotation of lut[b % lut_count] by the switched ciphertext
     // switched[b][n_lwe+1] under the NTT-domain key bsk.  Returns false when this plan / shape has
     // no fused kernel (the caller then composes ext_product with elementwise kernels).
+    // bsk_tw: the key in the family's twiddle form (key_to_twiddle_form), or null.
     virtual bool blind_rotate(uint64_t* acc_out, const uint64_t* lut, size_t lut_count,
-                              const unsigned* switched, const uint64_t* bsk, size_t n_lwe,
-                              size_t glwe_size, unsigned base_log, unsigned level, size_t batch, int bnf,
-                              unsigned width, cudaStream_t stream) const {
-        (void)acc_out, (void)lut, (void)lut_count, (void)switched, (void)bsk, (void)n_lwe, (void)glwe_size;
-        (void)base_log, (void)level, (void)batch, (void)bnf, (void)width, (void)stream;
+                              const unsigned* switched, const uint64_t* bsk, const uint64_t* bsk_tw,
+                              size_t n_lwe, size_t glwe_size, unsigned base_log, unsigned level,
+                              size_t batch, int bnf, unsigned width, cudaStream_t stream) const {
+        (void)acc_out, (void)lut, (void)lut_count, (void)switched, (void)bsk, (void)bsk_tw, (void)n_lwe;
+        (void)glwe_size, (void)base_log, (void)level, (void)batch, (void)bnf, (void)width, (void)stream;
+        return false;
+    }
+    // out[i] = in[i] in the form the fused blind rotation multiplies by; false: none for this family
+    virtual bool key_to_twiddle_form(uint64_t* out, const uint64_t* in, size_t total,
+                                     cudaStream_t stream) const {
+        (void)out, (void)in, (void)total, (void)stream;
         return false;
     }
     virtual std::shared_ptr<PrimePlan> clone() const = 0;

@@ -2,13 +2,15 @@
 // CMUXes (tfhe ntt64_pbs.rs:213-286 classic, ntt64_bnf_pbs.rs:208-276 bnf) with the GLWE accumulator
 // resident in shared memory.  Per CMUX the CTA
 //   rotates / subtracts / gadget-decomposes the accumulator straight into registers,
-//   runs the (k+1)*l forward NTTs (fwd_from_regs), multiply-accumulates against the GGSW of this
-//   mask element (read once per CTA from L2, where the whole key stays resident) into register
-//   accumulators, runs the (k+1) inverse NTTs (inv_to_regs) and adds the result into shared memory.
+//   runs the (k+1)*l forward NTTs (fwd_from_regs, two polynomials per thread when k+1 is even),
+//   multiply-accumulates against the GGSW of this mask element (read once per CTA from L2, where
+//   the whole key stays resident) into NTT-domain accumulators in shared memory,
+//   runs the (k+1) inverse NTTs (inv_to_regs) and adds the result into the GLWE accumulator.
 // HBM traffic per ciphertext: the look-up table in, the accumulator out; the unfused sequence
 // moves ~(k+1)(l+2) polynomials per CMUX through HBM.
-// The level loop runs inside the polynomial loop (the reference nests them the other way round,
-// ntt64_pbs.rs:598-643); modular sums do not depend on the order.
+// Modular sums do not depend on the order of the (level, polynomial) loop.  For level > 1 the
+// decomposer state of a coefficient is recomputed per level (cheap next to a transform) instead
+// of being kept in registers across the transforms.
 #pragma once
 #include "ntt_fast.cuh"
 #include "pbs_math.cuh"
@@ -17,15 +19,32 @@ namespace nttb200 {
 
 constexpr unsigned kPbsSkip = 0x80000000u;  // flag in a switched mask element: CMUX not executed
 
-template <int LOGN, int GS>
-struct PbsSmem {
-    static constexpr size_t kTile = FastShape<LOGN>::kPaddedElems;       // NTT exchange tile
-    static constexpr size_t kAcc = (size_t)GS << LOGN;                   // GLWE accumulator
-    static size_t bytes(size_t n_lwe) { return (kTile + kAcc) * 8 + (n_lwe + 1) * 4; }
+// Families whose modulus is a compile-time constant let the decomposition shifts fold.
+template <class A>
+struct FixedModulus {
+    static constexpr uint64_t value = 0;
+};
+template <>
+struct FixedModulus<Solinas64> {
+    static constexpr uint64_t value = Solinas64::P;
 };
 
-template <class A, int LOGN, int GS, bool BNF>
-__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly)
+template <int LOGN, int GS>
+struct PbsShape {
+    static constexpr int kPPT = (GS % 2 == 0) ? 2 : 1;                      // polynomials per transform
+    static constexpr size_t kTile = (size_t)kPPT * FastShape<LOGN>::kPaddedElems;  // NTT exchange tiles
+    static constexpr size_t kAcc = (size_t)GS << LOGN;                       // GLWE accumulator
+    static constexpr size_t kAccN = (size_t)GS << LOGN;                      // NTT-domain accumulators
+    static constexpr int kThreads = FastShape<LOGN>::kThreadsPerPoly;
+    // all shapes keep 512 threads per SM resident (128 registers per thread)
+    static constexpr int kMinBlocks = 512 / kThreads > 0 ? 512 / kThreads : 1;
+    static size_t bytes(size_t n_lwe) { return (kTile + kAcc + kAccN) * 8 + (n_lwe + 1) * 4; }
+};
+
+// MONT: `bsk` holds the key in the plan's twiddle form (A::mul_const applies); else plain
+// residues (A::mul_full).
+template <class A, int LOGN, int GS, bool BNF, bool MONT>
+__global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, GS>::kMinBlocks)
     ntt_fast_blind_rotate_kernel(uint64_t* __restrict__ acc_out, const uint64_t* __restrict__ lut,
                                  size_t lut_count, const unsigned* __restrict__ switched,
                                  const uint64_t* __restrict__ bsk, unsigned n_lwe, unsigned base_log,
@@ -34,15 +53,21 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly)
                                  const typename A::TW* __restrict__ tw_inv, typename A::Ctx c,
                                  typename A::TW n_inv) {
     using S = FastShape<LOGN>;
+    using PS = PbsShape<LOGN, GS>;
+    constexpr int PPT = PS::kPPT;
     constexpr unsigned N = 1u << LOGN, TPP = S::kThreadsPerPoly;
     extern __shared__ __align__(16) uint64_t pbs_smem[];
     uint64_t* tile = pbs_smem;
-    uint64_t* accS = pbs_smem + PbsSmem<LOGN, GS>::kTile;
-    unsigned* sw = reinterpret_cast<unsigned*>(accS + PbsSmem<LOGN, GS>::kAcc);
+    uint64_t* accS = pbs_smem + PS::kTile;
+    uint64_t* accN = accS + PS::kAcc;
+    unsigned* sw = reinterpret_cast<unsigned*>(accN + PS::kAccN);
     const unsigned t = threadIdx.x;
     const size_t b = blockIdx.x;
-    const uint64_t p = c.p;
+    const uint64_t p = FixedModulus<A>::value ? FixedModulus<A>::value : c.p;
     const SubPoly sub{0u, 0u};
+    // accN is private per thread: vector q (two coefficients) of column cc lives at
+    // ((cc * 4 + q) * TPP + t) * 2, so the 128-bit accesses of a warp are contiguous
+    ulonglong2* accN2 = reinterpret_cast<ulonglong2*>(accN);
 
     for (unsigned i = t; i <= n_lwe; i += TPP) sw[i] = switched[b * (n_lwe + 1) + i];
     __syncthreads();
@@ -61,72 +86,97 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly)
         const unsigned a = sw[i];
         if (a & kPbsSkip) continue;  // uniform over the CTA
         const uint64_t* ggsw = bsk + (size_t)i * level * GS * GS * N;
-        uint64_t accr[GS][8];
-#pragma unroll
-        for (int cc = 0; cc < GS; ++cc)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) accr[cc][k] = 0;
-
+        bool first = true;
 #pragma unroll 1
-        for (int r = 0; r < GS; ++r) {
-            // ct1 - ct0 = acc * X^a - acc at this thread's 8 positions, then the decomposer state
-            const uint64_t* poly = accS + r * N;
-            uint64_t state[8];
-            unsigned negmask = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                unsigned j = t + k * TPP;
-                uint64_t rot = pbs::monomial_mul_coeff(poly, j, a, LOGN, BNF ? 0 : p);
-                if (BNF) {
-                    state[k] = pbs::init_decomposer_state_native(rot - poly[j], base_log, level);
-                } else {
-                    bool neg;
-                    state[k] = pbs::init_state_non_native(pbs::sub_mod(rot, poly[j], p), base_log, level, p, neg);
-                    negmask |= (unsigned)neg << k;
-                }
-            }
+        for (unsigned lv = 0; lv < level; ++lv) {
 #pragma unroll 1
-            for (unsigned lv = 0; lv < level; ++lv) {
-                uint64_t x[1][8];
+            for (int rp = 0; rp < GS; rp += PPT) {
+                uint64_t x[PPT][8];
+                // digit `lv` of decompose(acc * X^a - acc) at this thread's 8 positions
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (BNF) {
-                        uint64_t d = pbs::decompose_one_level(base_log, state[k]);
-                        x[0][k] = (int64_t)d < 0 ? d + p : d;  // forward_from_decomp, ntt64.rs:229-236
-                    } else {
-                        x[0][k] = pbs::next_term_non_native(base_log, state[k], (negmask >> k) & 1u, p);
+                for (int pp = 0; pp < PPT; ++pp) {
+                    const uint64_t* poly = accS + (rp + pp) * N;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        unsigned j = t + k * TPP;
+                        uint64_t rot = pbs::monomial_mul_coeff(poly, j, a, LOGN, BNF ? 0 : p);
+                        uint64_t d;
+                        if (BNF) {
+                            uint64_t state = pbs::init_decomposer_state_native(rot - poly[j], base_log, level);
+                            for (unsigned s = 0; s < lv; ++s) pbs::decompose_one_level(base_log, state);
+                            d = pbs::decompose_one_level(base_log, state);
+                            d = (int64_t)d < 0 ? d + p : d;  // forward_from_decomp, ntt64.rs:229-236
+                        } else {
+                            bool neg;
+                            uint64_t state =
+                                pbs::init_state_non_native(pbs::sub_mod(rot, poly[j], p), base_log, level, p, neg);
+                            for (unsigned s = 0; s < lv; ++s) pbs::decompose_one_level(base_log, state);
+                            d = pbs::next_term_non_native(base_log, state, neg, p);
+                        }
+                        x[pp][k] = d;
                     }
                 }
-                fwd_from_regs<A, LOGN, 1>(x, tile, t, tw_fwd, c, sub);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) x[0][k] = A::fwd_fin(c, x[0][k]);
-                const uint64_t* row = ggsw + ((size_t)(lv * GS + r) * GS << LOGN) + 8 * t;
+                fwd_from_regs<A, LOGN, PPT>(x, tile, t, tw_fwd, c, sub);
+                // multiply-accumulate against the GGSW rows rp .. rp+PPT-1 of this level
 #pragma unroll
                 for (int cc = 0; cc < GS; ++cc) {
-                    uint64_t g[8];
-                    load8_consecutive(row + ((size_t)cc << LOGN), g);
+                    uint64_t acc[8];
+                    if (first) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        accr[cc][k] = A::acc_add(c, accr[cc][k], A::mul_full(c, x[0][k], g[k]));
+                        for (int k = 0; k < 8; ++k) acc[k] = 0;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            ulonglong2 v = accN2[(cc * 4 + q) * TPP + t];
+                            acc[2 * q] = v.x;
+                            acc[2 * q + 1] = v.y;
+                        }
+                    }
+#pragma unroll
+                    for (int pp = 0; pp < PPT; ++pp) {
+                        uint64_t g[8];
+                        load8_consecutive(ggsw + (((size_t)(lv * GS + rp + pp) * GS + cc) << LOGN) + 8 * t, g);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            uint64_t prod = MONT ? A::mul_const(c, x[pp][k], g[k])
+                                                 : A::mul_full(c, A::fwd_fin(c, x[pp][k]), g[k]);
+                            acc[k] = A::acc_add(c, acc[k], prod);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        accN2[(cc * 4 + q) * TPP + t] = make_ulonglong2(acc[2 * q], acc[2 * q + 1]);
                 }
-                __syncthreads();  // the tile is reused by the next transform
+                first = false;
+                __syncthreads();  // the tiles are reused by the next transform
             }
         }
+#pragma unroll 1
+        for (int cp = 0; cp < GS; cp += PPT) {
+            uint64_t x[PPT][8];
 #pragma unroll
-        for (int cc = 0; cc < GS; ++cc) {
-            uint64_t x[1][8];
+            for (int pp = 0; pp < PPT; ++pp)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) x[0][k] = A::acc_fin(c, accr[cc][k]);
-            inv_to_regs<A, LOGN, 1>(x, tile, t, tw_inv, c, sub);
+                for (int q = 0; q < 4; ++q) {
+                    ulonglong2 v = accN2[((cp + pp) * 4 + q) * TPP + t];
+                    x[pp][2 * q] = A::acc_fin(c, v.x);
+                    x[pp][2 * q + 1] = A::acc_fin(c, v.y);
+                }
+            inv_to_regs<A, LOGN, PPT>(x, tile, t, tw_inv, c, sub);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                uint64_t v = (k < 4) ? A::inv_fin(c, x[0][k]) : A::inv_fin_prod(c, x[0][k]);
-                uint64_t* dst = accS + cc * N + t + k * TPP;
-                if (BNF)  // normalize, modswitch p -> 2^width, wrapping add (ntt64_bnf_pbs.rs:669-673)
-                    *dst += pbs::modswitch_prime_to_pow2(A::mul_const(c, v, n_inv), width, p);
-                else  // add_backward, ntt64.rs:110-131
-                    *dst = pbs::add_mod(*dst, v, p);
-            }
+            for (int pp = 0; pp < PPT; ++pp)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint64_t v = (k < 4) ? A::inv_fin(c, x[pp][k]) : A::inv_fin_prod(c, x[pp][k]);
+                    uint64_t* dst = accS + (cp + pp) * N + t + k * TPP;
+                    if (BNF) {  // normalize, modswitch p -> 2^width, wrapping add (ntt64_bnf_pbs.rs:669-673)
+                        uint64_t nv = A::mul_const(c, v, n_inv);
+                        *dst += FixedModulus<A>::value == Solinas64::P ? pbs::modswitch_solinas_to_pow2(nv, width)
+                                                                       : pbs::modswitch_prime_to_pow2(nv, width, p);
+                    }
+                    else  // add_backward, ntt64.rs:110-131
+                        *dst = pbs::add_mod(*dst, v, p);
+                }
             __syncthreads();
         }
     }
@@ -138,11 +188,17 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly)
     }
 }
 
+// Fused blind rotation.  bsk_tw may be null (then the plain key is used).  false: no kernel for
+// this shape.
 template <class A>
 bool fast_blind_rotate(uint64_t* acc_out, const uint64_t* lut, size_t lut_count, const unsigned* switched,
-                       const uint64_t* bsk, size_t n_lwe, size_t glwe_size, unsigned base_log,
-                       unsigned level, size_t batch, int bnf, unsigned width, int logn,
+                       const uint64_t* bsk, const uint64_t* bsk_tw, size_t n_lwe, size_t glwe_size,
+                       unsigned base_log, unsigned level, size_t batch, int bnf, unsigned width, int logn,
                        const typename A::TW* tw_fwd, const typename A::TW* tw_inv,
                        const typename A::Ctx& c, typename A::TW n_inv, cudaStream_t st);
+// out[i] = twiddle form of in[i] (the form A::mul_const multiplies by); false: family has none
+template <class A>
+bool fast_key_to_twiddle_form(uint64_t* out, const uint64_t* in, size_t total, const typename A::Ctx& c,
+                              cudaStream_t st);
 
 }  // namespace nttb200

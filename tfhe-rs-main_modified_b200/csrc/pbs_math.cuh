@@ -119,5 +119,19 @@ __host__ __device__ __forceinline__ uint64_t modswitch_prime_to_pow2(uint64_t v,
     return width == 64 ? q : q << (64 - width);
 }
 
+// The same modswitch for p = 2^64 - 2^32 + 1 without a 128-bit division: with 2^64 = p + eps
+// (eps = 2^32 - 1), x = xh*2^64 + xl = xh*p + y, y = xh*eps + xl = yh*p + z, z = yh*eps + yl < 3p,
+// so floor(x / p) = xh + yh + [z >= p] + [z >= 2p].
+__host__ __device__ __forceinline__ uint64_t modswitch_solinas_to_pow2(uint64_t v, unsigned width) {
+    constexpr uint64_t P = 0xFFFFFFFF00000001ull, EPS = 0xFFFFFFFFull;
+    unsigned __int128 x = ((unsigned __int128)v << width) | (unsigned __int128)(P >> 1);
+    uint64_t xh = (uint64_t)(x >> 64), xl = (uint64_t)x;
+    unsigned __int128 y = (unsigned __int128)xh * EPS + xl;
+    uint64_t yh = (uint64_t)(y >> 64), yl = (uint64_t)y;
+    unsigned __int128 z = (unsigned __int128)yh * EPS + yl;
+    uint64_t q = xh + yh + (z >= (unsigned __int128)P ? 1 : 0) + (z >= ((unsigned __int128)P << 1) ? 1 : 0);
+    return width == 64 ? q : q << (64 - width);
+}
+
 }  // namespace pbs
 }  // namespace nttb200
