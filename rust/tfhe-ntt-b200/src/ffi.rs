@@ -11,6 +11,7 @@ pub const ERR_CUDA: c_int = 3;
 #[repr(C)] pub struct ntt_b200_plan32 { _p: [u8; 0] }
 #[repr(C)] pub struct ntt_b200_native_plan { _p: [u8; 0] }
 #[repr(C)] pub struct ntt_b200_product_plan { _p: [u8; 0] }
+#[repr(C)] pub struct ntt_b200_bsk { _p: [u8; 0] }
 
 extern "C" {
     pub fn ntt_b200_last_error() -> *const c_char;
@@ -68,6 +69,23 @@ extern "C" {
     pub fn ntt_b200_product_normalize(plan: *const ntt_b200_product_plan, values: *mut u64, len: usize) -> c_int;
     pub fn ntt_b200_product_mul_assign_normalize(plan: *const ntt_b200_product_plan, lhs: *mut u64, lhs_len: usize, rhs: *const u64, rhs_len: usize) -> c_int;
     pub fn ntt_b200_product_mul_accumulate(plan: *const ntt_b200_product_plan, acc: *mut u64, acc_len: usize, lhs: *const u64, lhs_len: usize, rhs: *const u64, rhs_len: usize) -> c_int;
+
+    pub fn ntt_b200_bsk_new(plan: *const ntt_b200_plan64, ntt_bsk: *const u64, n_lwe: usize, glwe_size: usize, base_log: u32, level: u32, out: *mut *mut ntt_b200_bsk) -> c_int;
+    pub fn ntt_b200_bsk_convert_new(plan: *const ntt_b200_plan64, standard_bsk: *const u64, n_lwe: usize, glwe_size: usize, base_log: u32, level: u32, input_width: u32, normalize: c_int, out: *mut *mut ntt_b200_bsk) -> c_int;
+    pub fn ntt_b200_convert_standard_lwe_bootstrap_key_to_ntt64(plan: *const ntt_b200_plan64, input: *const u64, output: *mut u64, len: usize, input_width: u32, normalize: c_int) -> c_int;
+    pub fn ntt_b200_bsk_free(key: *mut ntt_b200_bsk);
+    pub fn ntt_b200_bsk_input_lwe_dimension(key: *const ntt_b200_bsk) -> usize;
+    pub fn ntt_b200_bsk_glwe_size(key: *const ntt_b200_bsk) -> usize;
+    pub fn ntt_b200_bsk_polynomial_size(key: *const ntt_b200_bsk) -> usize;
+    pub fn ntt_b200_bsk_decomposition_base_log(key: *const ntt_b200_bsk) -> u32;
+    pub fn ntt_b200_bsk_decomposition_level_count(key: *const ntt_b200_bsk) -> u32;
+    pub fn ntt_b200_bsk_read(key: *const ntt_b200_bsk, out: *mut u64, len: usize) -> c_int;
+    pub fn ntt_b200_blind_rotate_ntt64_assign(key: *const ntt_b200_bsk, lwe: *const u64, lut: *mut u64, batch: usize, path: c_int) -> c_int;
+    pub fn ntt_b200_blind_rotate_ntt64_bnf_assign(key: *const ntt_b200_bsk, width: u32, msed: *const u64, lut: *mut u64, batch: usize, path: c_int) -> c_int;
+    pub fn ntt_b200_programmable_bootstrap_ntt64(key: *const ntt_b200_bsk, lwe_in: *const u64, lwe_out: *mut u64, accumulator: *const u64, acc_count: usize, batch: usize, path: c_int) -> c_int;
+    pub fn ntt_b200_programmable_bootstrap_ntt64_bnf(key: *const ntt_b200_bsk, width: u32, lwe_in: *const u64, lwe_out: *mut u64, accumulator: *const u64, acc_count: usize, batch: usize, path: c_int) -> c_int;
+    pub fn ntt_b200_blind_rotate_ntt64_device(key: *const ntt_b200_bsk, bnf: c_int, width: u32, lwe: *const u64, lwe_is_switched: c_int, lut: *const u64, lut_count: usize, acc_out: *mut u64, batch: usize, path: c_int, stream: *mut c_void) -> c_int;
+    pub fn ntt_b200_extract_lwe_sample_device(key: *const ntt_b200_bsk, bnf: c_int, glwe: *const u64, lwe_out: *mut u64, batch: usize, stream: *mut c_void) -> c_int;
 
     pub fn ntt_b200_native_try_new(kind: c_int, n: usize, out: *mut *mut ntt_b200_native_plan) -> c_int;
     pub fn ntt_b200_native_free(plan: *mut ntt_b200_native_plan);

@@ -23,6 +23,8 @@ impl Plan {
             e => { check(e, "prime64::Plan::try_new"); None }
         }
     }
+    /// the C handle, for the sibling modules that take a plan (ntt64_pbs)
+    #[inline] pub(crate) fn as_raw(&self) -> *const ffi::ntt_b200_plan64 { self.raw }
     #[inline] pub fn ntt_size(&self) -> usize { unsafe { ffi::ntt_b200_plan64_ntt_size(self.raw) } }
     #[inline] pub fn modulus(&self) -> u64 { unsafe { ffi::ntt_b200_plan64_modulus(self.raw) } }
     #[inline] pub fn use_ifma(&self) -> bool { unsafe { ffi::ntt_b200_plan64_use_ifma(self.raw) != 0 } }

@@ -227,7 +227,8 @@ void blind_rotate_dev(const ntt_b200_bsk* key, const uint64_t* lwe, const uint64
 void make_twiddle_form(ntt_b200_bsk* key) {
     size_t total = key->total_len();
     NTT_CUDA_CHECK(cudaMalloc(&key->d_bsk_tw, total * 8));
-    bool ok = key->plan->key_to_twiddle_form(key->d_bsk_tw, key->d_bsk, total, nullptr);
+    bool ok = key->plan->key_to_twiddle_form(key->d_bsk_tw, key->d_bsk, key->n_lwe * key->level, key->glwe_size,
+                                             nullptr);
     NTT_CUDA_CHECK(cudaDeviceSynchronize());
     if (!ok) {
         cudaFree(key->d_bsk_tw);

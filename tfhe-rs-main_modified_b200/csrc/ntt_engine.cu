@@ -172,10 +172,11 @@ struct PlanImpl final : PrimePlan {
             return false;
         }
     }
-    bool key_to_twiddle_form(uint64_t* out, const uint64_t* in, size_t total, cudaStream_t st) const override {
+    bool key_to_twiddle_form(uint64_t* out, const uint64_t* in, size_t matrices, size_t glwe_size,
+                             cudaStream_t st) const override {
         if constexpr (std::is_same<A, Solinas64>::value) {
             DeviceGuard g(device);
-            return fast_key_to_twiddle_form<A>(out, in, total, ctx, st);
+            return fast_key_to_twiddle_form<A>(out, in, matrices, glwe_size, logn, ctx, st);
         } else {
             return false;
         }

@@ -73,10 +73,11 @@ struct PrimePlan {
         (void)glwe_size, (void)base_log, (void)level, (void)batch, (void)bnf, (void)width, (void)stream;
         return false;
     }
-    // out[i] = in[i] in the form the fused blind rotation multiplies by; false: none for this family
-    virtual bool key_to_twiddle_form(uint64_t* out, const uint64_t* in, size_t total,
+    // out = the key `in` ([matrices][glwe_size][glwe_size][n]) in the layout and form the fused blind
+    // rotation reads; false: none for this family / shape
+    virtual bool key_to_twiddle_form(uint64_t* out, const uint64_t* in, size_t matrices, size_t glwe_size,
                                      cudaStream_t stream) const {
-        (void)out, (void)in, (void)total, (void)stream;
+        (void)out, (void)in, (void)matrices, (void)glwe_size, (void)stream;
         return false;
     }
     virtual std::shared_ptr<PrimePlan> clone() const = 0;

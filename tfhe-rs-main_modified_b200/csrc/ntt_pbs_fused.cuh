@@ -4,7 +4,8 @@
 //   rotates / subtracts / gadget-decomposes the accumulator straight into registers,
 //   runs the (k+1)*l forward NTTs (fwd_from_regs, two polynomials per thread when k+1 is even),
 //   multiply-accumulates against the GGSW of this mask element (read once per CTA from L2, where
-//   the whole key stays resident) into NTT-domain accumulators in shared memory,
+//   the whole key stays resident; stored in Montgomery form, permuted so that a thread's operands
+//   are contiguous) in registers -- or, with more than one transform group, in an L2 scratch --,
 //   runs the (k+1) inverse NTTs (inv_to_regs) and adds the result into the GLWE accumulator.
 // HBM traffic per ciphertext: the look-up table in, the accumulator out; the unfused sequence
 // moves ~(k+1)(l+2) polynomials per CMUX through HBM.
@@ -32,23 +33,37 @@ struct FixedModulus<Solinas64> {
 template <int LOGN, int GS>
 struct PbsShape {
     static constexpr int kPPT = (GS % 2 == 0) ? 2 : 1;                      // polynomials per transform
+    static constexpr int kGroups = GS / kPPT;                                // transforms per level
     static constexpr size_t kTile = (size_t)kPPT * FastShape<LOGN>::kPaddedElems;  // NTT exchange tiles
     static constexpr size_t kAcc = (size_t)GS << LOGN;                       // GLWE accumulator
-    static constexpr size_t kAccN = (size_t)GS << LOGN;                      // NTT-domain accumulators
     static constexpr int kThreads = FastShape<LOGN>::kThreadsPerPoly;
-    // all shapes keep 512 threads per SM resident (128 registers per thread)
-    static constexpr int kMinBlocks = 512 / kThreads > 0 ? 512 / kThreads : 1;
-    static size_t bytes(size_t n_lwe) { return (kTile + kAcc + kAccN) * 8 + (n_lwe + 1) * 4; }
+    // shared memory (71 KiB at N = 2048, k = 1) allows three CTAs per SM: ask for <= 80 registers
+    static constexpr int kMinBlocks = 768 / kThreads > 0 ? 768 / kThreads : 1;
+    static size_t bytes(size_t n_lwe) { return (kTile + kAcc) * 8 + (n_lwe + 1) * 4; }
 };
 
-// MONT: `bsk` holds the key in the plan's twiddle form (A::mul_const applies); else plain
-// residues (A::mul_full).
-template <class A, int LOGN, int GS, bool BNF, bool MONT>
+// Key layout read by the fused kernel ("twiddle form"): values in the form A::mul_const
+// multiplies by, permuted so that a thread's operands are contiguous.  Per mask element and level
+// the (k+1) x (k+1) matrix of polynomials is stored as
+//   [row group rg][q < 4][thread t < N/8][pp < PPT][column cc < GS][e < 2]
+// holding coefficient 8t + 2q + e of polynomial (row rg*PPT + pp, column cc).
+template <int LOGN, int GS>
+__host__ __device__ inline size_t pbs_key_index(unsigned rg, unsigned q, unsigned t, unsigned pp, unsigned cc,
+                                                unsigned e) {
+    constexpr unsigned PPT = PbsShape<LOGN, GS>::kPPT, TPP = PbsShape<LOGN, GS>::kThreads;
+    return (((((size_t)rg * 4 + q) * TPP + t) * PPT + pp) * GS + cc) * 2 + e;
+}
+
+// SINGLE: k + 1 == PPT and level == 1, i.e. one forward and one inverse transform group per CMUX
+// (the reference's parameter set): the multiply-accumulate runs in place in registers.  Otherwise
+// the NTT-domain accumulators live in `scratch` ([batch][GS][4][N/8] 16-byte vectors, private per
+// thread, L2 resident).
+template <class A, int LOGN, int GS, bool BNF, bool SINGLE>
 __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, GS>::kMinBlocks)
     ntt_fast_blind_rotate_kernel(uint64_t* __restrict__ acc_out, const uint64_t* __restrict__ lut,
                                  size_t lut_count, const unsigned* __restrict__ switched,
-                                 const uint64_t* __restrict__ bsk, unsigned n_lwe, unsigned base_log,
-                                 unsigned level, unsigned width,
+                                 const uint64_t* __restrict__ bsk_tw, ulonglong2* __restrict__ scratch,
+                                 unsigned n_lwe, unsigned base_log, unsigned level, unsigned width,
                                  const typename A::TW* __restrict__ tw_fwd,
                                  const typename A::TW* __restrict__ tw_inv, typename A::Ctx c,
                                  typename A::TW n_inv) {
@@ -56,18 +71,16 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
     using PS = PbsShape<LOGN, GS>;
     constexpr int PPT = PS::kPPT;
     constexpr unsigned N = 1u << LOGN, TPP = S::kThreadsPerPoly;
+    static_assert(!SINGLE || GS == PPT, "SINGLE needs one transform group");
     extern __shared__ __align__(16) uint64_t pbs_smem[];
     uint64_t* tile = pbs_smem;
     uint64_t* accS = pbs_smem + PS::kTile;
-    uint64_t* accN = accS + PS::kAcc;
-    unsigned* sw = reinterpret_cast<unsigned*>(accN + PS::kAccN);
+    unsigned* sw = reinterpret_cast<unsigned*>(accS + PS::kAcc);
     const unsigned t = threadIdx.x;
     const size_t b = blockIdx.x;
     const uint64_t p = FixedModulus<A>::value ? FixedModulus<A>::value : c.p;
     const SubPoly sub{0u, 0u};
-    // accN is private per thread: vector q (two coefficients) of column cc lives at
-    // ((cc * 4 + q) * TPP + t) * 2, so the 128-bit accesses of a warp are contiguous
-    ulonglong2* accN2 = reinterpret_cast<ulonglong2*>(accN);
+    ulonglong2* accN = SINGLE ? nullptr : scratch + b * (size_t)(GS * 4 * TPP);
 
     for (unsigned i = t; i <= n_lwe; i += TPP) sw[i] = switched[b * (n_lwe + 1) + i];
     __syncthreads();
@@ -85,17 +98,18 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
     for (unsigned i = 0; i < n_lwe; ++i) {
         const unsigned a = sw[i];
         if (a & kPbsSkip) continue;  // uniform over the CTA
-        const uint64_t* ggsw = bsk + (size_t)i * level * GS * GS * N;
+        const ulonglong2* ggsw =
+            reinterpret_cast<const ulonglong2*>(bsk_tw + (size_t)i * level * GS * GS * N);
+        uint64_t x[PPT][8];
         bool first = true;
 #pragma unroll 1
         for (unsigned lv = 0; lv < level; ++lv) {
 #pragma unroll 1
-            for (int rp = 0; rp < GS; rp += PPT) {
-                uint64_t x[PPT][8];
+            for (int rg = 0; rg < PS::kGroups; ++rg) {
                 // digit `lv` of decompose(acc * X^a - acc) at this thread's 8 positions
 #pragma unroll
                 for (int pp = 0; pp < PPT; ++pp) {
-                    const uint64_t* poly = accS + (rp + pp) * N;
+                    const uint64_t* poly = accS + (rg * PPT + pp) * N;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         unsigned j = t + k * TPP;
@@ -106,6 +120,8 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
                             for (unsigned s = 0; s < lv; ++s) pbs::decompose_one_level(base_log, state);
                             d = pbs::decompose_one_level(base_log, state);
                             d = (int64_t)d < 0 ? d + p : d;  // forward_from_decomp, ntt64.rs:229-236
+                        } else if (SINGLE) {  // level == 1
+                            d = pbs::single_level_term_non_native(pbs::sub_mod(rot, poly[j], p), base_log, p);
                         } else {
                             bool neg;
                             uint64_t state =
@@ -117,65 +133,79 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
                     }
                 }
                 fwd_from_regs<A, LOGN, PPT>(x, tile, t, tw_fwd, c, sub);
-                // multiply-accumulate against the GGSW rows rp .. rp+PPT-1 of this level
+                // multiply-accumulate against rows rg*PPT .. rg*PPT+PPT-1 of this level's matrix;
+                // this thread's PPT*GS operand vectors for coefficient pair q are contiguous
+                const ulonglong2* gq =
+                    ggsw + ((size_t)lv * GS * GS * N) / 2 + pbs_key_index<LOGN, GS>(rg, 0, t, 0, 0, 0) / 2;
 #pragma unroll
-                for (int cc = 0; cc < GS; ++cc) {
-                    uint64_t acc[8];
-                    if (first) {
+                for (int q = 0; q < 4; ++q) {
+                    ulonglong2 g[PPT][GS];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[k] = 0;
+                    for (int pp = 0; pp < PPT; ++pp)
+#pragma unroll
+                        for (int cc = 0; cc < GS; ++cc) g[pp][cc] = gq[(size_t)q * TPP * PPT * GS + pp * GS + cc];
+                    if (SINGLE) {
+                        // out[cc] = sum_pp x[pp] * g[pp][cc], written over x (PPT == GS)
+                        uint64_t o[GS][2];
+#pragma unroll
+                        for (int cc = 0; cc < GS; ++cc) {
+                            o[cc][0] = A::mul_const(c, x[0][2 * q], g[0][cc].x);
+                            o[cc][1] = A::mul_const(c, x[0][2 * q + 1], g[0][cc].y);
+#pragma unroll
+                            for (int pp = 1; pp < PPT; ++pp) {
+                                o[cc][0] = A::acc_add(c, o[cc][0], A::mul_const(c, x[pp][2 * q], g[pp][cc].x));
+                                o[cc][1] = A::acc_add(c, o[cc][1], A::mul_const(c, x[pp][2 * q + 1], g[pp][cc].y));
+                            }
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < GS; ++cc) {
+                            x[cc % PPT][2 * q] = A::acc_fin(c, o[cc][0]);
+                            x[cc % PPT][2 * q + 1] = A::acc_fin(c, o[cc][1]);
+                        }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            ulonglong2 v = accN2[(cc * 4 + q) * TPP + t];
-                            acc[2 * q] = v.x;
-                            acc[2 * q + 1] = v.y;
+                        for (int cc = 0; cc < GS; ++cc) {
+                            ulonglong2 acc = first ? make_ulonglong2(0, 0) : accN[(cc * 4 + q) * TPP + t];
+#pragma unroll
+                            for (int pp = 0; pp < PPT; ++pp) {
+                                acc.x = A::acc_add(c, acc.x, A::mul_const(c, x[pp][2 * q], g[pp][cc].x));
+                                acc.y = A::acc_add(c, acc.y, A::mul_const(c, x[pp][2 * q + 1], g[pp][cc].y));
+                            }
+                            accN[(cc * 4 + q) * TPP + t] = acc;
                         }
                     }
-#pragma unroll
-                    for (int pp = 0; pp < PPT; ++pp) {
-                        uint64_t g[8];
-                        load8_consecutive(ggsw + (((size_t)(lv * GS + rp + pp) * GS + cc) << LOGN) + 8 * t, g);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            uint64_t prod = MONT ? A::mul_const(c, x[pp][k], g[k])
-                                                 : A::mul_full(c, A::fwd_fin(c, x[pp][k]), g[k]);
-                            acc[k] = A::acc_add(c, acc[k], prod);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        accN2[(cc * 4 + q) * TPP + t] = make_ulonglong2(acc[2 * q], acc[2 * q + 1]);
                 }
                 first = false;
-                __syncthreads();  // the tiles are reused by the next transform
+                // SINGLE: the inverse starts by writing the 8 tile positions this thread just read
+                if (!SINGLE) __syncthreads();
             }
         }
 #pragma unroll 1
-        for (int cp = 0; cp < GS; cp += PPT) {
-            uint64_t x[PPT][8];
+        for (int cg = 0; cg < PS::kGroups; ++cg) {
+            if (!SINGLE) {
 #pragma unroll
-            for (int pp = 0; pp < PPT; ++pp)
+                for (int pp = 0; pp < PPT; ++pp)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    ulonglong2 v = accN2[((cp + pp) * 4 + q) * TPP + t];
-                    x[pp][2 * q] = A::acc_fin(c, v.x);
-                    x[pp][2 * q + 1] = A::acc_fin(c, v.y);
-                }
+                    for (int q = 0; q < 4; ++q) {
+                        ulonglong2 v = accN[((cg * PPT + pp) * 4 + q) * TPP + t];
+                        x[pp][2 * q] = A::acc_fin(c, v.x);
+                        x[pp][2 * q + 1] = A::acc_fin(c, v.y);
+                    }
+            }
             inv_to_regs<A, LOGN, PPT>(x, tile, t, tw_inv, c, sub);
 #pragma unroll
             for (int pp = 0; pp < PPT; ++pp)
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     uint64_t v = (k < 4) ? A::inv_fin(c, x[pp][k]) : A::inv_fin_prod(c, x[pp][k]);
-                    uint64_t* dst = accS + (cp + pp) * N + t + k * TPP;
+                    uint64_t* dst = accS + (cg * PPT + pp) * N + t + k * TPP;
                     if (BNF) {  // normalize, modswitch p -> 2^width, wrapping add (ntt64_bnf_pbs.rs:669-673)
                         uint64_t nv = A::mul_const(c, v, n_inv);
                         *dst += FixedModulus<A>::value == Solinas64::P ? pbs::modswitch_solinas_to_pow2(nv, width)
                                                                        : pbs::modswitch_prime_to_pow2(nv, width, p);
-                    }
-                    else  // add_backward, ntt64.rs:110-131
+                    } else {  // add_backward, ntt64.rs:110-131
                         *dst = pbs::add_mod(*dst, v, p);
+                    }
                 }
             __syncthreads();
         }
@@ -188,17 +218,18 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
     }
 }
 
-// Fused blind rotation.  bsk_tw may be null (then the plain key is used).  false: no kernel for
-// this shape.
+// Fused blind rotation; bsk_tw is the key in twiddle form (fast_key_to_twiddle_form).  false: no
+// kernel for this shape.
 template <class A>
 bool fast_blind_rotate(uint64_t* acc_out, const uint64_t* lut, size_t lut_count, const unsigned* switched,
                        const uint64_t* bsk, const uint64_t* bsk_tw, size_t n_lwe, size_t glwe_size,
                        unsigned base_log, unsigned level, size_t batch, int bnf, unsigned width, int logn,
                        const typename A::TW* tw_fwd, const typename A::TW* tw_inv,
                        const typename A::Ctx& c, typename A::TW n_inv, cudaStream_t st);
-// out[i] = twiddle form of in[i] (the form A::mul_const multiplies by); false: family has none
+// out = the key `in` ([matrices][glwe_size][glwe_size][N], NTT domain) in the layout and form the
+// fused kernel reads (pbs_key_index); false: this family / shape has no fused kernel
 template <class A>
-bool fast_key_to_twiddle_form(uint64_t* out, const uint64_t* in, size_t total, const typename A::Ctx& c,
-                              cudaStream_t st);
+bool fast_key_to_twiddle_form(uint64_t* out, const uint64_t* in, size_t matrices, size_t glwe_size, int logn,
+                              const typename A::Ctx& c, cudaStream_t st);
 
 }  // namespace nttb200

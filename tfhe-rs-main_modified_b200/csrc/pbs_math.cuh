@@ -112,6 +112,20 @@ __host__ __device__ __forceinline__ uint64_t next_term_non_native(unsigned base_
     return (int64_t)t >= 0 ? t : p + t;
 }
 
+// level == 1: the whole non-native decomposition of one coefficient in closed form.  The centred
+// absolute value is below 2^63 after the shift to the native width, so its rounded top base_log
+// bits r = ((|x| << to_native >> (63 - base_log)) + 1) >> 1 are at most B/2: decompose_one_level
+// returns r with no carry, and the term is r, or p - r for the upper half (0 stays 0).
+// Identical to init_state_non_native + next_term_non_native (checked against them in the tests).
+__host__ __device__ __forceinline__ uint64_t single_level_term_non_native(uint64_t x, unsigned base_log,
+                                                                          uint64_t p) {
+    uint64_t half_up = p / 2 + (p & 1);
+    bool neg = !(x < half_up);
+    uint64_t abs_value = neg ? p - x : x;
+    uint64_t r = (((abs_value << (64 - ceil_ilog2(p))) >> (63 - base_log)) + 1) >> 1;
+    return (neg && r) ? p - r : r;
+}
+
 // modswitch_from_ntt_prime_to_power_of_two, commons/math/ntt/ntt64.rs:184-196
 __host__ __device__ __forceinline__ uint64_t modswitch_prime_to_pow2(uint64_t v, unsigned width, uint64_t p) {
     unsigned __int128 x = ((unsigned __int128)v << width) | (unsigned __int128)(p >> 1);

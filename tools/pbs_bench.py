@@ -33,7 +33,8 @@ def main():
     ap.add_argument("--bnf", action="store_true")
     ap.add_argument("--composed", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
     rng = np.random.default_rng(0)
     n_lwe, N, gs = a.n_lwe, a.poly, a.glwe_dim + 1
@@ -54,7 +55,8 @@ def main():
             G.blind_rotate_ntt64_device(key, lwe, lut, 1, acc, batch, bnf=a.bnf, path=path, stream=st)
             G.extract_lwe_sample_device(key, acc, out, batch, bnf=a.bnf, stream=st)
 
-        step()
+        for _ in range(a.warmup):
+            step()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
