@@ -310,9 +310,50 @@ def run_gpu(args):
                     "sample": "%d x (fwd+inv over 2048 polynomials), %.1f s of CPU work, %d threads" % (reps, dt, threads)}
             except Exception as e:  # the GPU numbers stand on their own
                 line["cpu_baseline"] = {"error": repr(e)}
+        if world == 1 and not args.no_pbs:
+            try:  # informational: the NTT-PBS that calls the hot path (not the headline metric)
+                line["pbs"] = pbs_leg(plan, torch)
+            except Exception as e:
+                line["pbs"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def pbs_leg(plan, torch, batch=888, n_lwe=742, base_log=23, level=1, reps=3):
+    """Programmable bootstraps per second at the reference's parameter set (tfhe test/mod.rs:106-130:
+    n_lwe 742, k 1, N 2048, base_log 23, level 1, Solinas prime), device resident, random key."""
+    import numpy as np
+    from tfhe_ntt_b200 import ntt64_pbs as G
+    rng = np.random.default_rng(1)
+    n, gs = plan.ntt_size(), 2
+    bsk = (rng.integers(0, 1 << 63, n_lwe * level * gs * gs * n, dtype=np.uint64) * np.uint64(2)) % np.uint64(SOLINAS_P)
+    key = G.NttLweBootstrapKey.from_container(plan, bsk, n_lwe, gs, base_log, level)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    lut = torch.from_numpy(rng.integers(0, 1 << 62, gs * n, dtype=np.uint64).view(np.int64)).to(dev)
+    lwe = torch.from_numpy(rng.integers(1, 1 << 62, (batch, n_lwe + 1), dtype=np.uint64).view(np.int64)).to(dev)
+    acc = torch.empty((batch, gs * n), dtype=torch.int64, device=dev)
+    out = torch.empty((batch, (gs - 1) * n + 1), dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream()
+
+    def step():
+        G.blind_rotate_ntt64_device(key, lwe, lut, 1, acc, batch, stream=st)
+        G.extract_lwe_sample_device(key, acc, out, batch, stream=st)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"value": batch / ms * 1e3, "unit": "PBS/s", "ms_per_batch": ms,
+            "config": {"workload": "programmable_bootstrap_ntt64 (classic), fused blind rotation + sample extraction",
+                       "batch": batch, "n_lwe": n_lwe, "n": n, "k": 1, "base_log": base_log, "level": level},
+            "ntt_per_s_inside": batch * n_lwe * 4 / ms * 1e3}
 
 
 def main():
@@ -323,6 +364,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--normalize", action="store_true", help="also run normalize in warm-up steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-pbs", action="store_true", help="skip the informational NTT-PBS leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
