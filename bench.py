@@ -28,7 +28,7 @@ N = 2048
 SOLINAS_P = (1 << 64) - (1 << 32) + 1
 BATCH_PER_GPU = 65536          # 65536 * 16 KiB = 1 GiB per GPU: far beyond the 126 MB L2
 ALG_BYTES_PER_NTT = 2 * N * 8  # one in-place NTT reads and writes each coefficient once
-E2E_BATCH = 32768              # host-buffer leg: 512 MiB in + 512 MiB out per step
+E2E_BATCH = 65536              # host-buffer leg: 1 GiB in + 1 GiB out per step
 NCU_TRAFFIC_PER_LAUNCH = 2.097e9  # measured by ncu --set full for one launch of this workload (see profiles/)
 METRIC = "fwd+inv NTTs/sec, N=2048 u64 prime, batched"
 UNIT = "NTT/s"
@@ -269,7 +269,8 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = 2.0 * eb * world * e2e_steps / float(te.item())
     e2e_bytes = eb * N * 8  # per step and direction
-    e2e_launches = e2e_steps * ((eb * N * 8 + (16 << 20) - 1) // (16 << 20))
+    chunk = 32 << 20  # staging chunk of the host pipeline (csrc/capi_prime.cu chunk_bytes())
+    e2e_launches = e2e_steps * ((eb * N * 8 + chunk - 1) // chunk)
 
     if rank == 0:
         peaks, which = measured_peaks()

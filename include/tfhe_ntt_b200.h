@@ -164,7 +164,7 @@ int ntt_b200_plan32_ext_product_device(const ntt_b200_plan32 *plan, uint32_t *ou
 /* Host-memory form of the fused call: lhs/out hold `batch` polynomials in host memory (pinned
  * memory lets the copies overlap the kernels); rhs / acc hold rhs_polys / acc_polys polynomials
  * (== batch, or fewer and reused cyclically; acc may be NULL).  H2D, kernel and D2H of successive
- * chunks (16 MiB) are pipelined on four streams.  out may alias lhs. */
+ * chunks (32 MiB) are pipelined on four streams.  out may alias lhs. */
 int ntt_b200_plan32_fwd_mac_inv_batch(const ntt_b200_plan32 *plan, uint32_t *out,
                                       const uint32_t *lhs, const uint32_t *rhs, size_t rhs_polys,
                                       const uint32_t *acc, size_t acc_polys, size_t batch);

@@ -181,7 +181,7 @@ def test_batch_edge_sizes(T):
         assert (y == ref.fwd(x)).all()
         plan.inv_batch(y)
         assert (y == ref.inv(ref.fwd(x))).all()
-    # several 16 MiB staging chunks with a ragged tail
+    # several 32 MiB staging chunks (1024 polynomials each) with a ragged tail
     n = 4096
     plan, ref = T.prime64.Plan.try_new(n, p), OraclePlan(64, n, p)
     batch = 2 * 1024 + 5

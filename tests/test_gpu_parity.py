@@ -237,7 +237,7 @@ def test_fwd_mac_inv_batch_host(T):
     n, p = 1024, SOLINAS_P
     gp, op = plan_pair(T, 64, n, p)
     rng = np.random.default_rng(9)
-    batch = 9000  # several staging chunks (16 MiB / 8 KiB = 2048 polynomials each), ragged tail
+    batch = 9000  # several staging chunks (32 MiB / 8 KiB = 4096 polynomials each), ragged tail
     lhs = rand_below(rng, p, (batch, n), np.uint64)
     ggsw = rand_below(rng, p, (4, n), np.uint64)
     acc = rand_below(rng, p, (2, n), np.uint64)

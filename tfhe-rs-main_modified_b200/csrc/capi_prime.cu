@@ -1,6 +1,7 @@
 // C ABI for the prime plans (include/tfhe_ntt_b200.h).  No torch, no oracle, no CPU fallback:
 // every compute entry point runs CUDA kernels or fails with NTT_B200_ERR_CUDA.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -46,8 +47,27 @@ int ntt_b200_largest_prime_in_arithmetic_progression64(uint64_t factor, uint64_t
 namespace {
 
 // ---- host-pointer paths: stage through device memory, chunked and double-buffered ---------
-constexpr size_t kChunkBytes = size_t(16) << 20;
-constexpr int kStreams = 4;  // H2D, kernel and D2H of successive chunks overlap across these
+constexpr int kMaxStreams = 8;
+// Staging chunk and the number of streams the H2D / kernel / D2H stages of successive chunks
+// overlap across; tunable for experiments through NTT_B200_CHUNK_MIB / NTT_B200_STREAMS.
+size_t chunk_bytes() {
+    static const size_t v = [] {
+        const char* e = std::getenv("NTT_B200_CHUNK_MIB");
+        long m = e ? std::atol(e) : 0;
+        return size_t(m > 0 && m <= 1024 ? m : 32) << 20;  // tools/e2e_sweep.py: 32 MiB x 4 streams
+    }();
+    return v;
+}
+int stream_count() {
+    static const int v = [] {
+        const char* e = std::getenv("NTT_B200_STREAMS");
+        long m = e ? std::atol(e) : 0;
+        return (int)(m > 0 && m <= kMaxStreams ? m : 4);
+    }();
+    return v;
+}
+#define kChunkBytes chunk_bytes()
+#define kStreams stream_count()
 
 struct Stage {
     cudaStream_t st = nullptr;
@@ -64,7 +84,7 @@ int host_transform(const PrimePlan* pl, void* host, size_t batch, bool inverse) 
         chunk_polys = std::min(chunk_polys, batch);
         size_t nchunks = (batch + chunk_polys - 1) / chunk_polys;
         int ns = (int)std::min<size_t>(kStreams, nchunks);
-        Stage sg[kStreams];
+        Stage sg[kMaxStreams];
         for (int i = 0; i < ns; ++i) {
             NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&sg[i].st, cudaStreamNonBlocking));
             NTT_CUDA_CHECK(cudaMallocAsync(&sg[i].d, chunk_polys * poly_bytes, sg[i].st));
@@ -150,8 +170,8 @@ int host_fwd_mac_inv(const PrimePlan* pl, void* out, const void* lhs, const void
         chunk = std::min(chunk, batch);
         size_t nchunks = (batch + chunk - 1) / chunk;
         int ns = (int)std::min<size_t>(kStreams, nchunks);
-        cudaStream_t st[kStreams] = {};
-        void *d_io[kStreams] = {}, *d_rhs[kStreams] = {}, *d_acc[kStreams] = {};
+        cudaStream_t st[kMaxStreams] = {};
+        void *d_io[kMaxStreams] = {}, *d_rhs[kMaxStreams] = {}, *d_acc[kMaxStreams] = {};
         void *d_rhs_shared = nullptr, *d_acc_shared = nullptr;
         cudaEvent_t shared_ready = nullptr;
         for (int i = 0; i < ns; ++i) {
