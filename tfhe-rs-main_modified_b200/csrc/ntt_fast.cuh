@@ -257,8 +257,9 @@ NTT_DEVINL void inv_to_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsign
 // ---- kernels ------------------------------------------------------------------------------
 // blockDim = (N/8, POLYS); each thread group works on PPT rows at once, so a CTA covers
 // POLYS*PPT rows.  `rows` counts rows of length N; with depth > 0 row r is sub-block
-// (r mod 2^depth) of polynomial r >> depth (PPT must be 1 then: the rows of a group would need
-// different twiddles).  Out-of-range rows are clamped and not stored (whole-CTA barriers inside).
+// (r mod 2^depth) of polynomial r >> depth; a thread group then pairs the same sub-block of PPT
+// consecutive polynomials, which share their twiddles.  Out-of-range rows are clamped and not
+// stored (whole-CTA barriers inside).
 template <class A, int LOGN, int POLYS, int PPT>
 __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
                                   FastMinBlocks<A, FastShape<LOGN>::kThreadsPerPoly * POLYS>::value)
@@ -266,17 +267,20 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
                         const typename A::TW* __restrict__ tw, typename A::Ctx c) {
     using T = typename A::T;
     using S = FastShape<LOGN>;
-    __shared__ __align__(16) T smem[POLYS * PPT * S::kPaddedElems];
+    extern __shared__ __align__(16) unsigned char fast_smem_raw[];  // POLYS * PPT padded tiles
+    T* smem = reinterpret_cast<T*>(fast_smem_raw);
     const unsigned t = threadIdx.x;
-    const size_t row0 = ((size_t)blockIdx.x * POLYS + threadIdx.y) * PPT;
-    const SubPoly sub{depth, (unsigned)row0 & ((1u << depth) - 1u)};
+    // thread group `grp` works on sub-block `half` of PPT consecutive polynomials (same twiddles)
+    const size_t grp = (size_t)blockIdx.x * POLYS + threadIdx.y;
+    const unsigned half = (unsigned)grp & ((1u << depth) - 1u);
+    const SubPoly sub{depth, half};
     T* s = smem + threadIdx.y * PPT * S::kPaddedElems;
     T x[PPT][8];
     T* g[PPT];
     bool live[PPT];
 #pragma unroll
     for (int pp = 0; pp < PPT; ++pp) {
-        size_t row = row0 + pp;
+        size_t row = ((((grp >> depth) * PPT + pp)) << depth) + half;
         live[pp] = row < rows;
         g[pp] = data + ((live[pp] ? row : rows - 1) << LOGN);
 #pragma unroll
@@ -298,17 +302,20 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
                         const typename A::TW* __restrict__ tw, typename A::Ctx c) {
     using T = typename A::T;
     using S = FastShape<LOGN>;
-    __shared__ __align__(16) T smem[POLYS * PPT * S::kPaddedElems];
+    extern __shared__ __align__(16) unsigned char fast_smem_raw[];  // POLYS * PPT padded tiles
+    T* smem = reinterpret_cast<T*>(fast_smem_raw);
     const unsigned t = threadIdx.x;
-    const size_t row0 = ((size_t)blockIdx.x * POLYS + threadIdx.y) * PPT;
-    const SubPoly sub{depth, (unsigned)row0 & ((1u << depth) - 1u)};
+    // thread group `grp` works on sub-block `half` of PPT consecutive polynomials (same twiddles)
+    const size_t grp = (size_t)blockIdx.x * POLYS + threadIdx.y;
+    const unsigned half = (unsigned)grp & ((1u << depth) - 1u);
+    const SubPoly sub{depth, half};
     T* s = smem + threadIdx.y * PPT * S::kPaddedElems;
     T x[PPT][8];
     T* g[PPT];
     bool live[PPT];
 #pragma unroll
     for (int pp = 0; pp < PPT; ++pp) {
-        size_t row = row0 + pp;
+        size_t row = ((((grp >> depth) * PPT + pp)) << depth) + half;
         live[pp] = row < rows;
         g[pp] = data + ((live[pp] ? row : rows - 1) << LOGN);
         load8_consecutive(g[pp] + 8 * t, x[pp]);
@@ -340,7 +347,8 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS)
                                 const typename A::TW* __restrict__ tw_inv, typename A::Ctx c) {
     using T = typename A::T;
     using S = FastShape<LOGN>;
-    __shared__ __align__(16) T smem[POLYS * PPT * S::kPaddedElems];
+    extern __shared__ __align__(16) unsigned char fast_smem_raw[];  // POLYS * PPT padded tiles
+    T* smem = reinterpret_cast<T*>(fast_smem_raw);
     const unsigned t = threadIdx.x;
     const size_t poly0 = ((size_t)blockIdx.x * POLYS + threadIdx.y) * PPT;
     const SubPoly sub{0u, 0u};

@@ -11,27 +11,55 @@ struct FastPolys {  // polynomials per CTA: keep CTAs at >= 256 threads
     static constexpr int value = (1 << LOGN) >= 2048 ? 1 : 2048 / (1 << LOGN);
 };
 
-// Polynomials per thread: two when both tiles fit the 48 KiB static shared-memory window and the
-// polynomial is big enough for the shared index arithmetic to matter.
+// Polynomials per thread: two when the polynomial is big enough for the shared index arithmetic
+// and twiddle loads to matter (the tiles are dynamic shared memory: 72 KiB for two 4096-point
+// u64 polynomials, still two CTAs per SM).
 template <class A, int LOGN>
 struct FastPPT {
+    static constexpr int value = LOGN >= 10 ? 2 : 1;
+};
+
+// The fused fwd -> pointwise -> inv kernel needs more registers; with two 4096-point u64
+// polynomials per thread it drops to one CTA per SM and loses (measured), so it keeps one there.
+template <class A, int LOGN>
+struct FastPPTFused {
     static constexpr bool fits =
         2 * FastPolys<LOGN>::value * FastShape<LOGN>::kPaddedElems * sizeof(typename A::T) <= 48 * 1024;
     static constexpr int value = (LOGN >= 10 && fits) ? 2 : 1;
 };
 
 template <class A, int LOGN, int PPT>
+constexpr size_t fast_smem_bytes() {
+    return (size_t)FastPolys<LOGN>::value * PPT * FastShape<LOGN>::kPaddedElems * sizeof(typename A::T);
+}
+// Kernels that need more than the default 48 KiB of dynamic shared memory opt in once per device.
+// (the kernel is a template argument so that the "done" flags are per kernel, not per signature)
+template <auto Kernel>
+void fast_allow_smem(size_t bytes) {
+    if (bytes <= 48 * 1024) return;
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done[dev]) return;
+    NTT_CUDA_CHECK(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+}
+
+template <class A, int LOGN, int PPT>
 void launch_fast_fwd_p(typename A::T* data, size_t rows, unsigned depth, const typename A::TW* tw,
                        const typename A::Ctx& c, cudaStream_t st) {
     constexpr int P = FastPolys<LOGN>::value;
     dim3 block(FastShape<LOGN>::kThreadsPerPoly, P);
-    unsigned grid = (unsigned)((rows + P * PPT - 1) / (P * PPT));
-    ntt_fast_fwd_kernel<A, LOGN, P, PPT><<<grid, block, 0, st>>>(data, rows, depth, tw, c);
+    size_t polys = rows >> depth, groups = ((polys + PPT - 1) / PPT) << depth;
+    unsigned grid = (unsigned)((groups + P - 1) / P);
+    constexpr size_t smem = fast_smem_bytes<A, LOGN, PPT>();
+    fast_allow_smem<ntt_fast_fwd_kernel<A, LOGN, P, PPT>>(smem);
+    ntt_fast_fwd_kernel<A, LOGN, P, PPT><<<grid, block, smem, st>>>(data, rows, depth, tw, c);
 }
 template <class A, int LOGN>
 void launch_fast_fwd(typename A::T* data, size_t rows, unsigned depth, const typename A::TW* tw,
                      const typename A::Ctx& c, cudaStream_t st) {
-    if (FastPPT<A, LOGN>::value == 2 && depth == 0 && rows > 1)
+    if (FastPPT<A, LOGN>::value == 2 && (rows >> depth) > 1)
         launch_fast_fwd_p<A, LOGN, FastPPT<A, LOGN>::value>(data, rows, depth, tw, c, st);
     else
         launch_fast_fwd_p<A, LOGN, 1>(data, rows, depth, tw, c, st);
@@ -41,13 +69,16 @@ void launch_fast_inv_p(typename A::T* data, size_t rows, unsigned depth, const t
                        const typename A::Ctx& c, cudaStream_t st) {
     constexpr int P = FastPolys<LOGN>::value;
     dim3 block(FastShape<LOGN>::kThreadsPerPoly, P);
-    unsigned grid = (unsigned)((rows + P * PPT - 1) / (P * PPT));
-    ntt_fast_inv_kernel<A, LOGN, P, PPT><<<grid, block, 0, st>>>(data, rows, depth, tw, c);
+    size_t polys = rows >> depth, groups = ((polys + PPT - 1) / PPT) << depth;
+    unsigned grid = (unsigned)((groups + P - 1) / P);
+    constexpr size_t smem = fast_smem_bytes<A, LOGN, PPT>();
+    fast_allow_smem<ntt_fast_inv_kernel<A, LOGN, P, PPT>>(smem);
+    ntt_fast_inv_kernel<A, LOGN, P, PPT><<<grid, block, smem, st>>>(data, rows, depth, tw, c);
 }
 template <class A, int LOGN>
 void launch_fast_inv(typename A::T* data, size_t rows, unsigned depth, const typename A::TW* tw,
                      const typename A::Ctx& c, cudaStream_t st) {
-    if (FastPPT<A, LOGN>::value == 2 && depth == 0 && rows > 1)
+    if (FastPPT<A, LOGN>::value == 2 && (rows >> depth) > 1)
         launch_fast_inv_p<A, LOGN, FastPPT<A, LOGN>::value>(data, rows, depth, tw, c, st);
     else
         launch_fast_inv_p<A, LOGN, 1>(data, rows, depth, tw, c, st);
@@ -58,10 +89,12 @@ void launch_fast_fmi(typename A::T* out, const typename A::T* lhs, const typenam
                      const typename A::TW* tw_fwd, const typename A::TW* tw_inv,
                      const typename A::Ctx& c, cudaStream_t st) {
     constexpr int P = FastPolys<LOGN>::value;
-    constexpr int PPT = FastPPT<A, LOGN>::value;
+    constexpr int PPT = FastPPTFused<A, LOGN>::value;
     dim3 block(FastShape<LOGN>::kThreadsPerPoly, P);
     unsigned grid = (unsigned)((batch + P * PPT - 1) / (P * PPT));
-    ntt_fast_fwd_mac_inv_kernel<A, LOGN, P, PPT><<<grid, block, 0, st>>>(
+    constexpr size_t smem = fast_smem_bytes<A, LOGN, PPT>();
+    fast_allow_smem<ntt_fast_fwd_mac_inv_kernel<A, LOGN, P, PPT>>(smem);
+    ntt_fast_fwd_mac_inv_kernel<A, LOGN, P, PPT><<<grid, block, smem, st>>>(
         out, lhs, rhs, rhs_polys, acc, acc_polys ? acc_polys : 1, batch, tw_fwd, tw_inv, c);
 }
 
