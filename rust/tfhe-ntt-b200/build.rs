@@ -10,7 +10,8 @@ fn main() {
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let sources = [
         "ntt_engine.cu", "ntt_fast_solinas.cu", "ntt_fast_shoup64.cu", "ntt_fast_shoup32.cu",
-        "ntt_fast_exact.cu", "capi_prime.cu", "capi_native.cu", "capi_product.cu",
+        "ntt_fast_exact.cu", "ntt_pbs_solinas.cu", "capi_prime.cu", "capi_native.cu", "capi_product.cu",
+        "capi_pbs.cu",
     ];
     let mut objects = Vec::new();
     for src in sources {

@@ -128,3 +128,20 @@ def test_gloo_world_size_2_sharding(T, tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "gloo ok" in r.stdout
+
+
+def test_rust_crate_build_lists_every_cuda_source():
+    """rust/tfhe-ntt-b200/build.rs compiles the same translation units as build.py (no rustc here to try it)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_b", os.path.join(ROOT, "tfhe-rs-main_modified_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    text = open(os.path.join(ROOT, "rust", "tfhe-ntt-b200", "build.rs")).read()
+    for src in mod.SOURCES:
+        assert '"%s"' % src in text, src
+    # and every extern "C" symbol the Rust ffi block names exists in the header
+    ffi = open(os.path.join(ROOT, "rust", "tfhe-ntt-b200", "src", "ffi.rs")).read()
+    header = open(HEADER).read()
+    import re
+    for name in re.findall(r"pub fn (ntt_b200_\w+)\(", ffi):
+        assert re.search(r"\b%s\s*\(" % name, header), name
