@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
 #pragma unroll
                     for (int pp = 0; pp < PPT; ++pp)
 #pragma unroll
-                        for (int cc = 0; cc < GS; ++cc) g[pp][cc] = gq[(size_t)q * TPP * PPT * GS + pp * GS + cc];
+                        for (int cc = 0; cc < GS; ++cc)  // read once per CTA: keep it out of L1 (twiddles live there)
+                            g[pp][cc] = __ldcg(gq + (size_t)q * TPP * PPT * GS + pp * GS + cc);
                     if (SINGLE) {
                         // out[cc] = sum_pp x[pp] * g[pp][cc], written over x (PPT == GS)
                         uint64_t o[GS][2];
