@@ -352,7 +352,7 @@ def pbs_leg(plan, torch, batch=888, n_lwe=742, base_log=23, level=1, reps=3):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     return {"value": batch / ms * 1e3, "unit": "PBS/s", "ms_per_batch": ms,
-            "config": {"workload": "programmable_bootstrap_ntt64 (classic), fused blind rotation + sample extraction",
+            "config": {"workload": "programmable_bootstrap_ntt64 (classic), persistent two-CTA-cluster blind rotation + sample extraction",
                        "batch": batch, "n_lwe": n_lwe, "n": n, "k": 1, "base_log": base_log, "level": level},
             "ntt_per_s_inside": batch * n_lwe * 4 / ms * 1e3}
 

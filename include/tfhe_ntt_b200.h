@@ -267,8 +267,10 @@ int ntt_b200_ntt64_add_backward_device(const ntt_b200_plan64 *plan, uint64_t *st
  * Containers are the reference's flat ones: lwe [n_lwe+1] (mask, body), glwe / lut / accumulator
  * [(k+1)*N], NTT bootstrap key [n_lwe][level][k+1][k+1][N] with the first level slice = level l
  * (entities/ntt_ggsw_ciphertext.rs:176-190).  New: every call takes `batch` ciphertexts.
- * `path`: 0 = fused kernel when the shape has one, else composed; 1 = fused only (ERR_CUDA when
- * there is none); 2 = composed only.  All paths give identical bits.
+ * `path`: 0 = automatic (two-CTA cluster kernel when k = 1, level = 1 and N = 512..4096; else
+ * the one-CTA fused kernel when the shape has one; else composed);
+ * 1 = one-CTA fused only, 3 = cluster only (ERR_CUDA when there is none); 2 = composed only.
+ * All paths give identical bits.
  * ------------------------------------------------------------------------------------------ */
 typedef struct ntt_b200_bsk ntt_b200_bsk;
 /* NttLweBootstrapKey::from_container   entities/ntt_lwe_bootstrap_key.rs:68-110; copies the

@@ -252,7 +252,7 @@ using Plan32 = NativePlan<NTT_B200_NATIVE_BINARY128_PLAN32, u128, uint32_t, 5, t
 // Containers are the reference's flat ones; every call takes `batch` ciphertexts.
 namespace ntt64_pbs {
 enum class NttLweBootstrapKeyOption { Raw = 0, Normalize = 1 };  // lwe_bootstrap_key_conversion.rs:283-288
-enum class Path { Auto = 0, Fused = 1, Composed = 2 };
+enum class Path { Auto = 0, Fused = 1, Composed = 2, Cluster = 3 };
 
 class NttLweBootstrapKey {
     struct Del {

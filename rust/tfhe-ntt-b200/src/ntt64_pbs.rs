@@ -12,7 +12,7 @@ pub enum NttLweBootstrapKeyOption { Raw, Normalize }
 
 /// Device path: fused persistent kernel when the shape has one, else composed kernels.
 #[derive(Copy, Clone, Debug, PartialEq, Eq)]
-pub enum Path { Auto = 0, Fused = 1, Composed = 2 }
+pub enum Path { Auto = 0, Fused = 1, Composed = 2, Cluster = 3 }
 
 /// Device-resident `NttLweBootstrapKey` (entities/ntt_lwe_bootstrap_key.rs:26-33).
 pub struct NttLweBootstrapKey { raw: *mut ffi::ntt_b200_bsk }

@@ -225,3 +225,36 @@ def test_cpp_host_mirror_pbs_example(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "cpp pbs example ok" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("bnf", [False, True])
+def test_cluster_latency_path_bit_exact(N, bnf):
+    """two-CTA cluster kernel (k = 1, level = 1): same bits as the oracle; zero mask elements skipped"""
+    import tfhe_ntt_b200 as T
+    n_lwe = 9
+    rng = np.random.default_rng(N + bnf)
+    G, key, opbs = _setup(rng, n_lwe, 1, N, 23, 1)
+    batch = 3
+    if bnf:
+        lwe = rng.integers(0, 2 * N, (batch, n_lwe + 1), dtype=np.uint64)
+        lut = _rand_u64(rng, (batch, 2 * N), 64)
+    else:
+        lwe = _rand_mod(rng, (batch, n_lwe + 1), P)
+        lut = _rand_mod(rng, (batch, 2 * N), P)
+    lwe[1, 0] = 0
+    lwe[1, 1] = 0
+    lwe[2, 4] = 0
+    got = lut.copy()
+    if bnf:
+        G.blind_rotate_ntt64_bnf_assign(lwe.reshape(-1), got.reshape(-1), key, 64, path=G.PATH_CLUSTER)
+        want = np.stack([opbs.blind_rotate_bnf(lwe[b], lut[b], 64) for b in range(batch)])
+    else:
+        G.blind_rotate_ntt64_assign(lwe.reshape(-1), got.reshape(-1), key, path=G.PATH_CLUSTER)
+        want = np.stack([opbs.blind_rotate(lwe[b], lut[b]) for b in range(batch)])
+    assert np.array_equal(got, want)
+    # shapes without a cluster kernel fail loudly when it is requested explicitly
+    G2, key2, _ = _setup(rng, 3, 1, 512, 10, 2)
+    with pytest.raises(T.NttB200Error):
+        G2.blind_rotate_ntt64_assign(_rand_mod(rng, 4, P), _rand_mod(rng, 1024, P), key2, path=G2.PATH_CLUSTER)

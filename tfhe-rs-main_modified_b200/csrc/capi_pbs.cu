@@ -3,9 +3,10 @@
 // modulus = NTT prime) and ntt64_bnf_pbs.rs (power-of-two ciphertext modulus), plus the bootstrap
 // key conversion of algorithms/lwe_bootstrap_key_conversion.rs:294-447.
 //
-// Two device paths, both batched over LWE ciphertexts:
-//  * fused: one persistent CTA per ciphertext runs the whole blind rotation with the accumulator
-//    in shared memory (ntt_fast.cuh, PrimePlan::blind_rotate) -- n = 256 ... 4096;
+// Device paths, all batched over LWE ciphertexts:
+//  * cluster / fused: one persistent two-CTA cluster (k = 1, level = 1) or one persistent CTA per
+//    ciphertext runs the whole blind rotation with the accumulator in shared memory
+//    (ntt_pbs_fused.cuh, PrimePlan::blind_rotate) -- Solinas prime, n = 256 ... 4096;
 //  * composed: per mask element, rotate/subtract/decompose kernel -> PrimePlan::ext_product ->
 //    add kernel.  Any n, any prime64 plan; also the cross-check of the fused path.
 // No torch, no oracle, no CPU fallback.
@@ -194,9 +195,18 @@ void blind_rotate_dev(const ntt_b200_bsk* key, const uint64_t* lwe, const uint64
     pbs_switch_kernel<<<grid_for(batch * lwe_size), 256, 0, st>>>(switched, lwe, batch * lwe_size, lwe_size,
                                                                  log2n, p, bnf, raw_bnf_input);
     NTT_CUDA_CHECK(cudaGetLastError());
+    // path 0: the two-CTA cluster kernel when the shape has one (k = 1, level = 1: lower latency AND
+    // higher throughput than one CTA per ciphertext, profiles/r01_pbs_bench.jsonl), else the one-CTA
+    // fused kernel, else composed; 1: one-CTA fused only; 2: composed only; 3: cluster only
+    if (path == 3 || path == 0) {
+        if (pl->blind_rotate(acc_out, lut, lut_count, switched, key->d_bsk, key->d_bsk_tw, key->n_lwe, gs,
+                             key->base_log, key->level, batch, bnf, width, 1, st))
+            return;
+        if (path == 3) throw std::runtime_error("no cluster blind-rotation kernel for this shape");
+    }
     if (path != 2 &&
         pl->blind_rotate(acc_out, lut, lut_count, switched, key->d_bsk, key->d_bsk_tw, key->n_lwe, gs,
-                         key->base_log, key->level, batch, bnf, width, st))
+                         key->base_log, key->level, batch, bnf, width, 0, st))
         return;
     if (path == 1) throw std::runtime_error("no fused blind-rotation kernel for this shape");
     uint64_t* acc = bnf ? sc.get<uint64_t>(batch * per) : acc_out;

@@ -161,10 +161,14 @@ struct PlanImpl final : PrimePlan {
     std::shared_ptr<PrimePlan> clone() const override { return std::make_shared<PlanImpl>(*this); }
     bool blind_rotate(uint64_t* acc_out, const uint64_t* lut, size_t lut_count, const unsigned* switched,
                       const uint64_t* bsk, const uint64_t* bsk_tw, size_t n_lwe, size_t glwe_size,
-                      unsigned base_log, unsigned level, size_t batch, int bnf, unsigned width,
+                      unsigned base_log, unsigned level, size_t batch, int bnf, unsigned width, int latency,
                       cudaStream_t st) const override {
         if constexpr (std::is_same<A, Solinas64>::value) {
             DeviceGuard g(device);
+            if (latency)
+                return fast_blind_rotate_cluster<A>(acc_out, lut, lut_count, switched, bsk_tw, n_lwe, glwe_size,
+                                                    base_log, level, batch, bnf, width, logn, d_fwd.get(),
+                                                    d_inv.get(), ctx, n_inv, st);
             return fast_blind_rotate<A>(acc_out, lut, lut_count, switched, bsk, bsk_tw, n_lwe, glwe_size,
                                         base_log, level, batch, bnf, width, logn, d_fwd.get(), d_inv.get(), ctx,
                                         n_inv, st);

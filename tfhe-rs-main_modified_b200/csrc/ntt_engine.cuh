@@ -65,10 +65,13 @@ struct PrimePlan {
     // switched[b][n_lwe+1] under the NTT-domain key bsk.  Returns false when this plan / shape has
     // no fused kernel (the caller then composes ext_product with elementwise kernels).
     // bsk_tw: the key in the family's twiddle form (key_to_twiddle_form), or null.
+    // latency != 0 asks for the two-CTA cluster kernel (one ciphertext per CTA pair; k = 1, level = 1).
     virtual bool blind_rotate(uint64_t* acc_out, const uint64_t* lut, size_t lut_count,
                               const unsigned* switched, const uint64_t* bsk, const uint64_t* bsk_tw,
                               size_t n_lwe, size_t glwe_size, unsigned base_log, unsigned level,
-                              size_t batch, int bnf, unsigned width, cudaStream_t stream) const {
+                              size_t batch, int bnf, unsigned width, int latency,
+                              cudaStream_t stream) const {
+        (void)latency;
         (void)acc_out, (void)lut, (void)lut_count, (void)switched, (void)bsk, (void)bsk_tw, (void)n_lwe;
         (void)glwe_size, (void)base_log, (void)level, (void)batch, (void)bnf, (void)width, (void)stream;
         return false;

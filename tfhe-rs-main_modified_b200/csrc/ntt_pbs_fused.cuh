@@ -13,6 +13,8 @@
 // decomposer state of a coefficient is recomputed per level (cheap next to a transform) instead
 // of being kept in registers across the transforms.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ntt_fast.cuh"
 #include "pbs_math.cuh"
 
@@ -219,6 +221,126 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
     }
 }
 
+// Latency variant for small batches (k = 1, level = 1): a thread-block cluster of two CTAs shares
+// one ciphertext, CTA r owning accumulator polynomial r.  Per CMUX each CTA decomposes and
+// forward-transforms its own polynomial, multiplies it by row r of the GGSW, keeps the product
+// for its own column and writes the product for the other column into the peer's shared memory
+// (distributed shared memory, ping-pong buffers), one cluster barrier, then adds the peer's
+// contribution, inverse-transforms and updates its polynomial.  Same arithmetic, same bits as the
+// one-CTA kernel; half the transforms per SM per CMUX.
+template <int LOGN>
+struct PbsClusterShape {
+    static constexpr size_t kTile = FastShape<LOGN>::kPaddedElems;
+    static constexpr size_t kAcc = (size_t)1 << LOGN;
+    static constexpr size_t kXbuf = (size_t)2 << LOGN;  // two exchange buffers of one polynomial (ping-pong)
+    static constexpr int kThreads = FastShape<LOGN>::kThreadsPerPoly;
+    // 69 KiB of shared memory at N = 2048 and 80 registers: 3 CTAs per SM.  (A single exchange buffer
+    // with a second, split-phase barrier fits 4 CTAs at 64 registers: same peak throughput, +10 %
+    // latency -- measured, not kept.)
+    static constexpr int kMinBlocks = 768 / kThreads > 0 ? 768 / kThreads : 1;
+    static size_t bytes(size_t n_lwe) { return (kTile + kAcc + kXbuf) * 8 + (n_lwe + 1) * 4; }
+};
+
+template <class A, int LOGN, bool BNF>
+__global__ void __cluster_dims__(2, 1, 1)
+    __launch_bounds__(PbsClusterShape<LOGN>::kThreads, PbsClusterShape<LOGN>::kMinBlocks)
+        ntt_fast_blind_rotate_cluster2_kernel(uint64_t* __restrict__ acc_out, const uint64_t* __restrict__ lut,
+                                          size_t lut_count, const unsigned* __restrict__ switched,
+                                          const uint64_t* __restrict__ bsk_tw, unsigned n_lwe,
+                                          unsigned base_log, unsigned width,
+                                          const typename A::TW* __restrict__ tw_fwd,
+                                          const typename A::TW* __restrict__ tw_inv, typename A::Ctx c,
+                                          typename A::TW n_inv) {
+    namespace cg = cooperative_groups;
+    using S = FastShape<LOGN>;
+    using CS = PbsClusterShape<LOGN>;
+    constexpr unsigned N = 1u << LOGN, TPP = S::kThreadsPerPoly, GS = 2;
+    extern __shared__ __align__(16) uint64_t pbs_smem[];
+    uint64_t* tile = pbs_smem;
+    uint64_t* accS = pbs_smem + CS::kTile;                                  // polynomial r of the accumulator
+    ulonglong2* xbuf = reinterpret_cast<ulonglong2*>(accS + CS::kAcc);      // [2][4][TPP] vectors
+    unsigned* sw = reinterpret_cast<unsigned*>(accS + CS::kAcc + CS::kXbuf);
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned r = cluster.block_rank();
+    ulonglong2* peer_xbuf = cluster.map_shared_rank(xbuf, r ^ 1u);
+    const unsigned t = threadIdx.x;
+    const size_t b = blockIdx.x >> 1;
+    const uint64_t p = FixedModulus<A>::value ? FixedModulus<A>::value : c.p;
+    const SubPoly sub{0u, 0u};
+
+    for (unsigned i = t; i <= n_lwe; i += TPP) sw[i] = switched[b * (n_lwe + 1) + i];
+    __syncthreads();
+    const unsigned body = sw[n_lwe] & ~kPbsSkip;
+    {
+        const uint64_t* l = lut + (b % lut_count) * (size_t)(GS * N) + (size_t)r * N;
+        for (unsigned j = t; j < N; j += TPP) accS[j] = BNF ? l[j] : pbs::monomial_div_coeff(l, j, body, LOGN, p);
+    }
+    cluster.sync();  // both CTAs are resident before any remote shared-memory write
+
+    // Ping-pong exchange buffers indexed by the number of executed CMUXes: the peer's write of round
+    // e + 2 into the buffer of round e comes after barrier e + 1, which this CTA reaches only after
+    // it has read round e.
+    unsigned executed = 0;
+    for (unsigned i = 0; i < n_lwe; ++i) {
+        const unsigned a = sw[i];
+        if (a & kPbsSkip) continue;  // uniform over the cluster
+        const ulonglong2* gq = reinterpret_cast<const ulonglong2*>(bsk_tw + (size_t)i * GS * GS * N) +
+                               pbs_key_index<LOGN, GS>(0, 0, t, r, 0, 0) / 2;
+        uint64_t x[1][8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            unsigned j = t + k * TPP;
+            uint64_t rot = pbs::monomial_mul_coeff(accS, j, a, LOGN, BNF ? 0 : p);
+            uint64_t d;
+            if (BNF) {
+                uint64_t state = pbs::init_decomposer_state_native(rot - accS[j], base_log, 1);
+                d = pbs::decompose_one_level(base_log, state);
+                d = (int64_t)d < 0 ? d + p : d;
+            } else {
+                d = pbs::single_level_term_non_native(pbs::sub_mod(rot, accS[j], p), base_log, p);
+            }
+            x[0][k] = d;
+        }
+        fwd_from_regs<A, LOGN, 1>(x, tile, t, tw_fwd, c, sub);
+        ulonglong2* send = peer_xbuf + (size_t)(executed & 1u) * 4 * TPP;
+        const ulonglong2* recv = xbuf + (size_t)(executed & 1u) * 4 * TPP;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            ulonglong2 g_own = __ldcg(gq + (size_t)q * TPP * 4 + r);         // column r
+            ulonglong2 g_peer = __ldcg(gq + (size_t)q * TPP * 4 + (r ^ 1u));  // column 1 - r
+            send[q * TPP + t] = make_ulonglong2(A::mul_const(c, x[0][2 * q], g_peer.x),
+                                                A::mul_const(c, x[0][2 * q + 1], g_peer.y));
+            x[0][2 * q] = A::mul_const(c, x[0][2 * q], g_own.x);
+            x[0][2 * q + 1] = A::mul_const(c, x[0][2 * q + 1], g_own.y);
+        }
+        cluster.sync();  // the peer's products for my column have landed
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            ulonglong2 v = recv[q * TPP + t];
+            x[0][2 * q] = A::acc_fin(c, A::acc_add(c, x[0][2 * q], v.x));
+            x[0][2 * q + 1] = A::acc_fin(c, A::acc_add(c, x[0][2 * q + 1], v.y));
+        }
+        ++executed;
+        inv_to_regs<A, LOGN, 1>(x, tile, t, tw_inv, c, sub);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint64_t v = (k < 4) ? A::inv_fin(c, x[0][k]) : A::inv_fin_prod(c, x[0][k]);
+            uint64_t* dst = accS + t + k * TPP;
+            if (BNF) {
+                uint64_t nv = A::mul_const(c, v, n_inv);
+                *dst += FixedModulus<A>::value == Solinas64::P ? pbs::modswitch_solinas_to_pow2(nv, width)
+                                                               : pbs::modswitch_prime_to_pow2(nv, width, p);
+            } else {
+                *dst = pbs::add_mod(*dst, v, p);
+            }
+        }
+        __syncthreads();
+    }
+    uint64_t* o = acc_out + b * (size_t)(GS * N) + (size_t)r * N;
+    for (unsigned j = t; j < N; j += TPP) o[j] = BNF ? pbs::monomial_div_coeff(accS, j, body, LOGN, 0) : accS[j];
+    cluster.sync();  // no CTA leaves while its peer could still address its shared memory
+}
+
 // Fused blind rotation; bsk_tw is the key in twiddle form (fast_key_to_twiddle_form).  false: no
 // kernel for this shape.
 template <class A>
@@ -227,6 +349,13 @@ bool fast_blind_rotate(uint64_t* acc_out, const uint64_t* lut, size_t lut_count,
                        unsigned base_log, unsigned level, size_t batch, int bnf, unsigned width, int logn,
                        const typename A::TW* tw_fwd, const typename A::TW* tw_inv,
                        const typename A::Ctx& c, typename A::TW n_inv, cudaStream_t st);
+// The two-CTA cluster (latency) variant: k = 1, level = 1 only.
+template <class A>
+bool fast_blind_rotate_cluster(uint64_t* acc_out, const uint64_t* lut, size_t lut_count, const unsigned* switched,
+                               const uint64_t* bsk_tw, size_t n_lwe, size_t glwe_size, unsigned base_log,
+                               unsigned level, size_t batch, int bnf, unsigned width, int logn,
+                               const typename A::TW* tw_fwd, const typename A::TW* tw_inv,
+                               const typename A::Ctx& c, typename A::TW n_inv, cudaStream_t st);
 // out = the key `in` ([matrices][glwe_size][glwe_size][N], NTT domain) in the layout and form the
 // fused kernel reads (pbs_key_index); false: this family / shape has no fused kernel
 template <class A>

@@ -106,6 +106,50 @@ bool fast_blind_rotate<Solinas64>(uint64_t* acc_out, const uint64_t* lut, size_t
 #undef NTT_PBS_CASE
 }
 
+namespace {
+template <class A, int LOGN, bool BNF>
+bool launch_cluster(uint64_t* acc_out, const uint64_t* lut, size_t lut_count, const unsigned* switched,
+                    const uint64_t* bsk_tw, size_t n_lwe, unsigned base_log, size_t batch, unsigned width,
+                    const typename A::TW* tw_fwd, const typename A::TW* tw_inv, const typename A::Ctx& c,
+                    typename A::TW n_inv, cudaStream_t st) {
+    auto kern = ntt_fast_blind_rotate_cluster2_kernel<A, LOGN, BNF>;
+    size_t smem = PbsClusterShape<LOGN>::bytes(n_lwe);
+    if (smem > size_t(227) * 1024) return false;
+    NTT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)(2 * batch), FastShape<LOGN>::kThreadsPerPoly, smem, st>>>(
+        acc_out, lut, lut_count, switched, bsk_tw, (unsigned)n_lwe, base_log, width, tw_fwd, tw_inv, c, n_inv);
+    NTT_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+}  // namespace
+
+template <>
+bool fast_blind_rotate_cluster<Solinas64>(uint64_t* acc_out, const uint64_t* lut, size_t lut_count,
+                                          const unsigned* switched, const uint64_t* bsk_tw, size_t n_lwe,
+                                          size_t glwe_size, unsigned base_log, unsigned level, size_t batch,
+                                          int bnf, unsigned width, int logn, const uint64_t* tw_fwd,
+                                          const uint64_t* tw_inv, const Solinas64::Ctx& c, uint64_t n_inv,
+                                          cudaStream_t st) {
+    using A = Solinas64;
+    if (!bsk_tw || glwe_size != 2 || level != 1) return false;
+    if (!batch) return true;
+    if (batch > 0x3fffffffull) return false;
+#define NTT_PBS_CASE(L)                                                                                         \
+    case L:                                                                                                     \
+        return bnf ? launch_cluster<A, L, true>(acc_out, lut, lut_count, switched, bsk_tw, n_lwe, base_log,     \
+                                                batch, width, tw_fwd, tw_inv, c, n_inv, st)                    \
+                   : launch_cluster<A, L, false>(acc_out, lut, lut_count, switched, bsk_tw, n_lwe, base_log,    \
+                                                 batch, width, tw_fwd, tw_inv, c, n_inv, st);
+    switch (logn) {
+        NTT_PBS_CASE(9)
+        NTT_PBS_CASE(10)
+        NTT_PBS_CASE(11)
+        NTT_PBS_CASE(12)
+        default: return false;
+    }
+#undef NTT_PBS_CASE
+}
+
 template <>
 bool fast_key_to_twiddle_form<Solinas64>(uint64_t* out, const uint64_t* in, size_t matrices, size_t glwe_size,
                                          int logn, const Solinas64::Ctx&, cudaStream_t st) {

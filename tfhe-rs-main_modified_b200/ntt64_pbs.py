@@ -14,7 +14,7 @@ import numpy as np
 from . import _binding as B
 from . import prime64
 
-PATH_AUTO, PATH_FUSED, PATH_COMPOSED = 0, 1, 2
+PATH_AUTO, PATH_FUSED, PATH_COMPOSED, PATH_CLUSTER = 0, 1, 2, 3
 
 # NttLweBootstrapKeyOption (lwe_bootstrap_key_conversion.rs:283-288)
 RAW, NORMALIZE = 0, 1

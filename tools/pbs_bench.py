@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--level", type=int, default=1)
     ap.add_argument("--bnf", action="store_true")
     ap.add_argument("--composed", action="store_true")
+    ap.add_argument("--cluster", action="store_true", help="two-CTA cluster (latency) kernel")
+    ap.add_argument("--fused", action="store_true", help="one-CTA fused kernel only")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -43,7 +45,7 @@ def main():
     key = G.NttLweBootstrapKey.from_container(plan, bsk, n_lwe, gs, a.base_log, a.level)
     dev = torch.device("cuda:0")
     lut = torch.from_numpy((rng.integers(0, 1 << 62, gs * N, dtype=np.uint64)).view(np.int64)).to(dev)
-    path = G.PATH_COMPOSED if a.composed else G.PATH_AUTO
+    path = G.PATH_COMPOSED if a.composed else G.PATH_CLUSTER if a.cluster else G.PATH_FUSED if a.fused else G.PATH_AUTO
     for batch in [int(x) for x in a.batches.split(",")]:
         lwe_h = rng.integers(1, 1 << 62, (batch, n_lwe + 1), dtype=np.uint64)
         lwe = torch.from_numpy(lwe_h.view(np.int64)).to(dev)
@@ -67,7 +69,7 @@ def main():
         ms = e0.elapsed_time(e1) / a.reps
         ntts = batch * n_lwe * (gs * a.level + gs)
         print(json.dumps({"what": "pbs", "variant": "bnf" if a.bnf else "classic",
-                          "path": "composed" if a.composed else "fused", "batch": batch, "ms": ms,
+                          "path": "composed" if a.composed else "cluster" if a.cluster else "fused" if a.fused else "auto", "batch": batch, "ms": ms,
                           "pbs_per_s": batch / ms * 1e3, "ms_per_pbs_latency": ms,
                           "ntt_per_s": ntts / ms * 1e3, "n_lwe": n_lwe, "N": N, "k": a.glwe_dim,
                           "level": a.level}), flush=True)
