@@ -245,8 +245,16 @@ struct Solinas64 {
     }
     // canonical representative of an arbitrary 64-bit value: a >= p <=> a + eps wraps
     NTT_DEVINL static uint64_t canon(uint64_t a) {
-        uint64_t u = a + EPS;
-        return u < a ? u : a;
+        // a >= p  <=>  high word all ones and low word nonzero; then a - p = (0 : lo - 1)
+        uint64_t r;
+        asm("{ .reg .pred q0,q1; .reg .u32 lo,hi;\n\t"
+            "mov.b64 {lo,hi}, %1;\n\t"
+            "setp.eq.u32 q0,hi,0xFFFFFFFF; setp.ne.and.u32 q1,lo,0,q0;\n\t"
+            "@q1 add.u32 lo,lo,0xFFFFFFFF; @q1 mov.u32 hi,0;\n\t"
+            "mov.b64 %0, {lo,hi}; }"
+            : "=l"(r)
+            : "l"(a));
+        return r;
     }
     // plain (non-Montgomery) product of two arbitrary 64-bit values, canonical:
     // the reference's fold (generic_solinas.rs:102-128) with 2^64 == eps, 2^96 == -1
