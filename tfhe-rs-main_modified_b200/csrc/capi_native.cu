@@ -53,16 +53,21 @@ __device__ inline U128 u128_mul(U128 a, U128 b) {  // wrapping
 }
 inline U128 to_U128(u128 v) { return U128{(uint64_t)v, (uint64_t)(v >> 64)}; }
 
+struct Sh32 {
+    uint32_t v, s;
+};
 // All CRT constants (lib.rs:517-598, :639-653), by value as a kernel parameter.
 struct CrtConsts {
     uint32_t P[10];
     uint64_t P_b64[10];  // floor(2^64 / P_i): exact 64-bit Barrett for `% P_i`
     uint32_t P_c64[10];  // 2^64 mod P_i (u128 split)
+    uint32_t P_c32[10];  // 2^32 mod P_i, floor(2^32 / P_i): the one-word split of rem64_p30
+    uint32_t P_mu32[10];
     uint64_t Q[3];       // primes52 P0..P2
     uint64_t Q_b64[3];
-    // primes32
-    uint32_t P0_INV_MOD_P1, P01_INV_MOD_P2, P1_INV_MOD_P2, P3_INV_MOD_P4;
-    uint32_t P2_INV_MOD_P3, P4_INV_MOD_P5, P6_INV_MOD_P7, P8_INV_MOD_P9;
+    // primes32: Garner constants with their 32-bit Shoup companions floor(v * 2^32 / P)
+    Sh32 P0_INV_MOD_P1, P01_INV_MOD_P2, P1_INV_MOD_P2, P3_INV_MOD_P4;
+    Sh32 P2_INV_MOD_P3, P4_INV_MOD_P5, P6_INV_MOD_P7, P8_INV_MOD_P9, P0_MOD_P2;
     uint64_t P12, P34, P0_INV_MOD_P12, P0_INV_MOD_P12_SHOUP, P0_MOD_P34_SHOUP, P012_INV_MOD_P34,
         P012_INV_MOD_P34_SHOUP;
     uint64_t P01, P23, P45, P67, P89;
@@ -89,12 +94,16 @@ CrtConsts make_consts() {
         k.P[i] = P[i];
         k.P_b64[i] = ~uint64_t(0) / P[i];
         k.P_c64[i] = (uint32_t)((((u128)1) << 64) % P[i]);
+        k.P_c32[i] = (uint32_t)((uint64_t(1) << 32) % P[i]);
+        k.P_mu32[i] = (uint32_t)((uint64_t(1) << 32) / P[i]);
     }
     for (int i = 0; i < 3; ++i) {
         k.Q[i] = pm::kPrimes52[i];
         k.Q_b64[i] = ~uint64_t(0) / k.Q[i];
     }
-    auto inv32 = [](uint32_t x, uint32_t p) { return (uint32_t)pm::inv_mod_prime(x % p, p); };
+    auto sh32 = [](uint32_t v, uint32_t p) { return Sh32{v, (uint32_t)(((uint64_t)v << 32) / p)}; };
+    auto inv32 = [&](uint32_t x, uint32_t p) { return sh32((uint32_t)pm::inv_mod_prime(x % p, p), p); };
+    k.P0_MOD_P2 = sh32(P[0] % P[2], P[2]);
     k.P0_INV_MOD_P1 = inv32(P[0], P[1]);
     k.P01_INV_MOD_P2 = inv32((uint32_t)pm::mulmod(P[0], P[1], P[2]), P[2]);
     k.P1_INV_MOD_P2 = inv32(P[1], P[2]);
@@ -150,9 +159,24 @@ CrtConsts make_consts() {
 }
 
 // ---- device arithmetic for the recombinations -------------------------------------------
-// exact (a*b) mod p, p < 2^32  (reference mul_mod32 = `%`, native32.rs:21-24)
-NTT_DEVINL uint32_t mm32(uint32_t p, uint64_t b64, uint32_t a, uint32_t b) {
-    return barrett32((uint64_t)a * b, p, b64);
+// exact (a*b) mod p for a Garner constant a < p given with its Shoup companion and any 32-bit b
+// (reference mul_mod32 = `%`, native32.rs:21-24): b*a - floor(b*a'/2^32)*p lies in [0, 2p)
+NTT_DEVINL uint32_t mm32(uint32_t p, Sh32 a, uint32_t b) {
+    uint32_t q = __umulhi(b, a.s);
+    uint32_t r = b * a.v - q * p;
+    return umin_<uint32_t>(r, r - p);
+}
+// exact v % p for the CRT primes (2^29 < p < 2^30): reduce the high word, then one narrow Barrett
+// step on hi' * (2^32 mod p) + lo < p^2 + 2^32 (see barrett32_narrow; shift 29)
+NTT_DEVINL uint32_t rem64_p30(uint64_t v, uint32_t p, uint32_t mu32, uint32_t c32, uint32_t bar_mu) {
+    uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    uint32_t h = hi - __umulhi(hi, mu32) * p;  // [0, 2p)
+    h = umin_<uint32_t>(h, h - p);
+    return barrett32_narrow((uint64_t)h * c32 + lo, p, 2 * p, bar_mu, 29);
+}
+NTT_DEVINL uint32_t rem32_p30(uint32_t v, uint32_t p, uint32_t mu32) {
+    uint32_t h = v - __umulhi(v, mu32) * p;  // [0, 2p)
+    return umin_<uint32_t>(h, h - p);
 }
 // native64.rs:36-40 (Shoup product with one conditional subtract), restated literally
 NTT_DEVINL uint64_t mm64s(uint64_t p_neg, uint64_t a, uint64_t b, uint64_t b_shoup) {
@@ -202,8 +226,8 @@ __global__ void crt_split_kernel(const VT* __restrict__ value, ResPtrs res, int 
 }
 
 // pairwise Garner used by the v2 recombinations: (ra mod Pa, rb mod Pb) -> value mod Pa*Pb
-NTT_DEVINL uint64_t pair32(const CrtConsts& k, int a, int b, uint32_t inv, uint32_t ra, uint32_t rb) {
-    uint32_t vb = mm32(k.P[b], k.P_b64[b], inv, 2 * k.P[b] + rb - ra);
+NTT_DEVINL uint64_t pair32(const CrtConsts& k, int a, int b, Sh32 inv, uint32_t ra, uint32_t rb) {
+    uint32_t vb = mm32(k.P[b], inv, 2 * k.P[b] + rb - ra);
     return (uint64_t)ra + (uint64_t)vb * k.P[a];
 }
 
@@ -215,9 +239,8 @@ NTT_DEVINL void crt_with(const CrtConsts& k, R32 r32, R64 r64, size_t i, void* v
         // native32.rs:27-55 / native_binary64.rs:32-60 (same Garner chain, u32 vs u64 accumulation)
         uint32_t P0 = k.P[0], P1 = k.P[1], P2 = k.P[2];
         uint32_t v0 = r32(0);
-        uint32_t v1 = mm32(P1, k.P_b64[1], k.P0_INV_MOD_P1, 2 * P1 + r32(1) - v0);
-        uint32_t v2 = mm32(P2, k.P_b64[2], k.P01_INV_MOD_P2,
-                           2 * P2 + r32(2) - (v0 + mm32(P2, k.P_b64[2], P0, v1)));
+        uint32_t v1 = mm32(P1, k.P0_INV_MOD_P1, 2 * P1 + r32(1) - v0);
+        uint32_t v2 = mm32(P2, k.P01_INV_MOD_P2, 2 * P2 + r32(2) - (v0 + mm32(P2, k.P0_MOD_P2, v1)));
         bool sign = v2 > P2 / 2;
         if constexpr (KIND == NTT_B200_NATIVE32_PLAN32) {
             uint32_t _01 = P0 * P1, _012 = _01 * P2;
@@ -304,7 +327,7 @@ NTT_DEVINL void crt_with(const CrtConsts& k, R32 r32, R64 r64, size_t i, void* v
         // native_binary32.rs:21-40
         uint32_t P0 = k.P[0], P1 = k.P[1];
         uint32_t v0 = r32(0);
-        uint32_t v1 = mm32(P1, k.P_b64[1], k.P0_INV_MOD_P1, 2 * P1 + r32(1) - v0);
+        uint32_t v1 = mm32(P1, k.P0_INV_MOD_P1, 2 * P1 + r32(1) - v0);
         bool sign = v1 > P1 / 2;
         uint32_t pos = v0 + v1 * P0;
         static_cast<uint32_t*>(value)[i] = sign ? pos - P0 * P1 : pos;
@@ -366,8 +389,14 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly)
         uint32_t x[1][8], y[1][8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            x[0][q] = (uint32_t)rem64((uint64_t)lv[q], k.P[j], k.P_b64[j]);
-            y[0][q] = BINARY ? (uint32_t)rv[q] : (uint32_t)rem64((uint64_t)rv[q], k.P[j], k.P_b64[j]);
+            if constexpr (sizeof(VT) == 4) {
+                x[0][q] = rem32_p30((uint32_t)lv[q], k.P[j], k.P_mu32[j]);
+                y[0][q] = BINARY ? (uint32_t)rv[q] : rem32_p30((uint32_t)rv[q], k.P[j], k.P_mu32[j]);
+            } else {
+                x[0][q] = rem64_p30((uint64_t)lv[q], k.P[j], k.P_mu32[j], k.P_c32[j], P.ctx[j].bar_mu);
+                y[0][q] = BINARY ? (uint32_t)rv[q]
+                                 : rem64_p30((uint64_t)rv[q], k.P[j], k.P_mu32[j], k.P_c32[j], P.ctx[j].bar_mu);
+            }
         }
         fwd_from_regs<S32H, LOGN, 1>(x, smem, t, P.fwd[j], P.ctx[j], sub);
         __syncthreads();  // everyone has read its last-pass inputs before the tile is reused

@@ -55,6 +55,9 @@ struct Shoup {
         T pinv;     // p^-1 mod 2^W
         T r2;       // 2^(2W) mod p
         uint64_t barrett64;  // floor(2^64 / p), W=32 only
+        // W=32, p < 2^30: one-word Barrett for products of canonical operands (barrett32_narrow)
+        uint32_t bar_mu;     // floor(2^(k+31) / p), k = bit length of p
+        uint32_t bar_shift;  // k - 1
     };
     static constexpr bool kHarvey = HARVEY;
 
@@ -131,9 +134,21 @@ NTT_DEVINL uint32_t barrett32(uint64_t d, uint32_t p, uint64_t b64) {
     uint64_t r = d - q * p;           // < 2p
     return (uint32_t)(r >= p ? r - p : r);
 }
+// exact d mod p for d < p^2, p < 2^30 (k = bit length of p): with s = floor(d / 2^(k-1)) < 2^32 and
+// mu = floor(2^(k+31) / p) < 2^32 the estimate q = floor(s * mu / 2^32) satisfies
+// floor(d/p) - 2 <= q <= floor(d/p)   (d / 2^(k+31) <= 1/2 and 2^(k-1) / p <= 1),
+// so d - q*p lies in [0, 3p) < 2^32 and one 32-bit multiply-subtract plus two conditional
+// subtractions finish.  One IMAD.HI + one IMAD against the four IMAD.WIDE of the 64-bit Barrett.
+NTT_DEVINL uint32_t barrett32_narrow(uint64_t d, uint32_t p, uint32_t two_p, uint32_t mu, uint32_t shift) {
+    uint32_t s = __funnelshift_r((uint32_t)d, (uint32_t)(d >> 32), shift);
+    uint32_t q = __umulhi(s, mu);
+    uint32_t r = (uint32_t)d - q * p;
+    r = umin_<uint32_t>(r, r - two_p);
+    return umin_<uint32_t>(r, r - p);
+}
 template <>
 NTT_DEVINL uint32_t Shoup<uint32_t, true>::mul_full(const Ctx& c, uint32_t a, uint32_t b) {
-    return barrett32((uint64_t)a * b, c.p, c.barrett64);
+    return barrett32_narrow((uint64_t)a * b, c.p, c.two_p, c.bar_mu, c.bar_shift);
 }
 template <>
 NTT_DEVINL uint32_t Shoup<uint32_t, false>::mul_full(const Ctx& c, uint32_t a, uint32_t b) {

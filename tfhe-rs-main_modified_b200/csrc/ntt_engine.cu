@@ -56,6 +56,9 @@ struct Build<Shoup<T, H>> {
             c.r2 = (T)pm::mulmod(r, r, p);
         } else {
             c.barrett64 = ~uint64_t(0) / p;
+            int k = 64 - __builtin_clzll(p);  // bit length
+            c.bar_shift = (uint32_t)(k - 1);
+            c.bar_mu = (uint32_t)((((u128)1) << (k + 31)) / p);
         }
         return c;
     }
