@@ -367,55 +367,72 @@ struct FusedPrimes {
     S32H::TW n_inv[NP];
 };
 
+// Register budget: the residues of the first NP-1 primes wait for the Garner step in shared memory
+// (each thread reads back exactly what it wrote, layout [prime][q][thread]: conflict free), the
+// operands are re-read per prime (L1/L2 hits after the first), so a thread holds 16 residues at a
+// time and two 512-thread CTAs fit an SM.
+template <int LOGN>
+struct FusedMinBlocks {
+    static constexpr int value = 1024 / FastShape<LOGN>::kThreadsPerPoly > 0 ? 1024 / FastShape<LOGN>::kThreadsPerPoly : 1;
+};
+template <int NP, int LOGN>
+constexpr size_t fused_smem_bytes() {
+    return (size_t)(FastShape<LOGN>::kPaddedElems + (NP - 1) * (1 << LOGN)) * sizeof(uint32_t);
+}
+
 template <int KIND, class VT, int NP, int LOGN, bool BINARY>
-__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly)
+__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly, FusedMinBlocks<LOGN>::value)
     native_polymul_fused_kernel(VT* __restrict__ prod, const VT* __restrict__ lhs,
                                 const VT* __restrict__ rhs, FusedPrimes<NP> P, CrtConsts k) {
     using S = FastShape<LOGN>;
     constexpr int TPP = S::kThreadsPerPoly;
-    __shared__ __align__(16) uint32_t smem[S::kPaddedElems];
+    extern __shared__ __align__(16) unsigned char fused_smem_raw[];
+    uint32_t* smem = reinterpret_cast<uint32_t*>(fused_smem_raw);  // transform tile
+    uint32_t* res_s = smem + S::kPaddedElems;                       // residues of primes 0 .. NP-2
     const unsigned t = threadIdx.x;
     const size_t base = (size_t)blockIdx.x << LOGN;
     const SubPoly sub{0u, 0u};
-    VT lv[8], rv[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        lv[q] = lhs[base + t + q * TPP];
-        rv[q] = rhs[base + t + q * TPP];
-    }
-    uint32_t res[NP][8];
-#pragma unroll
+    uint32_t last[8];  // residues of the last prime stay in registers
+#pragma unroll 1
     for (int j = 0; j < NP; ++j) {
+        const uint32_t pj = k.P[j], mu32 = k.P_mu32[j], c32 = k.P_c32[j];
+        const S32H::Ctx ctx = P.ctx[j];
         uint32_t x[1][8], y[1][8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
+            const VT lv = lhs[base + t + q * TPP], rv = rhs[base + t + q * TPP];
             if constexpr (sizeof(VT) == 4) {
-                x[0][q] = rem32_p30((uint32_t)lv[q], k.P[j], k.P_mu32[j]);
-                y[0][q] = BINARY ? (uint32_t)rv[q] : rem32_p30((uint32_t)rv[q], k.P[j], k.P_mu32[j]);
+                x[0][q] = rem32_p30((uint32_t)lv, pj, mu32);
+                y[0][q] = BINARY ? (uint32_t)rv : rem32_p30((uint32_t)rv, pj, mu32);
             } else {
-                x[0][q] = rem64_p30((uint64_t)lv[q], k.P[j], k.P_mu32[j], k.P_c32[j], P.ctx[j].bar_mu);
-                y[0][q] = BINARY ? (uint32_t)rv[q]
-                                 : rem64_p30((uint64_t)rv[q], k.P[j], k.P_mu32[j], k.P_c32[j], P.ctx[j].bar_mu);
+                x[0][q] = rem64_p30((uint64_t)lv, pj, mu32, c32, ctx.bar_mu);
+                y[0][q] = BINARY ? (uint32_t)rv : rem64_p30((uint64_t)rv, pj, mu32, c32, ctx.bar_mu);
             }
         }
-        fwd_from_regs<S32H, LOGN, 1>(x, smem, t, P.fwd[j], P.ctx[j], sub);
+        fwd_from_regs<S32H, LOGN, 1>(x, smem, t, P.fwd[j], ctx, sub);
         __syncthreads();  // everyone has read its last-pass inputs before the tile is reused
-        fwd_from_regs<S32H, LOGN, 1>(y, smem, t, P.fwd[j], P.ctx[j], sub);
+        fwd_from_regs<S32H, LOGN, 1>(y, smem, t, P.fwd[j], ctx, sub);
         // mul_assign_normalize on the 8 consecutive NTT-domain coefficients of this thread
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            uint32_t a = S32H::fwd_fin(P.ctx[j], x[0][q]), b = S32H::fwd_fin(P.ctx[j], y[0][q]);
-            x[0][q] = S32H::mul_const(P.ctx[j], S32H::mul_full(P.ctx[j], a, b), P.n_inv[j]);
+            uint32_t a = S32H::fwd_fin(ctx, x[0][q]), b = S32H::fwd_fin(ctx, y[0][q]);
+            x[0][q] = S32H::mul_const(ctx, S32H::mul_full(ctx, a, b), P.n_inv[j]);
         }
         __syncthreads();
-        inv_to_regs<S32H, LOGN, 1>(x, smem, t, P.inv[j], P.ctx[j], sub);
+        inv_to_regs<S32H, LOGN, 1>(x, smem, t, P.inv[j], ctx, sub);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) res[j][q] = S32H::inv_fin(P.ctx[j], x[0][q]);
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t r = S32H::inv_fin(ctx, x[0][q]);
+            if (j < NP - 1)
+                res_s[(j * 8 + q) * TPP + t] = r;
+            else
+                last[q] = r;
+        }
         __syncthreads();
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        auto r32 = [&](int j) { return res[j][q]; };
+        auto r32 = [&](int j) { return j < NP - 1 ? res_s[(j * 8 + q) * TPP + t] : last[q]; };
         auto r64 = [&](int) { return (uint64_t)0; };
         crt_with<KIND>(k, r32, r64, base + t + q * TPP, prod);
     }
@@ -499,11 +516,14 @@ struct ntt_b200_native_plan {
         if (!aligned(prod) || !aligned(lhs) || !aligned(rhs)) return false;
         unsigned grid = (unsigned)batch;
 #define NTT_FUSED_CASE(L)                                                                         \
-    case L:                                                                                       \
-        native_polymul_fused_kernel<KIND, VT, NP, L, BINARY>                                      \
-            <<<grid, FastShape<L>::kThreadsPerPoly, 0, st>>>((VT*)prod, (const VT*)lhs,           \
-                                                             (const VT*)rhs, P, consts);          \
-        break;
+    case L: {                                                                                     \
+        auto kern = native_polymul_fused_kernel<KIND, VT, NP, L, BINARY>;                         \
+        constexpr size_t smem = fused_smem_bytes<NP, L>();                                        \
+        if (smem > 48 * 1024)                                                                     \
+            NTT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, FastShape<L>::kThreadsPerPoly, smem, st>>>((VT*)prod, (const VT*)lhs,        \
+                                                                (const VT*)rhs, P, consts);       \
+    } break;
         switch (__builtin_ctzll((unsigned long long)n)) {
             NTT_FUSED_CASE(10)
             NTT_FUSED_CASE(11)
