@@ -369,3 +369,27 @@ def test_shared_plan_is_reentrant(T):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("n,p", [(8192, SOLINAS_P), (16384, SOLINAS_P), (8192, 4611686018427322369),
+                                  (16384, 9223372036853661697), (8192, 18446744073707716609)])
+def test_prime64_cluster_kernels_many_polynomials(T, n, p):
+    """Rows of 2^13 / 2^14 u64 coefficients run as one cluster of eight CTAs per polynomial
+    (csrc/ntt_fast.cuh ntt_cluster8_*): enough polynomials to fill every SM several times, sampled
+    rows against the oracle (generic_solinas.rs:449-514 / shoup.rs:544-615), all rows through
+    inv(fwd(x)) = n * x."""
+    gp, op = plan_pair(T, 64, n, p)
+    rng = np.random.default_rng(n ^ (p % 1000003))
+    batch = 333
+    x = rand_below(rng, p, (batch, n), np.uint64)
+    got = x.copy()
+    gp.fwd_batch(got)
+    assert (got < np.uint64(p)).all()
+    rows = [0, 1, 7, 8, 147, 148, 331, 332]
+    want_f = op.fwd(x[rows])
+    assert (got[rows] == want_f).all()
+    gp.inv_batch(got)
+    assert (got[rows] == op.inv(want_f)).all()
+    flat = got.reshape(-1)
+    gp.normalize(flat)
+    assert (flat.reshape(batch, n) == x).all()

@@ -2,6 +2,7 @@
 #include "ntt_engine.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <type_traits>
 
@@ -99,6 +100,15 @@ struct Build<Mont64> {
     }
     static const char* name() { return "mont64"; }
 };
+
+// NTT_B200_NO_CLUSTER=1 keeps polynomials longer than 4096 on the two-launch path (A/B measurements)
+bool cluster_path_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("NTT_B200_NO_CLUSTER");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -238,6 +248,10 @@ struct PlanImpl final : PrimePlan {
     // Longest polynomial the fast single-CTA kernels take; longer ones first run their top
     // `logn - kFastMaxLog` stages as strided global-memory passes (<= 4 stages per pass).
     static constexpr int kFastMaxLog = 12, kFastMinLog = 8;
+    // Sizes served by the cluster-of-eight kernels.  Measured (profiles/r01_large_n_cluster.txt): a gain for
+    // u64 rows of 2^13 (+21 %) and 2^14 (+4..15 %); with 512- and 1024-thread CTAs (2^15, 2^16) only 33 / 15
+    // clusters are resident and the two-launch path wins, and u32 rows gain nothing.
+    static bool cluster_sized(int logn) { return sizeof(T) == 8 && (logn == 13 || logn == 14); }
     static std::vector<std::pair<int, int>> global_groups(int depth) {
         std::vector<std::pair<int, int>> g;  // (first stage, number of stages)
         for (int s = 0; s < depth;) {
@@ -254,6 +268,10 @@ struct PlanImpl final : PrimePlan {
         DeviceGuard g(device);
         T* d = static_cast<T*>(data);
         const bool fast_ok = aligned16(d) && logn >= kFastMinLog;
+        // 2^13 / 2^14 u64 coefficients: one cluster of eight CTAs per polynomial, a single pass over HBM
+        if (fast_ok && cluster_sized(logn) && cluster_path_enabled() &&
+            fast_cluster_fwd<A>(d, batch, logn, d_fwd.get(), ctx, st))
+            return;
         if (fast_ok) {
             int depth = std::max(0, logn - kFastMaxLog);
             for (auto [s, r] : global_groups(depth)) launch_global_r<false>(r, d, batch, s, 0, st);
@@ -269,6 +287,9 @@ struct PlanImpl final : PrimePlan {
         DeviceGuard g(device);
         T* d = static_cast<T*>(data);
         const bool fast_ok = aligned16(d) && logn >= kFastMinLog;
+        if (fast_ok && cluster_sized(logn) && cluster_path_enabled() &&
+            fast_cluster_inv<A>(d, batch, logn, d_inv.get(), ctx, st))
+            return;
         int depth = std::max(0, logn - (fast_ok ? kFastMaxLog : kMaxLogRow));
         if (fast_ok) {
             bool ok = fast_inv<A>(d, batch << depth, logn - depth, (unsigned)depth, d_inv.get(), ctx, st);

@@ -13,9 +13,12 @@
 // every pass's 64-bit accesses and the last pass's 128-bit accesses are bank-conflict free
 // (DESIGN.md "shared-memory layout").
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ntt_kernels.cuh"
 
 namespace nttb200 {
+namespace cg = cooperative_groups;
 
 // A "row" handled by one thread group may be one of the 2^depth contiguous sub-blocks of a longer
 // polynomial whose first `depth` stages ran in global memory (the reference's depth-first
@@ -475,6 +478,77 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly)
     }
 }
 
+// ---- polynomials of 2^13 / 2^14 coefficients: one thread-block cluster per polynomial -------------
+// n = 8 * 2^LOGSUB.  A cluster of eight CTAs (2^LOGSUB / 8 threads each) holds the polynomial in
+// its eight shared-memory tiles, so it crosses HBM once in each direction (the two-launch path
+// ntt_global_pass_kernel + ntt_fast_*_kernel crosses it twice).
+//   forward: every thread of the cluster loads the radix-8 tuple {j + k * n/8} from global memory
+//            (stages 0..2 of the reference's sweep, twid[1], twid[2..3], twid[4..7]) and writes
+//            element k into the tile of CTA k through distributed shared memory; after one cluster
+//            barrier CTA r runs the remaining stages on sub-block r exactly like the single-CTA
+//            kernel (SubPoly{3, r}).
+//   inverse: the mirror image; the last radix-8 tuple gathers its inputs from the eight tiles.
+template <class A, int LOGSUB>
+__global__ void __cluster_dims__(8, 1, 1)
+    __launch_bounds__(FastShape<LOGSUB>::kThreadsPerPoly, FastMinBlocks<A, FastShape<LOGSUB>::kThreadsPerPoly>::value)
+        ntt_cluster8_fwd_kernel(typename A::T* __restrict__ data, const typename A::TW* __restrict__ tw,
+                                typename A::Ctx c) {
+    using T = typename A::T;
+    using S = FastShape<LOGSUB>;
+    constexpr unsigned TPP = S::kThreadsPerPoly, SUB = 1u << LOGSUB;
+    extern __shared__ __align__(16) unsigned char fast_smem_raw[];
+    T* tile = reinterpret_cast<T*>(fast_smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned r = cluster.block_rank(), t = threadIdx.x;
+    T* g = data + ((size_t)(blockIdx.x >> 3) << (LOGSUB + 3));
+    T x[1][8];
+    const unsigned j = r * TPP + t;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[0][k] = g[j + k * SUB];
+    cluster.sync();  // every CTA of the cluster is resident before its shared memory is written
+    tuple_ro<A, 3, 0, false, false, 1, false>(x, tw, 1u, c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cluster.map_shared_rank(tile, k)[pad_index<T>(j)] = x[0][k];
+    cluster.sync();
+    const SubPoly sub{3u, r};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[0][k] = tile[pad_index<T>(t + k * TPP)];
+    fwd_from_regs<A, LOGSUB, 1>(x, tile, t, tw, c, sub);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[0][k] = A::fwd_fin(c, x[0][k]);
+    store8_consecutive(g + r * SUB + 8 * t, x[0]);
+}
+
+template <class A, int LOGSUB>
+__global__ void __cluster_dims__(8, 1, 1)
+    __launch_bounds__(FastShape<LOGSUB>::kThreadsPerPoly, FastMinBlocks<A, FastShape<LOGSUB>::kThreadsPerPoly>::value)
+        ntt_cluster8_inv_kernel(typename A::T* __restrict__ data, const typename A::TW* __restrict__ tw,
+                                typename A::Ctx c) {
+    using T = typename A::T;
+    using S = FastShape<LOGSUB>;
+    constexpr unsigned TPP = S::kThreadsPerPoly, SUB = 1u << LOGSUB;
+    extern __shared__ __align__(16) unsigned char fast_smem_raw[];
+    T* tile = reinterpret_cast<T*>(fast_smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned r = cluster.block_rank(), t = threadIdx.x;
+    T* g = data + ((size_t)(blockIdx.x >> 3) << (LOGSUB + 3));
+    T x[1][8];
+    load8_consecutive(g + r * SUB + 8 * t, x[0]);
+    const SubPoly sub{3u, r};
+    inv_to_regs<A, LOGSUB, 1>(x, tile, t, tw, c, sub);
+    // x holds the lazy values of elements t + k*TPP of sub-block r (the slots this thread owns)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[pad_index<T>(t + k * TPP)] = x[0][k];
+    cluster.sync();
+    const unsigned j = r * TPP + t;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[0][k] = cluster.map_shared_rank(tile, k)[pad_index<T>(j)];
+    tuple_ro<A, 3, 0, true, false, 1, false>(x, tw, 1u, c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[j + k * SUB] = (k < 4) ? A::inv_fin(c, x[0][k]) : A::inv_fin_prod(c, x[0][k]);
+    cluster.sync();  // no CTA leaves while its tile may still be read
+}
+
 // Host-side dispatch (defined in ntt_fast_*.cu, one translation unit per modulus family).
 // Returns false when (A, logn) has no fast kernel; the caller then uses the generic path.
 // `rows` rows of 2^logn coefficients; depth as in SubPoly.
@@ -484,6 +558,13 @@ bool fast_fwd(typename A::T* data, size_t rows, int logn, unsigned depth, const 
 template <class A>
 bool fast_inv(typename A::T* data, size_t rows, int logn, unsigned depth, const typename A::TW* tw,
               const typename A::Ctx& c, cudaStream_t st);
+// one cluster of eight CTAs per polynomial, logn = 13 or 14 (false: no such kernel)
+template <class A>
+bool fast_cluster_fwd(typename A::T* data, size_t polys, int logn, const typename A::TW* tw,
+                      const typename A::Ctx& c, cudaStream_t st);
+template <class A>
+bool fast_cluster_inv(typename A::T* data, size_t polys, int logn, const typename A::TW* tw,
+                      const typename A::Ctx& c, cudaStream_t st);
 template <class A>
 bool fast_ext_product(typename A::T* out, const typename A::T* in, const typename A::T* ggsw,
                       unsigned rows, unsigned cols, size_t batch, int logn,

@@ -172,6 +172,27 @@ bool fast_ext_impl(typename A::T* out, const typename A::T* in, const typename A
     return ok;
 }
 
+template <class A, int LOGSUB, bool INV>
+void launch_cluster8(typename A::T* data, size_t polys, const typename A::TW* tw, const typename A::Ctx& c,
+                     cudaStream_t st) {
+    constexpr size_t smem = (size_t)FastShape<LOGSUB>::kPaddedElems * sizeof(typename A::T);
+    constexpr auto kern = INV ? ntt_cluster8_inv_kernel<A, LOGSUB> : ntt_cluster8_fwd_kernel<A, LOGSUB>;
+    fast_allow_smem<kern>(smem);
+    // grid.x limit is 2^31 - 1 CTAs: far above any batch that fits the device
+    kern<<<(unsigned)(polys * 8), FastShape<LOGSUB>::kThreadsPerPoly, smem, st>>>(data, tw, c);
+}
+template <class A, bool INV>
+bool fast_cluster_impl(typename A::T* data, size_t polys, int logn, const typename A::TW* tw,
+                       const typename A::Ctx& c, cudaStream_t st) {
+    switch (logn) {
+        case 13: launch_cluster8<A, 10, INV>(data, polys, tw, c, st); break;
+        case 14: launch_cluster8<A, 11, INV>(data, polys, tw, c, st); break;
+        default: return false;
+    }
+    NTT_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
 // explicit specialisations of the entry points declared in ntt_fast.cuh
 #define NTT_DEFINE_FAST(A)                                                                         \
     template <>                                                                                    \
@@ -183,6 +204,16 @@ bool fast_ext_impl(typename A::T* out, const typename A::T* in, const typename A
     bool fast_inv<A>(A::T * data, size_t batch, int logn, unsigned depth, const A::TW* tw,         \
                      const A::Ctx& c, cudaStream_t st) {                                           \
         return fast_inv_impl<A>(data, batch, logn, depth, tw, c, st);                              \
+    }                                                                                              \
+    template <>                                                                                    \
+    bool fast_cluster_fwd<A>(A::T * data, size_t polys, int logn, const A::TW* tw, const A::Ctx& c, \
+                             cudaStream_t st) {                                                    \
+        return fast_cluster_impl<A, false>(data, polys, logn, tw, c, st);                          \
+    }                                                                                              \
+    template <>                                                                                    \
+    bool fast_cluster_inv<A>(A::T * data, size_t polys, int logn, const A::TW* tw, const A::Ctx& c, \
+                             cudaStream_t st) {                                                    \
+        return fast_cluster_impl<A, true>(data, polys, logn, tw, c, st);                           \
     }                                                                                              \
     template <>                                                                                    \
     bool fast_ext_product<A>(A::T * out, const A::T* in, const A::T* ggsw, unsigned rows,          \
