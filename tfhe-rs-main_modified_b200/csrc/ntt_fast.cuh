@@ -15,7 +15,16 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "ntt_kernels.cuh"
+
+#ifndef NTT_FUSED_U32_THREADS_PER_SM
+#define NTT_FUSED_U32_THREADS_PER_SM 1280
+#endif
+#ifndef NTT_FAST_U32_THREADS_PER_SM
+#define NTT_FAST_U32_THREADS_PER_SM 1536
+#endif
 
 namespace nttb200 {
 namespace cg = cooperative_groups;
@@ -37,12 +46,24 @@ struct FastShape {
     static constexpr int kPaddedElems = (1 << LOGN) + ((1 << LOGN) >> 3);  // 16 B per 128 B
 };
 
-// Resident CTAs per SM the register allocator is asked to allow: 1024 threads per SM, i.e. 64
-// registers per thread.  Every family fits (the 64-bit ones with at most a few spilled words);
-// four 256-thread CTAs per SM hide the load phase of one CTA behind the butterflies of the others.
+// Resident CTAs per SM the register allocator is asked to allow.  64-bit families: 1024 threads per
+// SM, i.e. 64 registers per thread (they fit with at most a few spilled words); four 256-thread CTAs
+// per SM hide the load phase of one CTA behind the butterflies of the others.  32-bit families need
+// 40-48 registers, so they are given 1536 threads per SM (six 256-thread CTAs; measured +8 % at
+// n = 2048); the exact path for p >= 2^31 spills there and keeps 1024.
 template <class A, int THREADS>
 struct FastMinBlocks {
-    static constexpr int value = 1024 / THREADS > 0 ? 1024 / THREADS : 1;
+    static constexpr int kThreadsPerSM = (sizeof(typename A::T) == 4 && !std::is_same<A, Wide32>::value) ? NTT_FAST_U32_THREADS_PER_SM : 1024;
+    static constexpr int value = kThreadsPerSM / THREADS > 0 ? kThreadsPerSM / THREADS : 1;
+};
+
+// The fused fwd -> pointwise -> inv kernel: 32-bit families are held to NTT_FUSED_U32_THREADS_PER_SM
+// threads per SM, the 64-bit ones are left to the register allocator (one CTA more would spill).
+template <class A, int THREADS>
+struct FusedMinBlocks {
+    static constexpr int value =
+        (sizeof(typename A::T) == 4 && !std::is_same<A, Wide32>::value && NTT_FUSED_U32_THREADS_PER_SM / THREADS > 0)
+            ? NTT_FUSED_U32_THREADS_PER_SM / THREADS : 1;
 };
 
 // Whether the 8-byte twiddle records of a stage are fetched two per 128-bit load (ldg_tw_run).
@@ -372,7 +393,8 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
 // Fused fwd -> pointwise multiply(-accumulate) -> inv, one pass over HBM (BASELINE C2 / the
 // PBS external product shape):  out = inv(acc + fwd(lhs) * rhs).
 template <class A, int LOGN, int POLYS, int PPT>
-__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS)
+__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
+                                  FusedMinBlocks<A, FastShape<LOGN>::kThreadsPerPoly * POLYS>::value)
     ntt_fast_fwd_mac_inv_kernel(typename A::T* __restrict__ out,
                                 const typename A::T* __restrict__ lhs,
                                 const typename A::T* __restrict__ rhs, size_t rhs_polys,
