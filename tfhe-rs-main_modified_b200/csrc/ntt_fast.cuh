@@ -57,13 +57,14 @@ struct FastMinBlocks {
     static constexpr int value = kThreadsPerSM / THREADS > 0 ? kThreadsPerSM / THREADS : 1;
 };
 
-// The fused fwd -> pointwise -> inv kernel: 32-bit families are held to NTT_FUSED_U32_THREADS_PER_SM
-// threads per SM, the 64-bit ones are left to the register allocator (one CTA more would spill).
+// The fused fwd -> pointwise -> inv kernel: 32-bit Shoup families are held to
+// NTT_FUSED_U32_THREADS_PER_SM threads per SM, everything else to 1024 (64 registers: the 64-bit
+// families then spill a few words but run four 256-thread CTAs per SM instead of two).
 template <class A, int THREADS>
 struct FusedMinBlocks {
-    static constexpr int value =
-        (sizeof(typename A::T) == 4 && !std::is_same<A, Wide32>::value && NTT_FUSED_U32_THREADS_PER_SM / THREADS > 0)
-            ? NTT_FUSED_U32_THREADS_PER_SM / THREADS : 1;
+    static constexpr int kThreadsPerSM =
+        (sizeof(typename A::T) == 4 && !std::is_same<A, Wide32>::value) ? NTT_FUSED_U32_THREADS_PER_SM : 1024;
+    static constexpr int value = kThreadsPerSM / THREADS > 0 ? kThreadsPerSM / THREADS : 1;
 };
 
 // Whether the 8-byte twiddle records of a stage are fetched two per 128-bit load (ldg_tw_run).
