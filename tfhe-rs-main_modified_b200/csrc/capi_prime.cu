@@ -479,6 +479,7 @@ int ntt64_add_backward_dev(const PrimePlan* pl, uint64_t* standard, uint64_t* nt
         if (!out || !in || !ggsw) return NTT_B200_ERR_ARG;                                         \
         if (rows == 0 || cols == 0 || rows > 65535 || cols > 65535) return NTT_B200_ERR_LEN;       \
         return guarded([&] {                                                                       \
+            keep_pool_cached(plan->impl->device); /* stream-ordered scratch of the launcher */     \
             plan->impl->ext_product(out, in, ggsw, (unsigned)rows, (unsigned)cols, batch,          \
                                     (cudaStream_t)stream);                                         \
             return NTT_B200_OK;                                                                    \

@@ -108,6 +108,12 @@ struct Shoup {
     NTT_DEVINL static T acc_add(const Ctx& c, T acc, T prod) { return add_full(c, acc, prod); }
     NTT_DEVINL static T acc_fin(const Ctx&, T acc) { return acc; }
     NTT_DEVINL static T mul_full(const Ctx& c, T a, T b);
+    // Pointwise product against an operand that is reused many times (a GGSW shared by a batch):
+    // pw_form() is applied to it once, mul_pw(x, pw_form(g)) = x*g mod p canonical.  W = 64: the
+    // operand goes to Montgomery form so that one REDC suffices and x may be any lazy value.
+    static constexpr bool kPwLazyIn = sizeof(T) == 8;
+    NTT_DEVINL static T pw_form(const Ctx& c, T g);
+    NTT_DEVINL static T mul_pw(const Ctx& c, T x, T gf);
 };
 
 // Montgomery REDC for odd p < 2^64: returns (hi:lo) * 2^-64 mod p, canonical, for hi < p.
@@ -127,6 +133,22 @@ template <>
 NTT_DEVINL uint64_t Shoup<uint64_t, false>::mul_full(const Ctx& c, uint64_t a, uint64_t b) {
     uint64_t x = redc64(a * b, __umul64hi(a, b), c.p, c.pinv);
     return redc64(x * c.r2, __umul64hi(x, c.r2), c.p, c.pinv);
+}
+template <>
+NTT_DEVINL uint64_t Shoup<uint64_t, true>::pw_form(const Ctx& c, uint64_t g) {
+    return redc64(g * c.r2, __umul64hi(g, c.r2), c.p, c.pinv);
+}
+template <>
+NTT_DEVINL uint64_t Shoup<uint64_t, false>::pw_form(const Ctx& c, uint64_t g) {
+    return redc64(g * c.r2, __umul64hi(g, c.r2), c.p, c.pinv);
+}
+template <>
+NTT_DEVINL uint64_t Shoup<uint64_t, true>::mul_pw(const Ctx& c, uint64_t x, uint64_t gf) {
+    return redc64(x * gf, __umul64hi(x, gf), c.p, c.pinv);
+}
+template <>
+NTT_DEVINL uint64_t Shoup<uint64_t, false>::mul_pw(const Ctx& c, uint64_t x, uint64_t gf) {
+    return redc64(x * gf, __umul64hi(x, gf), c.p, c.pinv);
 }
 // exact a*b mod p for any p < 2^32 via a 64-bit Barrett quotient
 NTT_DEVINL uint32_t barrett32(uint64_t d, uint32_t p, uint64_t b64) {
@@ -154,6 +176,14 @@ template <>
 NTT_DEVINL uint32_t Shoup<uint32_t, false>::mul_full(const Ctx& c, uint32_t a, uint32_t b) {
     return barrett32((uint64_t)a * b, c.p, c.barrett64);
 }
+template <>
+NTT_DEVINL uint32_t Shoup<uint32_t, true>::pw_form(const Ctx&, uint32_t g) { return g; }
+template <>
+NTT_DEVINL uint32_t Shoup<uint32_t, false>::pw_form(const Ctx&, uint32_t g) { return g; }
+template <>
+NTT_DEVINL uint32_t Shoup<uint32_t, true>::mul_pw(const Ctx& c, uint32_t x, uint32_t gf) { return mul_full(c, x, gf); }
+template <>
+NTT_DEVINL uint32_t Shoup<uint32_t, false>::mul_pw(const Ctx& c, uint32_t x, uint32_t gf) { return mul_full(c, x, gf); }
 
 // ------------------------------------------------------------------------------------
 // Wide32: p >= 2^31, exact arithmetic through 64-bit intermediates
@@ -195,6 +225,9 @@ struct Wide32 {
     }
     NTT_DEVINL static T acc_add(const Ctx& c, T acc, T prod) { return add_full(c, acc, prod); }
     NTT_DEVINL static T acc_fin(const Ctx&, T acc) { return acc; }
+    static constexpr bool kPwLazyIn = false;
+    NTT_DEVINL static T pw_form(const Ctx&, T g) { return g; }
+    NTT_DEVINL static T mul_pw(const Ctx& c, T x, T gf) { return mul_full(c, x, gf); }
 };
 
 // ------------------------------------------------------------------------------------
@@ -305,6 +338,10 @@ struct Solinas64 {
     // running sum: arbitrary representative + canonical product, canonicalised once at the end
     NTT_DEVINL static T acc_add(const Ctx&, T acc, T prod) { return add_lazy(acc, prod); }
     NTT_DEVINL static T acc_fin(const Ctx&, T acc) { return canon(acc); }
+    // Montgomery form of a reused pointwise operand: g * 2^64 = g * eps mod p; then one REDC per product
+    static constexpr bool kPwLazyIn = true;
+    NTT_DEVINL static T pw_form(const Ctx&, T g) { return mul_plain(g, EPS); }
+    NTT_DEVINL static T mul_pw(const Ctx&, T x, T gf) { return mulm(x, gf); }
 };
 
 // ------------------------------------------------------------------------------------
@@ -346,6 +383,9 @@ struct Mont64 {
     }
     NTT_DEVINL static T acc_add(const Ctx& c, T acc, T prod) { return add_full(c, acc, prod); }
     NTT_DEVINL static T acc_fin(const Ctx&, T acc) { return acc; }
+    static constexpr bool kPwLazyIn = false;  // values are canonical throughout
+    NTT_DEVINL static T pw_form(const Ctx& c, T g) { return redc64(g * c.r2, __umul64hi(g, c.r2), c.p, c.pinv); }
+    NTT_DEVINL static T mul_pw(const Ctx& c, T x, T gf) { return mul_exact(c, x, gf); }
 };
 
 }  // namespace nttb200

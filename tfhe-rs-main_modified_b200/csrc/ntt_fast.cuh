@@ -19,6 +19,9 @@
 
 #include "ntt_kernels.cuh"
 
+#ifndef NTT_EXT_THREADS_PER_SM
+#define NTT_EXT_THREADS_PER_SM 768
+#endif
 #ifndef NTT_FUSED_U32_THREADS_PER_SM
 #define NTT_FUSED_U32_THREADS_PER_SM 1280
 #endif
@@ -447,6 +450,14 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
     }
 }
 
+// reused pointwise operand -> the family's pointwise form (Montgomery form for the 64-bit families)
+template <class A>
+__global__ void pw_form_kernel(typename A::T* __restrict__ out, const typename A::T* __restrict__ in,
+                               size_t total, typename A::Ctx c) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = A::pw_form(c, in[i]);
+}
+
 // External-product core (the NTT-PBS shape, tfhe ntt64_pbs.rs:598-661): for every batch item b
 //   out[b][c] = inv( sum_r fwd(in[b][r]) (*) ggsw[r][c] ),   r < rows, c < COLS
 // `ggsw` (rows x COLS NTT-domain polynomials) is shared by the whole batch and stays in L2.
@@ -454,7 +465,9 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
 // into register accumulators, COLS inverse transforms; HBM traffic is rows*n*w in, COLS*n*w out.
 // Equivalent to the reference's sequence Plan::fwd / Plan::mul_accumulate / Plan::inv.
 template <class A, int LOGN, int COLS>
-__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly)
+__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly,
+                                  (NTT_EXT_THREADS_PER_SM / FastShape<LOGN>::kThreadsPerPoly > 0
+                                       ? NTT_EXT_THREADS_PER_SM / FastShape<LOGN>::kThreadsPerPoly : 1))
     ntt_fast_ext_product_kernel(typename A::T* __restrict__ out, const typename A::T* __restrict__ in,
                                 const typename A::T* __restrict__ ggsw, unsigned rows,
                                 const typename A::TW* __restrict__ tw_fwd,
@@ -476,14 +489,16 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly)
 #pragma unroll
         for (int k = 0; k < 8; ++k) x[0][k] = gi[t + k * S::kThreadsPerPoly];
         fwd_from_regs<A, LOGN, 1>(x, smem, t, tw_fwd, c, sub);
+        if (!A::kPwLazyIn) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[0][k] = A::fwd_fin(c, x[0][k]);
+            for (int k = 0; k < 8; ++k) x[0][k] = A::fwd_fin(c, x[0][k]);
+        }
 #pragma unroll
         for (int cc = 0; cc < COLS; ++cc) {
-            T g[8];
+            T g[8];  // `ggsw` is in the family's pointwise form (A::pw_form, applied by the launcher)
             load8_consecutive(ggsw + (((size_t)r * COLS + cc) << LOGN) + 8 * t, g);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[cc][k] = A::acc_add(c, acc[cc][k], A::mul_full(c, x[0][k], g[k]));
+            for (int k = 0; k < 8; ++k) acc[cc][k] = A::acc_add(c, acc[cc][k], A::mul_pw(c, x[0][k], g[k]));
         }
         __syncthreads();  // the tile is reused by the next transform
     }

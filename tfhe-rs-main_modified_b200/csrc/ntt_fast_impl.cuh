@@ -146,6 +146,22 @@ bool launch_fast_ext(typename A::T* out, const typename A::T* in, const typename
                      const typename A::TW* tw_inv, const typename A::Ctx& c, cudaStream_t st) {
     dim3 block(FastShape<LOGN>::kThreadsPerPoly);
     unsigned grid = (unsigned)batch;
+    if (cols < 1 || cols > 4) return false;
+    // the shared GGSW goes to the family's pointwise form once per call (rows * cols polynomials)
+    typename A::T* gform = nullptr;
+    if (sizeof(typename A::T) == 8) {
+        size_t total = ((size_t)rows * cols) << LOGN;
+        NTT_CUDA_CHECK(cudaMallocAsync(&gform, total * sizeof(typename A::T), st));
+        pw_form_kernel<A><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gform, ggsw, total, c);
+        ggsw = gform;
+    }
+    struct Release {
+        typename A::T* p;
+        cudaStream_t st;
+        ~Release() {
+            if (p) cudaFreeAsync(p, st);
+        }
+    } release{gform, st};
     switch (cols) {
         case 1: ntt_fast_ext_product_kernel<A, LOGN, 1><<<grid, block, 0, st>>>(out, in, ggsw, rows, tw_fwd, tw_inv, c); break;
         case 2: ntt_fast_ext_product_kernel<A, LOGN, 2><<<grid, block, 0, st>>>(out, in, ggsw, rows, tw_fwd, tw_inv, c); break;
