@@ -29,7 +29,7 @@ SOLINAS_P = (1 << 64) - (1 << 32) + 1
 BATCH_PER_GPU = 65536          # 65536 * 16 KiB = 1 GiB per GPU: far beyond the 126 MB L2
 ALG_BYTES_PER_NTT = 2 * N * 8  # one in-place NTT reads and writes each coefficient once
 E2E_BATCH = 65536              # host-buffer leg: 1 GiB in + 1 GiB out per step
-NCU_TRAFFIC_PER_LAUNCH = 2.097e9  # measured by ncu --set full for one launch of this workload (see profiles/)
+NCU_TRAFFIC_PER_LAUNCH = {"fwd": 2.1099e9, "inv": 2.0913e9}  # dram read+write bytes of one launch, ncu --set full (profiles/ v4)
 METRIC = "fwd+inv NTTs/sec, N=2048 u64 prime, batched"
 UNIT = "NTT/s"
 WORKLOAD = "prime64 Solinas p=2^64-2^32+1 N=2048, batch %d polynomials per GPU, fwd then inv (in place, HBM-resident)" % BATCH_PER_GPU
@@ -286,9 +286,9 @@ def run_gpu(args):
                        "l2_policy": "inputs (1 GiB per GPU) far larger than the 126 MB L2",
                        "parallelism": "batch sharded over %d GPU(s), no collective" % world},
             "roofline": {"bound": "hbm", "kernel": "ntt %s (N=2048 Solinas)" % dom, "achieved": achieved, "peak": hbm,
-                         "unit": "GB/s", "frac": achieved / hbm, "traffic": NCU_TRAFFIC_PER_LAUNCH, "peak_source": which,
-                         "traffic_source": "profiles/r01_ncu_full_solinas2048_v3_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
-                         "limiter": "integer instruction throughput (ncu: ALU pipe 68-73 %, FMA-heavy pipe 68-71 %, DRAM 24 %): "
+                         "unit": "GB/s", "frac": achieved / hbm, "traffic": NCU_TRAFFIC_PER_LAUNCH[dom], "peak_source": which,
+                         "traffic_source": "profiles/r01_ncu_full_solinas2048_v4_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                         "limiter": "integer instruction throughput (ncu: ALU pipe 69-70 %, FMA-heavy pipe 70-74 %, DRAM 26-29 %): "
                                     "the Solinas butterfly is carry-chain adds, see DESIGN.md section 5",
                          "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                          "algorithmic_bytes_per_launch": batch * ALG_BYTES_PER_NTT},
