@@ -81,6 +81,16 @@ int ntt_b200_plan64_mul_accumulate(const ntt_b200_plan64 *plan, uint64_t *acc, s
 /* batched, host memory: `batch` polynomials of ntt_size() coefficients each, contiguous */
 int ntt_b200_plan64_fwd_batch(const ntt_b200_plan64 *plan, uint64_t *host, size_t batch);
 int ntt_b200_plan64_inv_batch(const ntt_b200_plan64 *plan, uint64_t *host, size_t batch);
+/* NEW (no reference counterpart: tfhe-ntt is single-device CPU code): the same host batch split over
+ * several GPUs of one box.  plans[g] are plans for the same (n, p), each created on its own GPU
+ * (ntt_b200_set_device(g) before try_new); GPU g gets a contiguous slice, batch / n_plans polynomials
+ * with the remainder one by one to the first GPUs -- the split rule of the reference's CUDA backend,
+ * backends/tfhe-cuda-backend/cuda/src/utils/helper_multi_gpu.cu:57-88 -- one host thread per GPU, no
+ * exchange between GPUs.  ERR_ARG if the plans disagree on n or p. */
+int ntt_b200_plan64_fwd_batch_multi_gpu(const ntt_b200_plan64 *const *plans, size_t n_plans,
+                                        uint64_t *host, size_t batch);
+int ntt_b200_plan64_inv_batch_multi_gpu(const ntt_b200_plan64 *const *plans, size_t n_plans,
+                                        uint64_t *host, size_t batch);
 
 /* device-resident: pointers on the plan's GPU, asynchronous on `stream` */
 int ntt_b200_plan64_fwd_device(const ntt_b200_plan64 *plan, uint64_t *dev, size_t batch,
@@ -122,6 +132,10 @@ int ntt_b200_plan32_mul_accumulate(const ntt_b200_plan32 *plan, uint32_t *acc, s
                                    size_t rhs_len); /* :993-1015 */
 int ntt_b200_plan32_fwd_batch(const ntt_b200_plan32 *plan, uint32_t *host, size_t batch);
 int ntt_b200_plan32_inv_batch(const ntt_b200_plan32 *plan, uint32_t *host, size_t batch);
+int ntt_b200_plan32_fwd_batch_multi_gpu(const ntt_b200_plan32 *const *plans, size_t n_plans,
+                                        uint32_t *host, size_t batch);
+int ntt_b200_plan32_inv_batch_multi_gpu(const ntt_b200_plan32 *const *plans, size_t n_plans,
+                                        uint32_t *host, size_t batch);
 int ntt_b200_plan32_fwd_device(const ntt_b200_plan32 *plan, uint32_t *dev, size_t batch,
                                void *stream);
 int ntt_b200_plan32_inv_device(const ntt_b200_plan32 *plan, uint32_t *dev, size_t batch,

@@ -123,6 +123,21 @@ struct Div64 {
         void inv_batch(ELEM* host, size_t batch) const {                                          \
             check(ntt_b200_plan##SFX##_inv_batch(h_.get(), host, batch), "inv_batch");            \
         }                                                                                         \
+        /* one host batch over several GPUs: plans[g] lives on GPU g (see the C header) */        \
+        static void fwd_batch_multi_gpu(const std::vector<const Plan*>& plans, ELEM* host,        \
+                                        size_t batch) {                                           \
+            std::vector<const ntt_b200_plan##SFX*> raw;                                           \
+            for (const Plan* p : plans) raw.push_back(p->h_.get());                               \
+            check(ntt_b200_plan##SFX##_fwd_batch_multi_gpu(raw.data(), raw.size(), host, batch),  \
+                  "fwd_batch_multi_gpu");                                                         \
+        }                                                                                         \
+        static void inv_batch_multi_gpu(const std::vector<const Plan*>& plans, ELEM* host,        \
+                                        size_t batch) {                                           \
+            std::vector<const ntt_b200_plan##SFX*> raw;                                           \
+            for (const Plan* p : plans) raw.push_back(p->h_.get());                               \
+            check(ntt_b200_plan##SFX##_inv_batch_multi_gpu(raw.data(), raw.size(), host, batch),  \
+                  "inv_batch_multi_gpu");                                                         \
+        }                                                                                         \
         void fwd_device(ELEM* dev, size_t batch, void* stream = nullptr) const {                  \
             check(ntt_b200_plan##SFX##_fwd_device(h_.get(), dev, batch, stream), "fwd_device");   \
         }                                                                                         \

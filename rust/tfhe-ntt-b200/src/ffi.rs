@@ -33,6 +33,8 @@ extern "C" {
     pub fn ntt_b200_plan64_mul_accumulate(plan: *const ntt_b200_plan64, acc: *mut u64, acc_len: usize, lhs: *const u64, lhs_len: usize, rhs: *const u64, rhs_len: usize) -> c_int;
     pub fn ntt_b200_plan64_fwd_batch(plan: *const ntt_b200_plan64, host: *mut u64, batch: usize) -> c_int;
     pub fn ntt_b200_plan64_inv_batch(plan: *const ntt_b200_plan64, host: *mut u64, batch: usize) -> c_int;
+    pub fn ntt_b200_plan64_fwd_batch_multi_gpu(plans: *const *const ntt_b200_plan64, n_plans: usize, host: *mut u64, batch: usize) -> c_int;
+    pub fn ntt_b200_plan64_inv_batch_multi_gpu(plans: *const *const ntt_b200_plan64, n_plans: usize, host: *mut u64, batch: usize) -> c_int;
     pub fn ntt_b200_plan64_fwd_device(plan: *const ntt_b200_plan64, dev: *mut u64, batch: usize, stream: *mut c_void) -> c_int;
     pub fn ntt_b200_plan64_inv_device(plan: *const ntt_b200_plan64, dev: *mut u64, batch: usize, stream: *mut c_void) -> c_int;
 
@@ -55,6 +57,8 @@ extern "C" {
     pub fn ntt_b200_plan32_mul_accumulate(plan: *const ntt_b200_plan32, acc: *mut u32, acc_len: usize, lhs: *const u32, lhs_len: usize, rhs: *const u32, rhs_len: usize) -> c_int;
     pub fn ntt_b200_plan32_fwd_batch(plan: *const ntt_b200_plan32, host: *mut u32, batch: usize) -> c_int;
     pub fn ntt_b200_plan32_inv_batch(plan: *const ntt_b200_plan32, host: *mut u32, batch: usize) -> c_int;
+    pub fn ntt_b200_plan32_fwd_batch_multi_gpu(plans: *const *const ntt_b200_plan32, n_plans: usize, host: *mut u32, batch: usize) -> c_int;
+    pub fn ntt_b200_plan32_inv_batch_multi_gpu(plans: *const *const ntt_b200_plan32, n_plans: usize, host: *mut u32, batch: usize) -> c_int;
 
     pub fn ntt_b200_plan32_fwd_device(plan: *const ntt_b200_plan32, dev: *mut u32, batch: usize, stream: *mut c_void) -> c_int;
     pub fn ntt_b200_plan32_inv_device(plan: *const ntt_b200_plan32, dev: *mut u32, batch: usize, stream: *mut c_void) -> c_int;

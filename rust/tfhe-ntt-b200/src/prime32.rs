@@ -49,6 +49,20 @@ impl Plan {
         assert_eq!(polys.len() % self.ntt_size(), 0);
         check(unsafe { ffi::ntt_b200_plan32_fwd_batch(self.raw, polys.as_mut_ptr(), polys.len() / self.ntt_size()) }, "fwd_batch")
     }
+    /// One host batch over several GPUs: `plans[g]` was created on GPU g (`set_device(g)` before
+    /// `try_new`); contiguous slices, no exchange between GPUs.
+    pub fn fwd_batch_multi_gpu(plans: &[&Plan], polys: &mut [u32]) {
+        let raw: Vec<*const ffi::ntt_b200_plan32> = plans.iter().map(|p| p.raw as *const _).collect();
+        let n = plans[0].ntt_size();
+        assert_eq!(polys.len() % n, 0);
+        check(unsafe { ffi::ntt_b200_plan32_fwd_batch_multi_gpu(raw.as_ptr(), raw.len(), polys.as_mut_ptr(), polys.len() / n) }, "fwd_batch_multi_gpu")
+    }
+    pub fn inv_batch_multi_gpu(plans: &[&Plan], polys: &mut [u32]) {
+        let raw: Vec<*const ffi::ntt_b200_plan32> = plans.iter().map(|p| p.raw as *const _).collect();
+        let n = plans[0].ntt_size();
+        assert_eq!(polys.len() % n, 0);
+        check(unsafe { ffi::ntt_b200_plan32_inv_batch_multi_gpu(raw.as_ptr(), raw.len(), polys.as_mut_ptr(), polys.len() / n) }, "inv_batch_multi_gpu")
+    }
     pub fn inv_batch(&self, polys: &mut [u32]) {
         assert_eq!(polys.len() % self.ntt_size(), 0);
         check(unsafe { ffi::ntt_b200_plan32_inv_batch(self.raw, polys.as_mut_ptr(), polys.len() / self.ntt_size()) }, "inv_batch")

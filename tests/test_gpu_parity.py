@@ -393,3 +393,35 @@ def test_prime64_cluster_kernels_many_polynomials(T, n, p):
     flat = got.reshape(-1)
     gp.normalize(flat)
     assert (flat.reshape(batch, n) == x).all()
+
+
+@pytest.mark.parametrize("bits,n,p", [(64, 2048, SOLINAS_P), (32, 2048, 1073479681)])
+@pytest.mark.parametrize("batch", [1, 2, 5, 37])
+def test_host_batch_split_over_gpus(T, bits, n, p, batch):
+    """*_batch_multi_gpu: contiguous slices, batch // G each with the remainder to the first GPUs
+    (helper_multi_gpu.cu:57-88), one host thread per slice.  Runs over every visible GPU and, so that
+    the slicing is exercised on a one-GPU box too, over three plans that all live on GPU 0."""
+    import tfhe_ntt_b200._binding as B
+    mod = T.prime64 if bits == 64 else T.prime32
+    dtype = np.uint64 if bits == 64 else np.uint32
+    op = OraclePlan.try_new(bits, n, p)
+    rng = np.random.default_rng(batch * 31 + bits)
+    x = rand_below(rng, p, (batch, n), dtype)
+    want_f = op.fwd(x)
+    want_i = op.inv(want_f)
+    for devices in ([0, 0, 0], list(range(B.device_count()))):
+        plans = mod.Plan.try_new_on_devices(n, p, devices)
+        assert plans is not None and len(plans) == len(devices)
+        got = x.copy()
+        mod.Plan.fwd_batch_multi_gpu(plans, got)
+        assert (got == want_f).all()
+        mod.Plan.inv_batch_multi_gpu(plans, got)
+        assert (got == want_i).all()
+
+
+def test_host_batch_split_rejects_mismatched_plans(T):
+    a = T.prime64.Plan.try_new(2048, SOLINAS_P)
+    b = T.prime64.Plan.try_new(1024, SOLINAS_P)
+    buf = np.zeros((2, 2048), dtype=np.uint64)
+    with pytest.raises(Exception):
+        T.prime64.Plan.fwd_batch_multi_gpu([a, b], buf)

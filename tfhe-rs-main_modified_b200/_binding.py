@@ -42,6 +42,8 @@ def _prime_sigs(sfx, elem):
         p + "mul_accumulate": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz]),
         p + "fwd_batch": (_i, [_vp, _vp, _sz]),
         p + "inv_batch": (_i, [_vp, _vp, _sz]),
+        p + "fwd_batch_multi_gpu": (_i, [_pp, _sz, _vp, _sz]),
+        p + "inv_batch_multi_gpu": (_i, [_pp, _sz, _vp, _sz]),
         p + "fwd_device": (_i, [_vp, _vp, _sz, _vp]),
         p + "inv_device": (_i, [_vp, _vp, _sz, _vp]),
         p + "normalize_device": (_i, [_vp, _vp, _sz, _vp]),

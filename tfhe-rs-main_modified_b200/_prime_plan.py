@@ -90,6 +90,38 @@ class PrimePlanBase:
     def inv_batch(self, buf):
         B.check(self._f("inv_batch")(self._h, B.host_ptr(buf, self._dtype, True), self._batch(buf)))
 
+    @classmethod
+    def try_new_on_devices(cls, polynomial_size, modulus, devices):
+        """One plan per GPU of `devices` for the same (n, p) (None where the reference returns None);
+        restores the calling thread's current device."""
+        plans = []
+        try:
+            for d in devices:
+                B.set_device(d)
+                pl = cls.try_new(polynomial_size, modulus)
+                if pl is None:
+                    return None
+                plans.append(pl)
+        finally:
+            if devices:
+                B.set_device(devices[0])
+        return plans
+
+    @staticmethod
+    def _multi(plans, name, buf):
+        first = plans[0]
+        arr = (C.c_void_p * len(plans))(*[pl._h for pl in plans])
+        B.check(first._f(name)(arr, len(plans), B.host_ptr(buf, first._dtype, True), first._batch(buf)))
+
+    @classmethod
+    def fwd_batch_multi_gpu(cls, plans, buf):
+        """fwd over a host batch split in contiguous slices over the GPUs the plans live on."""
+        cls._multi(plans, "fwd_batch_multi_gpu", buf)
+
+    @classmethod
+    def inv_batch_multi_gpu(cls, plans, buf):
+        cls._multi(plans, "inv_batch_multi_gpu", buf)
+
     def fwd_mac_inv_batch(self, out, lhs, rhs, acc=None):
         """out = inv(acc + fwd(lhs) * rhs) on host arrays; rhs / acc may hold fewer polynomials
         than lhs (reused cyclically).  out may be lhs."""

@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "capi_common.cuh"
 #include "plan_math.hpp"
@@ -110,6 +112,37 @@ int host_transform(const PrimePlan* pl, void* host, size_t batch, bool inverse) 
         NTT_CUDA_CHECK(first);
         return NTT_B200_OK;
     });
+}
+
+// The same host batch split over several GPUs of one box: contiguous slices, batch / G each with the
+// remainder one by one to the first GPUs (the reference CUDA backend's rule,
+// backends/tfhe-cuda-backend/cuda/src/utils/helper_multi_gpu.cu:57-88), one host thread and one set
+// of staging streams per GPU, no exchange between GPUs (the polynomials are independent).
+int host_transform_multi(const PrimePlan* const* plans, size_t n_plans, void* host, size_t batch, bool inverse) {
+    if (n_plans == 1) return host_transform(plans[0], host, batch, inverse);
+    const size_t poly_bytes = plans[0]->n * (size_t)plans[0]->elem_bytes;
+    std::vector<int> status(n_plans, NTT_B200_OK);
+    std::vector<std::string> message(n_plans);
+    std::vector<std::thread> workers;
+    const size_t base = batch / n_plans, rem = batch % n_plans;
+    size_t begin = 0;
+    for (size_t g = 0; g < n_plans; ++g) {
+        const size_t count = base + (g < rem ? 1 : 0);
+        char* slice = static_cast<char*>(host) + begin * poly_bytes;
+        begin += count;
+        if (!count) continue;
+        workers.emplace_back([=, &status, &message] {
+            status[g] = host_transform(plans[g], slice, count, inverse);
+            if (status[g] != NTT_B200_OK) message[g] = g_last_error;  // thread-local in the worker
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (size_t g = 0; g < n_plans; ++g)
+        if (status[g] != NTT_B200_OK) {
+            g_last_error = "GPU slice " + std::to_string(g) + ": " + message[g];
+            return status[g];
+        }
+    return NTT_B200_OK;
 }
 
 // dst[0..len) op= ...; operands uploaded whole (pointwise calls are per-polynomial sized)
@@ -249,6 +282,19 @@ int dev_pointwise_check(size_t len, size_t sub_len) {
     return NTT_B200_OK;
 }
 
+
+// argument checks shared by the *_batch_multi_gpu entry points: same (n, p) everywhere, one plan per GPU slice
+template <class PlanT, class ELEM>
+int multi_entry(const PlanT* const* plans, size_t n_plans, ELEM* host, size_t batch, bool inverse) {
+    if (!plans || !n_plans || n_plans > 64 || (!host && batch)) return NTT_B200_ERR_ARG;
+    std::vector<const PrimePlan*> impl(n_plans);
+    for (size_t g = 0; g < n_plans; ++g) {
+        if (!plans[g]) return NTT_B200_ERR_ARG;
+        impl[g] = plans[g]->impl.get();
+        if (impl[g]->n != impl[0]->n || impl[g]->p != impl[0]->p) return NTT_B200_ERR_ARG;
+    }
+    return host_transform_multi(impl.data(), n_plans, host, batch, inverse);
+}
 }  // namespace
 
 // ---- tfhe Ntt64View on top of a prime64 plan (tfhe .../math/ntt/ntt64.rs:89-266) ------------
@@ -369,6 +415,14 @@ int ntt64_add_backward_dev(const PrimePlan* pl, uint64_t* standard, uint64_t* nt
     int ntt_b200_plan##SFX##_inv_batch(const ntt_b200_plan##SFX* plan, ELEM* host, size_t batch) { \
         if (!plan || (!host && batch)) return NTT_B200_ERR_ARG;                                    \
         return host_transform(plan->impl.get(), host, batch, true);                                \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_fwd_batch_multi_gpu(const ntt_b200_plan##SFX* const* plans,           \
+                                                 size_t n_plans, ELEM* host, size_t batch) {       \
+        return multi_entry(plans, n_plans, host, batch, false);                                    \
+    }                                                                                              \
+    int ntt_b200_plan##SFX##_inv_batch_multi_gpu(const ntt_b200_plan##SFX* const* plans,           \
+                                                 size_t n_plans, ELEM* host, size_t batch) {       \
+        return multi_entry(plans, n_plans, host, batch, true);                                     \
     }                                                                                              \
     int ntt_b200_plan##SFX##_normalize(const ntt_b200_plan##SFX* plan, ELEM* v, size_t len) {      \
         if (!plan || (!v && len)) return NTT_B200_ERR_ARG;                                         \
