@@ -30,6 +30,11 @@ BATCH_PER_GPU = 65536          # 65536 * 16 KiB = 1 GiB per GPU: far beyond the 
 ALG_BYTES_PER_NTT = 2 * N * 8  # one in-place NTT reads and writes each coefficient once
 E2E_BATCH = 65536              # host-buffer leg: 1 GiB in + 1 GiB out per step
 NCU_TRAFFIC_PER_LAUNCH = {"fwd": 2.1099e9, "inv": 2.0913e9}  # dram read+write bytes of one launch, ncu --set full (profiles/ v4)
+# Issue cost of one thread of the shipped kernels (two polynomials, 88 butterflies), from the SASS of
+# ntt_fast_{fwd,inv}_kernel<Solinas64,11,1,2> weighted by the measured issue costs of
+# profiles/r01_int_pipe_microbench.txt (IMAD.WIDE 4 clk, other IMAD 2 clk on the FMA-heavy pipe; IADD3 / LOP3 /
+# SEL / ISETP 2 clk on the ALU pipe); a polynomial pair is 8 warps.
+PIPE_CLK_PER_THREAD = {"fwd": {"fmaheavy": 2790, "alu": 2690}, "inv": {"fmaheavy": 2820, "alu": 3082}}
 METRIC = "fwd+inv NTTs/sec, N=2048 u64 prime, batched"
 UNIT = "NTT/s"
 WORKLOAD = "prime64 Solinas p=2^64-2^32+1 N=2048, batch %d polynomials per GPU, fwd then inv (in place, HBM-resident)" % BATCH_PER_GPU
@@ -278,6 +283,16 @@ def run_gpu(args):
         dom_ms = max(fwd_ms, inv_ms)
         dom = "fwd" if fwd_ms >= inv_ms else "inv"
         achieved = batch * ALG_BYTES_PER_NTT / (dom_ms * 1e-3) / 1e9
+        # the binding roofline: busy fraction of the two integer pipes, = pipe clocks the launch needs
+        # (SASS mix) / pipe clocks available (SMs x 4 sub-partitions x duration x sampled SM clock)
+        clk = clocks.summary()
+        sm_hz = (clk.get("sm_mhz") or 1965.0) * 1e6
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        int_pipes = {}
+        for name, ms in (("fwd", fwd_ms), ("inv", inv_ms)):
+            avail = sms * 4 * ms * 1e-3 * sm_hz
+            warps = batch / 2 * 8
+            int_pipes[name] = {k: warps * v / avail for k, v in PIPE_CLK_PER_THREAD[name].items()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
@@ -290,6 +305,10 @@ def run_gpu(args):
                          "traffic_source": "profiles/r01_ncu_full_solinas2048_v4_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                          "limiter": "integer instruction throughput (ncu: ALU pipe 69-70 %, FMA-heavy pipe 70-74 %, DRAM 26-29 %): "
                                     "the Solinas butterfly is carry-chain adds, see DESIGN.md section 5",
+                         "int_pipe_busy_frac": int_pipes,
+                         "int_pipe_note": "pipe clocks needed by the SASS instruction mix / pipe clocks available; ncu measures "
+                                          "70-74 % (fmaheavy) and 69-70 % (alu), profiles/r01_ncu_full_solinas2048_v4_summary.md; "
+                                          "a two-pipe mix tops out at 0.76 in profiles/r01_int_pipe_microbench.txt",
                          "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                          "algorithmic_bytes_per_launch": batch * ALG_BYTES_PER_NTT},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,
@@ -297,7 +316,7 @@ def run_gpu(args):
                            "buffers: %d polynomials in, fwd + pointwise + inv, %d polynomials out per step" % (eb, eb),
                     "steps": e2e_steps, "kernel_launches": e2e_launches},
             "gpu_launches": 2 * args.steps,
-            "clocks": clocks.summary(),
+            "clocks": clk,
             "wall_s": t_wall,
         }
         if world == 1 and not args.no_cpu:

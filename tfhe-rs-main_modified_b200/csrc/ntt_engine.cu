@@ -110,6 +110,15 @@ bool cluster_path_enabled() {
     return on;
 }
 
+// NTT_B200_NO_TMA=1 keeps the radix-16 strided passes on the register-staged kernel (A/B measurements)
+bool tma_pass_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("NTT_B200_NO_TMA");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count(int device) {
@@ -229,16 +238,40 @@ struct PlanImpl final : PrimePlan {
 
     template <bool INV, int R>
     void launch_global(T* data, size_t batch, int stage, int finalize, cudaStream_t st) const {
-        size_t total = batch << (logn - R);
-        unsigned threads = 256;
-        size_t blocks = std::min<size_t>((total + threads - 1) / threads, (size_t)sm_count(device) * 32);
-        ntt_global_pass_kernel<A, R, INV><<<(unsigned)blocks, threads, 0, st>>>(
+        // n >> R tuples per polynomial, 256 per CTA (n >= 2^13 and R <= 4 here, so at least 512)
+        const size_t gy = std::min<size_t>(batch, 32768);
+        dim3 grid((unsigned)((n >> R) / 256), (unsigned)gy, (unsigned)((batch + gy - 1) / gy));
+        ntt_global_pass_kernel<A, R, INV><<<grid, 256, 0, st>>>(
             data, batch, logn, stage, INV ? d_inv.get() : d_fwd.get(), ctx, finalize);
         NTT_CUDA_CHECK(cudaGetLastError());
+    }
+    // Radix-16 passes move their sixteen strided rows with the bulk-copy engine (double-buffered
+    // shared-memory tiles, ntt_global_pass_tma_kernel): 0.38 ms against 0.50 ms for 1 GiB of u64
+    // (profiles/r01_tma_pass_probe.txt); narrower passes already run at the HBM copy rate from registers.
+    template <bool INV>
+    bool launch_global_tma(T* data, size_t batch, int stage, int finalize, cudaStream_t st) const {
+        constexpr int R = 4;
+        if (!aligned16(data) || logn - stage - R < 8 || !tma_pass_enabled()) return false;
+        auto kern = ntt_global_pass_tma_kernel<A, R, INV>;
+        constexpr size_t smem = global_pass_tma_smem<A, R>();
+        static bool allowed[64] = {};
+        if (device >= 0 && device < 64 && !allowed[device]) {
+            NTT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            allowed[device] = true;
+        }
+        const unsigned log_tiles_per_poly = (unsigned)(logn - R - 8);
+        const size_t tiles = batch << log_tiles_per_poly;
+        const size_t per_sm = std::min<size_t>(3, (size_t(200) << 10) / smem);
+        const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)sm_count(device) * per_sm);
+        kern<<<grid, 256, smem, st>>>(data, tiles, log_tiles_per_poly, logn, stage,
+                                      INV ? d_inv.get() : d_fwd.get(), ctx, finalize);
+        NTT_CUDA_CHECK(cudaGetLastError());
+        return true;
     }
     template <bool INV>
     void launch_global_r(int r, T* data, size_t batch, int stage, int finalize,
                          cudaStream_t st) const {
+        if (r == 4 && launch_global_tma<INV>(data, batch, stage, finalize, st)) return;
         if (r == 1) launch_global<INV, 1>(data, batch, stage, finalize, st);
         if (r == 2) launch_global<INV, 2>(data, batch, stage, finalize, st);
         if (r == 3) launch_global<INV, 3>(data, batch, stage, finalize, st);

@@ -147,37 +147,213 @@ __global__ void __launch_bounds__(512) ntt_rows_kernel(typename A::T* __restrict
     }
 }
 
+// stage Q (2^Q twiddles, distance 2^(R-1-Q)) of a radix-2^R tuple held in registers
+template <class A, int R, int Q, bool INV>
+NTT_DEVINL void global_stage(typename A::T (&x)[1 << R], const typename A::TW* __restrict__ tw, unsigned w0,
+                             const typename A::Ctx& c) {
+    constexpr int d = 1 << (R - 1 - Q);
+#pragma unroll
+    for (int h = 0; h < (1 << Q); ++h) {
+        const typename A::TW w = tw[(w0 << Q) + h];
+#pragma unroll
+        for (int k = 0; k < d; ++k) {
+            constexpr int dd = d;
+            const int ja = h * 2 * dd + k, jb = ja + dd;
+            if (!INV)
+                A::fwd_bf(c, x[ja], x[jb], w);
+            else  // products of the previous stage sit where bit d/2 of the position is set
+                A::inv_bf(c, x[ja], x[jb], w, dd > 1 && (jb & (dd >> 1)) != 0);
+        }
+    }
+}
+
 // Strided pass in global memory over whole polynomials of length 2^logn: stages
 // [stage, stage+R).  Used for the top `depth` stages when a polynomial does not fit one CTA.
+// grid = (tuples per polynomial / 256, polys [folded into y and z]); a CTA covers 256 consecutive tuples of
+// one polynomial, which share their group index i (and so their twiddles) whenever the distance
+// 2^log_t2 of the last fused stage is at least 256 -- always the case for the passes the plans
+// launch (log_t2 >= 12).  The inverse knows statically which tuple positions hold products of the
+// previous stage (bit d/2 of the position), so only sums are re-canonicalised.
 template <class A, int R, bool INV>
-__global__ void __launch_bounds__(256) ntt_global_pass_kernel(typename A::T* __restrict__ data, size_t num_polys,
+__global__ void __launch_bounds__(256, 3) ntt_global_pass_kernel(typename A::T* __restrict__ data, size_t num_polys,
                                        int logn, int stage,
                                        const typename A::TW* __restrict__ tw, typename A::Ctx c,
                                        int finalize) {
     using T = typename A::T;
     const int log_t2 = logn - stage - R;
-    const size_t total = num_polys << (logn - R);
-    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
-         o += (size_t)gridDim.x * blockDim.x) {
-        size_t poly = o >> (logn - R);
-        size_t ot = o & (((size_t)1 << (logn - R)) - 1);
-        size_t i = ot >> log_t2, j = ot & (((size_t)1 << log_t2) - 1);
-        T* base = data + (poly << logn) + (i << (log_t2 + R)) + j;
-        size_t w0 = ((size_t)1 << stage) + i;
+    const unsigned ot = blockIdx.x * 256u + threadIdx.x;  // tuple index inside the polynomial
+    const unsigned i = log_t2 >= 8 ? (blockIdx.x * 256u) >> log_t2 : ot >> log_t2;
+    const unsigned j = ot & ((1u << log_t2) - 1u);
+    const size_t off = ((size_t)i << (log_t2 + R)) + j;
+    const unsigned w0 = (1u << stage) + i;
+    const size_t poly = (size_t)blockIdx.z * gridDim.y + blockIdx.y;
+    if (poly >= num_polys) return;
+    {
+        T* base = data + (poly << logn) + off;
         T x[1 << R];
 #pragma unroll
         for (int k = 0; k < (1 << R); ++k) x[k] = base[(size_t)k << log_t2];
-        if (INV)
-            inv_tuple<A, R>(x, tw, w0, c);
-        else
-            fwd_tuple<A, R>(x, tw, w0, c);
+        if (!INV) {
+            global_stage<A, R, 0, false>(x, tw, w0, c);
+            if constexpr (R >= 2) global_stage<A, R, 1, false>(x, tw, w0, c);
+            if constexpr (R >= 3) global_stage<A, R, 2, false>(x, tw, w0, c);
+            if constexpr (R >= 4) global_stage<A, R, 3, false>(x, tw, w0, c);
+        } else {
+            if constexpr (R >= 4) global_stage<A, R, 3, true>(x, tw, w0, c);
+            if constexpr (R >= 3) global_stage<A, R, 2, true>(x, tw, w0, c);
+            if constexpr (R >= 2) global_stage<A, R, 1, true>(x, tw, w0, c);
+            global_stage<A, R, 0, true>(x, tw, w0, c);
+        }
         if (finalize) {
+            if (!INV) {
 #pragma unroll
-            for (int k = 0; k < (1 << R); ++k) x[k] = INV ? A::inv_fin(c, x[k]) : A::fwd_fin(c, x[k]);
+                for (int k = 0; k < (1 << R); ++k) x[k] = A::fwd_fin(c, x[k]);
+            } else {  // the last stage leaves sums in the lower half, canonical products in the upper
+#pragma unroll
+                for (int k = 0; k < (1 << (R - 1)); ++k) x[k] = A::inv_fin(c, x[k]);
+#pragma unroll
+                for (int k = (1 << (R - 1)); k < (1 << R); ++k) x[k] = A::inv_fin_prod(c, x[k]);
+            }
         }
 #pragma unroll
         for (int k = 0; k < (1 << R); ++k) base[(size_t)k << log_t2] = x[k];
     }
+}
+
+// ---- TMA-staged strided pass -----------------------------------------------------------------
+// The same butterflies as ntt_global_pass_kernel, with the strided rows moved by the bulk-copy
+// engine (cp.async.bulk, 1-D TMA) instead of by the threads: a CTA walks over tiles of 256 tuples
+// (2^R rows of 256 contiguous coefficients), double-buffered in shared memory.  One thread arms an
+// mbarrier with the tile's byte count and issues the 2^R row loads of the NEXT tile, everybody
+// waits for the current tile, transforms it in place in shared memory, and the same thread sends
+// the rows back with bulk stores -- so the loads of tile t+1 and the stores of tile t-1 overlap
+// the arithmetic of tile t, which the register-staged kernel (two or three resident CTAs of
+// 80-100 registers) cannot do.
+namespace tma {
+NTT_DEVINL unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+NTT_DEVINL void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+NTT_DEVINL void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+NTT_DEVINL void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+NTT_DEVINL void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+NTT_DEVINL void bulk_store(void* dst_gmem, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+NTT_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+NTT_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+NTT_DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+NTT_DEVINL void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace tma
+
+template <class A, int R>
+constexpr size_t global_pass_tma_smem() {
+    return 2 * (size_t)(1 << R) * 256 * sizeof(typename A::T) + 16;
+}
+
+template <class A, int R, bool INV>
+__global__ void __launch_bounds__(256) ntt_global_pass_tma_kernel(typename A::T* __restrict__ data, size_t total_tiles,
+                                                                  unsigned log_tiles_per_poly, int logn, int stage,
+                                                                  const typename A::TW* __restrict__ tw, typename A::Ctx c,
+                                                                  int finalize) {
+    using T = typename A::T;
+    constexpr unsigned ROWS = 1u << R, ROW_BYTES = 256u * sizeof(T);
+    extern __shared__ __align__(128) unsigned char tma_smem_raw[];
+    T* buf = reinterpret_cast<T*>(tma_smem_raw);                                                // [2][ROWS][256]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(buf + 2 * ROWS * 256);  // [2]
+    const unsigned t = threadIdx.x;
+    const int log_t2 = logn - stage - R;
+    // global address of row 0 of tile g (row k is k << log_t2 elements further)
+    auto tile_base = [&](size_t g) {
+        const size_t poly = g >> log_tiles_per_poly;
+        const unsigned ot0 = ((unsigned)g & ((1u << log_tiles_per_poly) - 1u)) * 256u;
+        const unsigned i = ot0 >> log_t2, j0 = ot0 & ((1u << log_t2) - 1u);
+        return data + (poly << logn) + ((size_t)i << (log_t2 + R)) + j0;
+    };
+    if (t == 0) {
+        tma::mbar_init(&full[0], 1);
+        tma::mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    size_t g = blockIdx.x;
+    if (g >= total_tiles) return;
+    if (t == 0) {
+        tma::mbar_expect_tx(&full[0], ROWS * ROW_BYTES);
+        const T* src = tile_base(g);
+#pragma unroll
+        for (unsigned k = 0; k < ROWS; ++k) tma::bulk_load(buf + k * 256, src + ((size_t)k << log_t2), ROW_BYTES, &full[0]);
+    }
+    for (unsigned it = 0; g < total_tiles; ++it, g += gridDim.x) {
+        const unsigned cur = it & 1u;
+        T* tile = buf + cur * ROWS * 256;
+        const size_t gn = g + gridDim.x;
+        if (t == 0 && gn < total_tiles) {
+            tma::bulk_wait_read0();  // the stores of the previous tile have finished reading the other buffer
+            tma::mbar_expect_tx(&full[cur ^ 1u], ROWS * ROW_BYTES);
+            const T* src = tile_base(gn);
+            T* dst = buf + (cur ^ 1u) * ROWS * 256;
+#pragma unroll
+            for (unsigned k = 0; k < ROWS; ++k)
+                tma::bulk_load(dst + k * 256, src + ((size_t)k << log_t2), ROW_BYTES, &full[cur ^ 1u]);
+        }
+        tma::mbar_wait(&full[cur], (it >> 1) & 1u);
+        const unsigned ot0 = ((unsigned)g & ((1u << log_tiles_per_poly) - 1u)) * 256u;
+        const unsigned w0 = (1u << stage) + (ot0 >> log_t2);  // log_t2 >= 8: one group per tile
+        T x[ROWS];
+#pragma unroll
+        for (unsigned k = 0; k < ROWS; ++k) x[k] = tile[k * 256 + t];
+        if (!INV) {
+            global_stage<A, R, 0, false>(x, tw, w0, c);
+            if constexpr (R >= 2) global_stage<A, R, 1, false>(x, tw, w0, c);
+            if constexpr (R >= 3) global_stage<A, R, 2, false>(x, tw, w0, c);
+            if constexpr (R >= 4) global_stage<A, R, 3, false>(x, tw, w0, c);
+        } else {
+            if constexpr (R >= 4) global_stage<A, R, 3, true>(x, tw, w0, c);
+            if constexpr (R >= 3) global_stage<A, R, 2, true>(x, tw, w0, c);
+            if constexpr (R >= 2) global_stage<A, R, 1, true>(x, tw, w0, c);
+            global_stage<A, R, 0, true>(x, tw, w0, c);
+        }
+        if (finalize) {
+            if (!INV) {
+#pragma unroll
+                for (unsigned k = 0; k < ROWS; ++k) x[k] = A::fwd_fin(c, x[k]);
+            } else {
+#pragma unroll
+                for (unsigned k = 0; k < ROWS / 2; ++k) x[k] = A::inv_fin(c, x[k]);
+#pragma unroll
+                for (unsigned k = ROWS / 2; k < ROWS; ++k) x[k] = A::inv_fin_prod(c, x[k]);
+            }
+        }
+#pragma unroll
+        for (unsigned k = 0; k < ROWS; ++k) tile[k * 256 + t] = x[k];
+        tma::fence_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
+        __syncthreads();
+        if (t == 0) {
+            T* dst = tile_base(g);
+#pragma unroll
+            for (unsigned k = 0; k < ROWS; ++k) tma::bulk_store(dst + ((size_t)k << log_t2), tile + k * 256, ROW_BYTES);
+            tma::bulk_commit();
+        }
+    }
+    if (t == 0) tma::bulk_wait0();
 }
 
 // ---- pointwise kernels (reference: prime64.rs:1050-1222, prime32.rs:900-1015) ----
