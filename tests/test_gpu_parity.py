@@ -1,5 +1,7 @@
 """GPU parity: the CUDA engine (through the C ABI / the tfhe_ntt_b200 host mirror) against the
 CPU oracle on the same seeded inputs.  Bit-exact (integer path)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -7,6 +9,7 @@ import oracle_lib as O
 from oracle_lib import OraclePlan, OracleNativePlan, SOLINAS_P
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 PRIMES64 = [1125899904679937, 2251799813554177, 4611686018427322369, 9223372036853661697,
             18446744073707716609, SOLINAS_P]
@@ -374,8 +377,8 @@ def test_shared_plan_is_reentrant(T):
 @pytest.mark.parametrize("n,p", [(8192, SOLINAS_P), (16384, SOLINAS_P), (8192, 4611686018427322369),
                                   (16384, 9223372036853661697), (8192, 18446744073707716609)])
 def test_prime64_cluster_kernels_many_polynomials(T, n, p):
-    """Rows of 2^13 / 2^14 u64 coefficients run as one cluster of eight CTAs per polynomial
-    (csrc/ntt_fast.cuh ntt_cluster8_*): enough polynomials to fill every SM several times, sampled
+    """Rows of 2^13 / 2^14 u64 coefficients (TMA-staged radix-16 pass + 512/1024-point kernels by default;
+    the cluster-of-eight kernels have their own test below): enough polynomials to fill every SM several times, sampled
     rows against the oracle (generic_solinas.rs:449-514 / shoup.rs:544-615), all rows through
     inv(fwd(x)) = n * x."""
     gp, op = plan_pair(T, 64, n, p)
@@ -425,3 +428,31 @@ def test_host_batch_split_rejects_mismatched_plans(T):
     buf = np.zeros((2, 2048), dtype=np.uint64)
     with pytest.raises(Exception):
         T.prime64.Plan.fwd_batch_multi_gpu([a, b], buf)
+
+
+def test_cluster_of_eight_kernels_opt_in():
+    """The cluster-of-eight single-pass kernels (csrc/ntt_fast.cuh ntt_cluster8_*) are kept as an opt-in path
+    (NTT_B200_CLUSTER=1, read once per process): run them in a child process against the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import tfhe_ntt_b200 as T
+from oracle_lib import OraclePlan
+P = (1 << 64) - (1 << 32) + 1
+for n, p in ((8192, P), (16384, P), (8192, 4611686018427322369), (16384, 18446744073707716609)):
+    gp, op = T.prime64.Plan.try_new(n, p), OraclePlan.try_new(64, n, p)
+    rng = np.random.default_rng(n)
+    x = (rng.integers(0, 1 << 63, size=(19, n), dtype=np.uint64) * np.uint64(2)) %% np.uint64(p)
+    got = x.copy(); gp.fwd_batch(got)
+    want = op.fwd(x)
+    assert (got == want).all(), ("fwd", n, p)
+    gp.inv_batch(got)
+    assert (got == op.inv(want)).all(), ("inv", n, p)
+print("cluster ok")
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, NTT_B200_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "cluster ok" in r.stdout, r.stdout + r.stderr

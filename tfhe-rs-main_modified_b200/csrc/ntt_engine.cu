@@ -101,11 +101,12 @@ struct Build<Mont64> {
     static const char* name() { return "mont64"; }
 };
 
-// NTT_B200_NO_CLUSTER=1 keeps polynomials longer than 4096 on the two-launch path (A/B measurements)
+// NTT_B200_CLUSTER=1 routes u64 polynomials of 2^13 / 2^14 coefficients through the cluster-of-eight
+// single-pass kernels instead of the (since measured faster) TMA-staged pass + single-CTA kernel
 bool cluster_path_enabled() {
     static const bool on = [] {
-        const char* e = std::getenv("NTT_B200_NO_CLUSTER");
-        return !(e && e[0] == '1');
+        const char* e = std::getenv("NTT_B200_CLUSTER");
+        return e && e[0] == '1';
     }();
     return on;
 }
@@ -281,10 +282,27 @@ struct PlanImpl final : PrimePlan {
     // Longest polynomial the fast single-CTA kernels take; longer ones first run their top
     // `logn - kFastMaxLog` stages as strided global-memory passes (<= 4 stages per pass).
     static constexpr int kFastMaxLog = 12, kFastMinLog = 8;
-    // Sizes served by the cluster-of-eight kernels.  Measured (profiles/r01_large_n_cluster.txt): a gain for
-    // u64 rows of 2^13 (+21 %) and 2^14 (+4..15 %); with 512- and 1024-thread CTAs (2^15, 2^16) only 33 / 15
-    // clusters are resident and the two-launch path wins, and u32 rows gain nothing.
+    // Sizes served by the cluster-of-eight kernels (opt-in, see cluster_path_enabled).  Measured
+    // (profiles/r01_large_n_cluster.txt): against a radix-2/4 pass + 4096-point kernel they gain 21 % at 2^13
+    // and 4..15 % at 2^14 (u64), but the TMA-staged radix-16 pass + 512/1024-point kernels is faster still
+    // (profiles/r01_large_n_depth.txt); with 512- and 1024-thread CTAs (2^15, 2^16) too few clusters are resident.
     static bool cluster_sized(int logn) { return sizeof(T) == 8 && (logn == 13 || logn == 14); }
+    // Number of top stages run as strided passes before the single-CTA kernel takes the 2^(logn - depth)
+    // point sub-blocks.  NTT_B200_DEPTH=k overrides it (A/B measurements).
+    int fast_depth() const {
+        int lo = std::max(0, logn - kFastMaxLog), hi = std::max(lo, logn - kFastMinLog);
+        static const int forced = [] {
+            const char* e = std::getenv("NTT_B200_DEPTH");
+            return e ? std::atoi(e) : -1;
+        }();
+        if (forced >= 0) return std::min(hi, std::max(lo, forced));
+        // Measured (profiles/r01_large_n_depth.txt): as soon as a strided pass is needed, four stages in one
+        // TMA-staged radix-16 pass plus the smaller (more efficient) single-CTA kernels beat fewer stages
+        // plus the 4096-point kernel; the one exception is u32 at 2^14 (radix-8 pass + 2048-point kernel).
+        if (lo == 0) return 0;
+        if (sizeof(T) == 4 && logn == 14) return 3;
+        return std::min(hi, std::max(lo, 4));
+    }
     static std::vector<std::pair<int, int>> global_groups(int depth) {
         std::vector<std::pair<int, int>> g;  // (first stage, number of stages)
         for (int s = 0; s < depth;) {
@@ -301,12 +319,12 @@ struct PlanImpl final : PrimePlan {
         DeviceGuard g(device);
         T* d = static_cast<T*>(data);
         const bool fast_ok = aligned16(d) && logn >= kFastMinLog;
-        // 2^13 / 2^14 u64 coefficients: one cluster of eight CTAs per polynomial, a single pass over HBM
+        // opt-in: 2^13 / 2^14 u64 coefficients as one cluster of eight CTAs per polynomial, a single pass over HBM
         if (fast_ok && cluster_sized(logn) && cluster_path_enabled() &&
             fast_cluster_fwd<A>(d, batch, logn, d_fwd.get(), ctx, st))
             return;
         if (fast_ok) {
-            int depth = std::max(0, logn - kFastMaxLog);
+            int depth = fast_depth();
             for (auto [s, r] : global_groups(depth)) launch_global_r<false>(r, d, batch, s, 0, st);
             if (fast_fwd<A>(d, batch << depth, logn - depth, (unsigned)depth, d_fwd.get(), ctx, st)) return;
         }
@@ -323,7 +341,7 @@ struct PlanImpl final : PrimePlan {
         if (fast_ok && cluster_sized(logn) && cluster_path_enabled() &&
             fast_cluster_inv<A>(d, batch, logn, d_inv.get(), ctx, st))
             return;
-        int depth = std::max(0, logn - (fast_ok ? kFastMaxLog : kMaxLogRow));
+        int depth = fast_ok ? fast_depth() : std::max(0, logn - kMaxLogRow);
         if (fast_ok) {
             bool ok = fast_inv<A>(d, batch << depth, logn - depth, (unsigned)depth, d_inv.get(), ctx, st);
             if (!ok) throw CudaError("no fast inverse kernel for this size");

@@ -1,5 +1,6 @@
-"""Polynomials longer than one CTA (2^13 .. 2^17): cluster-of-eight single-pass kernels against the
-two-launch path (NTT_B200_NO_CLUSTER=1).  Developer tool; CUDA events, 1 GiB working sets."""
+"""Polynomials longer than one CTA (2^13 .. 2^16): the default dispatch, a forced number of strided top
+stages (NTT_B200_DEPTH=k) or the cluster-of-eight single-pass kernels (NTT_B200_CLUSTER=1).
+Developer tool; CUDA events, 1 GiB working sets."""
 import os
 import sys
 
@@ -26,9 +27,9 @@ def timeit(fn, iters=10, warm=3):
 
 def main():
     st = torch.cuda.current_stream()
-    tag = "two-launch" if os.environ.get("NTT_B200_NO_CLUSTER") == "1" else "cluster8"
+    tag = "cluster8" if os.environ.get("NTT_B200_CLUSTER") == "1" else "default" if "NTT_B200_DEPTH" not in os.environ else "depth=" + os.environ["NTT_B200_DEPTH"]
     cases = [(64, 1 << k, T.prime64.SOLINAS_PRIME) for k in (13, 14, 15, 16)]
-    cases += [(64, 1 << 14, 4611686018427322369), (32, 1 << 13, 1073479681), (32, 1 << 15, 1073479681), (32, 1 << 16, 1073479681)]
+    cases += [(64, 1 << 14, 4611686018427322369), (32, 1 << 13, 1073479681), (32, 1 << 14, 1073479681), (32, 1 << 15, 1073479681), (32, 1 << 16, 1073479681)]
     for bits, n, p in cases:
         mod = T.prime64 if bits == 64 else T.prime32
         plan = mod.Plan.try_new(n, p)
