@@ -357,27 +357,44 @@ struct PlanImpl final : PrimePlan {
     unsigned pointwise_blocks(size_t total) const {
         return (unsigned)std::min<size_t>((total + 255) / 256, (size_t)sm_count(device) * 16);
     }
+    // 128-bit path: every pointer 16-byte aligned, every length / period a multiple of 16 / sizeof(T)
+    static bool vec_ok(size_t a, size_t b = 0, size_t c = 0) {
+        constexpr size_t V = 16 / sizeof(T);
+        return a % V == 0 && b % V == 0 && c % V == 0;
+    }
     void normalize(void* v, size_t total, cudaStream_t st) const override {
         if (!total) return;
         DeviceGuard g(device);
-        normalize_kernel<A><<<pointwise_blocks(total), 256, 0, st>>>(static_cast<T*>(v), total, ctx, n_inv);
+        if (aligned16(v) && vec_ok(total))
+            normalize_vec_kernel<A><<<pointwise_blocks(total / (16 / sizeof(T))), 256, 0, st>>>(static_cast<T*>(v), total, ctx, n_inv);
+        else
+            normalize_kernel<A><<<pointwise_blocks(total), 256, 0, st>>>(static_cast<T*>(v), total, ctx, n_inv);
         NTT_CUDA_CHECK(cudaGetLastError());
     }
     void mul_assign_normalize(void* lhs, const void* rhs, size_t total, size_t rhs_period,
                               cudaStream_t st) const override {
         if (!total) return;
         DeviceGuard g(device);
-        mul_assign_normalize_kernel<A><<<pointwise_blocks(total), 256, 0, st>>>(
-            static_cast<T*>(lhs), static_cast<const T*>(rhs), total, rhs_period, ctx, n_inv);
+        if (aligned16(lhs) && aligned16(rhs) && vec_ok(total, rhs_period))
+            mul_assign_normalize_vec_kernel<A><<<pointwise_blocks(total / (16 / sizeof(T))), 256, 0, st>>>(
+                static_cast<T*>(lhs), static_cast<const T*>(rhs), total, rhs_period, ctx, n_inv);
+        else
+            mul_assign_normalize_kernel<A><<<pointwise_blocks(total), 256, 0, st>>>(
+                static_cast<T*>(lhs), static_cast<const T*>(rhs), total, rhs_period, ctx, n_inv);
         NTT_CUDA_CHECK(cudaGetLastError());
     }
     void mul_accumulate(void* acc, const void* lhs, const void* rhs, size_t total,
                         size_t lhs_period, size_t rhs_period, cudaStream_t st) const override {
         if (!total) return;
         DeviceGuard g(device);
-        mul_accumulate_kernel<A><<<pointwise_blocks(total), 256, 0, st>>>(
-            static_cast<T*>(acc), static_cast<const T*>(lhs), static_cast<const T*>(rhs), total,
-            lhs_period, rhs_period, ctx);
+        if (aligned16(acc) && aligned16(lhs) && aligned16(rhs) && vec_ok(total, lhs_period, rhs_period))
+            mul_accumulate_vec_kernel<A><<<pointwise_blocks(total / (16 / sizeof(T))), 256, 0, st>>>(
+                static_cast<T*>(acc), static_cast<const T*>(lhs), static_cast<const T*>(rhs), total,
+                lhs_period, rhs_period, ctx);
+        else
+            mul_accumulate_kernel<A><<<pointwise_blocks(total), 256, 0, st>>>(
+                static_cast<T*>(acc), static_cast<const T*>(lhs), static_cast<const T*>(rhs), total,
+                lhs_period, rhs_period, ctx);
         NTT_CUDA_CHECK(cudaGetLastError());
     }
     void ext_product(void* out, const void* in, const void* ggsw, unsigned rows, unsigned cols,

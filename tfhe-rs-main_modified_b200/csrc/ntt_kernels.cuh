@@ -358,6 +358,62 @@ __global__ void __launch_bounds__(256) ntt_global_pass_tma_kernel(typename A::T*
 
 // ---- pointwise kernels (reference: prime64.rs:1050-1222, prime32.rs:900-1015) ----
 // rhs may be shared by the whole batch: rhs index = i % rhs_period (rhs_period == total: none).
+// The *_vec kernels handle 16 bytes (V = 2 u64 / 4 u32 coefficients) per thread and iteration with
+// 128-bit accesses; the launcher uses them when every pointer is 16-byte aligned and every length
+// and period is a multiple of V (measured on u32: normalize 58 % -> of the HBM copy rate with scalars).
+template <class T>
+struct Vec16 {
+    static constexpr int V = 16 / sizeof(T);
+    T v[V];
+    NTT_DEVINL static Vec16 load(const T* p) {
+        Vec16 r;
+        *reinterpret_cast<uint4*>(r.v) = *reinterpret_cast<const uint4*>(p);
+        return r;
+    }
+    NTT_DEVINL void store(T* p) const { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(v); }
+};
+template <class A>
+__global__ void mul_accumulate_vec_kernel(typename A::T* __restrict__ acc, const typename A::T* __restrict__ lhs,
+                                          const typename A::T* __restrict__ rhs, size_t total, size_t lhs_period,
+                                          size_t rhs_period, typename A::Ctx c) {
+    using VT = Vec16<typename A::T>;
+    constexpr int V = VT::V;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < total;
+         i += (size_t)gridDim.x * blockDim.x * V) {
+        VT a = VT::load(acc + i), l = VT::load(lhs + (lhs_period == total ? i : i % lhs_period)),
+           r = VT::load(rhs + (rhs_period == total ? i : i % rhs_period));
+#pragma unroll
+        for (int k = 0; k < V; ++k) a.v[k] = A::add_full(c, a.v[k], A::mul_full(c, l.v[k], r.v[k]));
+        a.store(acc + i);
+    }
+}
+template <class A>
+__global__ void mul_assign_normalize_vec_kernel(typename A::T* __restrict__ lhs, const typename A::T* __restrict__ rhs,
+                                                size_t total, size_t rhs_period, typename A::Ctx c,
+                                                typename A::TW n_inv) {
+    using VT = Vec16<typename A::T>;
+    constexpr int V = VT::V;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < total;
+         i += (size_t)gridDim.x * blockDim.x * V) {
+        VT l = VT::load(lhs + i), r = VT::load(rhs + (rhs_period == total ? i : i % rhs_period));
+#pragma unroll
+        for (int k = 0; k < V; ++k) l.v[k] = A::mul_const(c, A::mul_full(c, l.v[k], r.v[k]), n_inv);
+        l.store(lhs + i);
+    }
+}
+template <class A>
+__global__ void normalize_vec_kernel(typename A::T* __restrict__ v, size_t total, typename A::Ctx c,
+                                     typename A::TW n_inv) {
+    using VT = Vec16<typename A::T>;
+    constexpr int V = VT::V;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < total;
+         i += (size_t)gridDim.x * blockDim.x * V) {
+        VT x = VT::load(v + i);
+#pragma unroll
+        for (int k = 0; k < V; ++k) x.v[k] = A::mul_const(c, x.v[k], n_inv);
+        x.store(v + i);
+    }
+}
 template <class A>
 __global__ void mul_accumulate_kernel(typename A::T* __restrict__ acc,
                                       const typename A::T* __restrict__ lhs,
