@@ -209,6 +209,9 @@ def test_device_api_and_fused(T):
 @pytest.mark.parametrize("bits,n,p,rows,cols", [
     (64, 2048, SOLINAS_P, 4, 2),          # GLWE k=1, l=2 (BASELINE C3 shape): fused kernel
     (64, 1024, 4611686018427322369, 3, 3),
+    (64, 2048, 9223372036853661697, 2, 2),  # 63-bit: Shoup without the Harvey range, Montgomery-form GGSW
+    (64, 512, 18446744073707716609, 4, 1),  # generic 64-bit prime (Mont64)
+    (64, 4096, 1125899904679937, 1, 4),     # 50-bit prime
     (32, 4096, 1073479681, 2, 4),
     (64, 256, SOLINAS_P, 4, 2),           # n outside the fused sizes: generic composition
     (32, 512, 2147352577, 2, 5),          # cols > 4: generic composition
@@ -490,3 +493,34 @@ def test_device_calls_are_cuda_graph_capturable(T, n):
     torch.cuda.synchronize()
     assert (snap.cpu().numpy().view(np.uint64) == op.fwd(x)).all()
     assert (d.cpu().numpy().view(np.uint64) == x).all()
+
+
+@pytest.mark.parametrize("n,p", [(32, 193), (64, 257), (2048, 12289), (1024, 65537), (4096, 786433),
+                                  (2048, 536903681), (1024, 1073707009)])
+def test_prime32_small_and_odd_sized_primes_pointwise(T, n, p):
+    """The one-word Barrett of the p < 2^30 family (csrc/ntt_arith.cuh barrett32_narrow) depends on the bit
+    length of p: small and mid-sized primes, transforms and every pointwise op against the oracle
+    (prime32.rs:383-408, 477-486, 575-598), including the worst-case operands p - 1."""
+    gp, op = plan_pair(T, 32, n, p)
+    assert (gp is None) == (op is None)
+    if gp is None:
+        pytest.skip("no plan")
+    rng = np.random.default_rng(p)
+    x = np.concatenate([rand_below(rng, p, (3, n), np.uint32), edge_rows(p, n, np.uint32)])
+    f = op.fwd(x)
+    got = x.copy()
+    gp.fwd_batch(got)
+    assert (got == f).all()
+    gp.inv_batch(got)
+    assert (got == op.inv(f)).all()
+    a, b, c = (rand_below(rng, p, (n,), np.uint32) for _ in range(3))
+    a[:4], b[:4] = p - 1, p - 1
+    acc = c.copy()
+    gp.mul_accumulate(acc, a, b)
+    assert (acc == op.mul_accumulate(c, a, b)).all()
+    l = a.copy()
+    gp.mul_assign_normalize(l, b)
+    assert (l == op.mul_assign_normalize(a, b)).all()
+    v = a.copy()
+    gp.normalize(v)
+    assert (v == op.normalize(a)).all()
