@@ -71,7 +71,8 @@ def test_prime64_fwd_inv(T, p, n):
 
 
 def test_prime64_solinas_large_n(T):
-    for n in [65536, 131072]:
+    # 2^17: a radix-8 and a radix-4 strided pass; 2^20: two TMA-staged radix-16 passes (the second with stage 4)
+    for n in [65536, 131072, 1 << 20]:
         gp, op = plan_pair(T, 64, n, SOLINAS_P)
         rng = np.random.default_rng(n)
         x = rand_below(rng, SOLINAS_P, (2, n), np.uint64)
