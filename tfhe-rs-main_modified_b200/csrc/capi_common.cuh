@@ -45,4 +45,23 @@ inline void keep_pool_cached(int device) {
     }
     done[device] = true;
 }
+// One non-blocking stream per host thread and device for the host-pointer entry points of the CRT and
+// product plans (creating and destroying a stream per call costs more than a small transform).
+// Thread-local, so concurrent callers never share a stream; never destroyed.
+inline cudaStream_t cached_stream(int device) {
+    thread_local cudaStream_t st[16] = {};
+    if (device < 0 || device >= 16) return nullptr;
+    if (!st[device]) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        if (prev != device) cudaSetDevice(device);
+        cudaError_t e = cudaStreamCreateWithFlags(&st[device], cudaStreamNonBlocking);
+        if (prev != device) cudaSetDevice(prev);
+        if (e != cudaSuccess) {
+            st[device] = nullptr;
+            throw CudaError(std::string("cudaStreamCreateWithFlags: ") + cudaGetErrorString(e));
+        }
+    }
+    return st[device];
+}
 }  // namespace nttb200

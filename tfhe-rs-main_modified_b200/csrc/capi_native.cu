@@ -671,11 +671,16 @@ namespace {
 struct HostStage {
     cudaStream_t st = nullptr;
     std::vector<void*> bufs;
+    bool owned = false;
     HostStage() {
         int dev = 0;
         cudaGetDevice(&dev);
         keep_pool_cached(dev);
-        NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        st = cached_stream(dev);
+        if (!st) {
+            NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            owned = true;
+        }
     }
     void* alloc(size_t bytes) {
         void* d = nullptr;
@@ -700,7 +705,7 @@ struct HostStage {
         for (void* d : bufs) cudaFreeAsync(d, st);
         if (st) {
             cudaStreamSynchronize(st);
-            cudaStreamDestroy(st);
+            if (owned) cudaStreamDestroy(st);
         }
     }
 };

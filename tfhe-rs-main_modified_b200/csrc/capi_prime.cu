@@ -76,7 +76,57 @@ struct Stage {
     void* d = nullptr;
 };
 
+// Per-thread, per-device resources for the small host calls (the reference's per-polynomial Plan::fwd /
+// inv / normalize / mul_* on one slice): a stream, a device buffer and a pinned staging buffer that are
+// created once and reused, so a call is two memcpy's into / out of pinned memory, two async copies, the
+// kernel and one synchronise instead of a stream creation, stream-ordered allocations and pageable
+// copies (137 -> see tools/latency_bench.py).  Thread-local, so calls stay re-entrant on a shared plan;
+// never freed (a thread-exit destructor could run after the CUDA context is gone).
+struct SmallCtx {
+    cudaStream_t st = nullptr;
+    char *d = nullptr, *h = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (!st) NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if (bytes <= cap) return;
+        size_t want = std::max<size_t>(bytes, size_t(256) << 10);
+        if (d) cudaFree(d);
+        if (h) cudaFreeHost(h);
+        d = h = nullptr;
+        cap = 0;
+        NTT_CUDA_CHECK(cudaMalloc(&d, want));
+        NTT_CUDA_CHECK(cudaMallocHost(&h, want));
+        cap = want;
+    }
+};
+constexpr size_t kSmallBytes = size_t(2) << 20;  // calls up to this size take the cached path
+SmallCtx& small_ctx(int device) {
+    thread_local SmallCtx ctx[16];
+    return ctx[device & 15];
+}
+
+int host_transform_small(const PrimePlan* pl, void* host, size_t batch, bool inverse) {
+    return guarded([&] {
+        DeviceGuard g(pl->device);
+        const size_t bytes = batch * pl->n * (size_t)pl->elem_bytes;
+        SmallCtx& c = small_ctx(pl->device);
+        c.ensure(bytes);
+        std::memcpy(c.h, host, bytes);
+        NTT_CUDA_CHECK(cudaMemcpyAsync(c.d, c.h, bytes, cudaMemcpyHostToDevice, c.st));
+        if (inverse)
+            pl->inv(c.d, batch, c.st);
+        else
+            pl->fwd(c.d, batch, c.st);
+        NTT_CUDA_CHECK(cudaMemcpyAsync(c.h, c.d, bytes, cudaMemcpyDeviceToHost, c.st));
+        NTT_CUDA_CHECK(cudaStreamSynchronize(c.st));
+        std::memcpy(host, c.h, bytes);
+        return NTT_B200_OK;
+    });
+}
+
 int host_transform(const PrimePlan* pl, void* host, size_t batch, bool inverse) {
+    if (batch && pl->device < 16 && batch * pl->n * (size_t)pl->elem_bytes <= kSmallBytes)
+        return host_transform_small(pl, host, batch, inverse);
     return guarded([&] {
         if (!batch) return NTT_B200_OK;
         DeviceGuard g(pl->device);
@@ -146,8 +196,33 @@ int host_transform_multi(const PrimePlan* const* plans, size_t n_plans, void* ho
 }
 
 // dst[0..len) op= ...; operands uploaded whole (pointwise calls are per-polynomial sized)
+int host_pointwise_small(const PrimePlan* pl, int op, void* dst, size_t len, const void* a, size_t a_len,
+                         const void* b, size_t b_len) {
+    return guarded([&] {
+        DeviceGuard g(pl->device);
+        const size_t eb = (size_t)pl->elem_bytes;
+        auto up16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+        const size_t o_a = up16(len * eb), o_b = o_a + up16(a_len * eb), total = o_b + up16(b_len * eb);
+        SmallCtx& c = small_ctx(pl->device);
+        c.ensure(total);
+        std::memcpy(c.h, dst, len * eb);
+        if (a) std::memcpy(c.h + o_a, a, a_len * eb);
+        if (b) std::memcpy(c.h + o_b, b, b_len * eb);
+        NTT_CUDA_CHECK(cudaMemcpyAsync(c.d, c.h, total, cudaMemcpyHostToDevice, c.st));
+        if (op == 0) pl->normalize(c.d, len, c.st);
+        if (op == 1) pl->mul_assign_normalize(c.d, c.d + o_a, len, a_len, c.st);
+        if (op == 2) pl->mul_accumulate(c.d, c.d + o_a, c.d + o_b, len, a_len, b_len, c.st);
+        NTT_CUDA_CHECK(cudaMemcpyAsync(c.h, c.d, len * eb, cudaMemcpyDeviceToHost, c.st));
+        NTT_CUDA_CHECK(cudaStreamSynchronize(c.st));
+        std::memcpy(dst, c.h, len * eb);
+        return NTT_B200_OK;
+    });
+}
+
 int host_pointwise(const PrimePlan* pl, int op, void* dst, size_t len, const void* a, size_t a_len,
                    const void* b, size_t b_len) {
+    if (len && pl->device < 16 && (len + a_len + b_len) * (size_t)pl->elem_bytes + 64 <= kSmallBytes)
+        return host_pointwise_small(pl, op, dst, len, a, a ? a_len : 0, b, b ? b_len : 0);
     return guarded([&] {
         if (!len) return NTT_B200_OK;
         DeviceGuard g(pl->device);

@@ -157,9 +157,14 @@ namespace {
 struct HostStage2 {
     cudaStream_t st = nullptr;
     std::vector<void*> bufs;
+    bool owned = false;
     explicit HostStage2(int device) {
         keep_pool_cached(device);
-        NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        st = cached_stream(device);
+        if (!st) {
+            NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            owned = true;
+        }
     }
     void* alloc(size_t bytes) {
         void* d = nullptr;
@@ -184,7 +189,7 @@ struct HostStage2 {
         for (void* d : bufs) cudaFreeAsync(d, st);
         if (st) {
             cudaStreamSynchronize(st);
-            cudaStreamDestroy(st);
+            if (owned) cudaStreamDestroy(st);
         }
     }
 };
