@@ -525,3 +525,31 @@ def test_prime32_small_and_odd_sized_primes_pointwise(T, n, p):
     v = a.copy()
     gp.normalize(v)
     assert (v == op.normalize(a)).all()
+
+
+@pytest.mark.parametrize("bits,n,p", [(64, 2048, SOLINAS_P), (64, 65536, SOLINAS_P), (64, 16384, 4611686018427322369),
+                                      (32, 2048, 1073479681), (32, 32768, 1073479681)])
+def test_device_pointers_without_16_byte_alignment(T, bits, n, p):
+    """Device buffers that are only element-aligned (a view one coefficient into an allocation) take the
+    generic kernels (no 128-bit accesses, no bulk copies): same bits as the aligned fast path and the oracle,
+    for the transforms and the pointwise calls."""
+    import torch
+    gp, op = plan_pair(T, bits, n, p)
+    dt = np.uint64 if bits == 64 else np.uint32
+    sdt = np.int64 if bits == 64 else np.int32
+    rng = np.random.default_rng(n + bits)
+    batch = 3
+    x = rand_below(rng, p, (batch, n), dt)
+    st = torch.cuda.current_stream()
+    big = torch.zeros(batch * n + 1, dtype=torch.int64 if bits == 64 else torch.int32, device="cuda")
+    view = big[1:]
+    assert view.data_ptr() % 16 != 0
+    view.copy_(torch.from_numpy(x.view(sdt).reshape(-1)))
+    gp.fwd_device(view, batch, stream=st)
+    want_f = op.fwd(x)
+    assert (view.cpu().numpy().view(dt).reshape(batch, n) == want_f).all()
+    gp.inv_device(view, batch, stream=st)
+    want_i = op.inv(want_f)
+    assert (view.cpu().numpy().view(dt).reshape(batch, n) == want_i).all()
+    gp.normalize_device(view, stream=st)
+    assert (view.cpu().numpy().view(dt).reshape(batch, n) == x).all()
