@@ -41,6 +41,8 @@ struct PbsShape {
     static constexpr int kThreads = FastShape<LOGN>::kThreadsPerPoly;
     // shared memory (71 KiB at N = 2048, k = 1) allows three CTAs per SM: ask for <= 80 registers
     static constexpr int kMinBlocks = 768 / kThreads > 0 ? 768 / kThreads : 1;
+    // REGACC keeps GS*8 more 64-bit accumulators per thread: 128 registers, two CTAs per SM
+    static constexpr int kMinBlocksRegAcc = 512 / kThreads > 0 ? 512 / kThreads : 1;
     static size_t bytes(size_t n_lwe) { return (kTile + kAcc) * 8 + (n_lwe + 1) * 4; }
 };
 
@@ -60,8 +62,12 @@ __host__ __device__ inline size_t pbs_key_index(unsigned rg, unsigned q, unsigne
 // (the reference's parameter set): the multiply-accumulate runs in place in registers.  Otherwise
 // the NTT-domain accumulators live in `scratch` ([batch][GS][4][N/8] 16-byte vectors, private per
 // thread, L2 resident).
-template <class A, int LOGN, int GS, bool BNF, bool SINGLE>
-__global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, GS>::kMinBlocks)
+// REGACC: k + 1 == PPT and level > 1 (e.g. k = 1, l = 2, the shape of BASELINE config C3): still one
+// transform group per level, so the NTT-domain accumulators of the GS output polynomials stay in
+// registers across the levels instead of travelling through the L2 scratch.
+template <class A, int LOGN, int GS, bool BNF, bool SINGLE, bool REGACC = false>
+__global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads,
+                                  REGACC ? PbsShape<LOGN, GS>::kMinBlocksRegAcc : PbsShape<LOGN, GS>::kMinBlocks)
     ntt_fast_blind_rotate_kernel(uint64_t* __restrict__ acc_out, const uint64_t* __restrict__ lut,
                                  size_t lut_count, const unsigned* __restrict__ switched,
                                  const uint64_t* __restrict__ bsk_tw, ulonglong2* __restrict__ scratch,
@@ -73,7 +79,8 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
     using PS = PbsShape<LOGN, GS>;
     constexpr int PPT = PS::kPPT;
     constexpr unsigned N = 1u << LOGN, TPP = S::kThreadsPerPoly;
-    static_assert(!SINGLE || GS == PPT, "SINGLE needs one transform group");
+    static_assert(!(SINGLE || REGACC) || GS == PPT, "SINGLE / REGACC need one transform group per level");
+    static_assert(!(SINGLE && REGACC), "SINGLE is the level == 1 case");
     extern __shared__ __align__(16) uint64_t pbs_smem[];
     uint64_t* tile = pbs_smem;
     uint64_t* accS = pbs_smem + PS::kTile;
@@ -82,7 +89,7 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
     const size_t b = blockIdx.x;
     const uint64_t p = FixedModulus<A>::value ? FixedModulus<A>::value : c.p;
     const SubPoly sub{0u, 0u};
-    ulonglong2* accN = SINGLE ? nullptr : scratch + b * (size_t)(GS * 4 * TPP);
+    ulonglong2* accN = (SINGLE || REGACC) ? nullptr : scratch + b * (size_t)(GS * 4 * TPP);
 
     for (unsigned i = t; i <= n_lwe; i += TPP) sw[i] = switched[b * (n_lwe + 1) + i];
     __syncthreads();
@@ -103,6 +110,7 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
         const ulonglong2* ggsw =
             reinterpret_cast<const ulonglong2*>(bsk_tw + (size_t)i * level * GS * GS * N);
         uint64_t x[PPT][8];
+        uint64_t o[REGACC ? GS : 1][8];  // REGACC: lazy sums of canonical products, one per output polynomial
         bool first = true;
 #pragma unroll 1
         for (unsigned lv = 0; lv < level; ++lv) {
@@ -165,6 +173,18 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
                             x[cc % PPT][2 * q] = A::acc_fin(c, o[cc][0]);
                             x[cc % PPT][2 * q + 1] = A::acc_fin(c, o[cc][1]);
                         }
+                    } else if (REGACC) {
+#pragma unroll
+                        for (int cc = 0; cc < GS; ++cc) {
+                            uint64_t s0 = first ? 0 : o[cc][2 * q], s1 = first ? 0 : o[cc][2 * q + 1];
+#pragma unroll
+                            for (int pp = 0; pp < PPT; ++pp) {
+                                s0 = A::acc_add(c, s0, A::mul_const(c, x[pp][2 * q], g[pp][cc].x));
+                                s1 = A::acc_add(c, s1, A::mul_const(c, x[pp][2 * q + 1], g[pp][cc].y));
+                            }
+                            o[cc][2 * q] = s0;
+                            o[cc][2 * q + 1] = s1;
+                        }
                     } else {
 #pragma unroll
                         for (int cc = 0; cc < GS; ++cc) {
@@ -185,7 +205,12 @@ __global__ void __launch_bounds__(PbsShape<LOGN, GS>::kThreads, PbsShape<LOGN, G
         }
 #pragma unroll 1
         for (int cg = 0; cg < PS::kGroups; ++cg) {
-            if (!SINGLE) {
+            if (REGACC) {
+#pragma unroll
+                for (int pp = 0; pp < PPT; ++pp)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) x[pp][k] = A::acc_fin(c, o[pp][k]);  // one group: cg == 0
+            } else if (!SINGLE) {
 #pragma unroll
                 for (int pp = 0; pp < PPT; ++pp)
 #pragma unroll

@@ -2,6 +2,7 @@
 // NTT-PBS parameter set in the reference (tfhe/src/core_crypto/algorithms/test/mod.rs:106-130).
 // Other primes use the composed path of capi_pbs.cu.
 #include <algorithm>
+#include <cstdlib>
 
 #include "ntt_engine.cuh"
 #include "ntt_pbs_fused.cuh"
@@ -9,17 +10,17 @@
 namespace nttb200 {
 namespace {
 
-template <class A, int LOGN, int GS, bool BNF, bool SINGLE>
+template <class A, int LOGN, int GS, bool BNF, bool SINGLE, bool REGACC = false>
 bool launch_blind_rotate(uint64_t* acc_out, const uint64_t* lut, size_t lut_count, const unsigned* switched,
                          const uint64_t* bsk_tw, size_t n_lwe, unsigned base_log, unsigned level, size_t batch,
                          unsigned width, const typename A::TW* tw_fwd, const typename A::TW* tw_inv,
                          const typename A::Ctx& c, typename A::TW n_inv, cudaStream_t st) {
-    auto kern = ntt_fast_blind_rotate_kernel<A, LOGN, GS, BNF, SINGLE>;
+    auto kern = ntt_fast_blind_rotate_kernel<A, LOGN, GS, BNF, SINGLE, REGACC>;
     size_t smem = PbsShape<LOGN, GS>::bytes(n_lwe);
     if (smem > size_t(227) * 1024) return false;
     NTT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ulonglong2* scratch = nullptr;
-    if (!SINGLE) NTT_CUDA_CHECK(cudaMallocAsync(&scratch, batch * ((size_t)GS << LOGN) * 8, st));
+    if (!SINGLE && !REGACC) NTT_CUDA_CHECK(cudaMallocAsync(&scratch, batch * ((size_t)GS << LOGN) * 8, st));
     kern<<<(unsigned)batch, FastShape<LOGN>::kThreadsPerPoly, smem, st>>>(
         acc_out, lut, lut_count, switched, bsk_tw, scratch, (unsigned)n_lwe, base_log, level, width, tw_fwd, tw_inv,
         c, n_inv);
@@ -29,6 +30,15 @@ bool launch_blind_rotate(uint64_t* acc_out, const uint64_t* lut, size_t lut_coun
     return true;
 }
 
+// NTT_B200_PBS_NO_REGACC=1 keeps the multi-level shapes on the L2-scratch accumulators (A/B measurements)
+bool reg_acc_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("NTT_B200_PBS_NO_REGACC");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
 template <class A, int LOGN, int GS, class... Args>
 bool by_variant(int bnf, unsigned level, Args... args) {
     constexpr bool kCanSingle = PbsShape<LOGN, GS>::kGroups == 1;
@@ -36,6 +46,9 @@ bool by_variant(int bnf, unsigned level, Args... args) {
         if (level == 1)
             return bnf ? launch_blind_rotate<A, LOGN, GS, true, true>(args...)
                        : launch_blind_rotate<A, LOGN, GS, false, true>(args...);
+        if (reg_acc_enabled())  // level > 1, one transform group per level: accumulators in registers
+            return bnf ? launch_blind_rotate<A, LOGN, GS, true, false, true>(args...)
+                       : launch_blind_rotate<A, LOGN, GS, false, false, true>(args...);
     }
     return bnf ? launch_blind_rotate<A, LOGN, GS, true, false>(args...)
                : launch_blind_rotate<A, LOGN, GS, false, false>(args...);
