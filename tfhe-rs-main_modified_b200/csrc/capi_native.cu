@@ -372,7 +372,7 @@ struct FusedPrimes {
 // operands are re-read per prime (L1/L2 hits after the first), so a thread holds 16 residues at a
 // time and two 512-thread CTAs fit an SM.
 template <int LOGN>
-struct FusedMinBlocks {
+struct CrtFusedMinBlocks {
     static constexpr int value = 1024 / FastShape<LOGN>::kThreadsPerPoly > 0 ? 1024 / FastShape<LOGN>::kThreadsPerPoly : 1;
 };
 template <int NP, int LOGN>
@@ -381,7 +381,7 @@ constexpr size_t fused_smem_bytes() {
 }
 
 template <int KIND, class VT, int NP, int LOGN, bool BINARY>
-__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly, FusedMinBlocks<LOGN>::value)
+__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly, CrtFusedMinBlocks<LOGN>::value)
     native_polymul_fused_kernel(VT* __restrict__ prod, const VT* __restrict__ lhs,
                                 const VT* __restrict__ rhs, const __grid_constant__ FusedPrimes<NP> P,
                                 const __grid_constant__ CrtConsts k) {
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly, FusedMinBloc
 // transforms: 2.3 GB instead of 0.94 GB per GiB of u64 values with five primes; 0.59 against 0.72 ms
 // for 8192 polynomials of 4096 u64).
 template <class VT, int NP, int LOGN>
-__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly, FusedMinBlocks<LOGN>::value)
+__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly, CrtFusedMinBlocks<LOGN>::value)
     native_fwd_fused_kernel(const VT* __restrict__ value, const __grid_constant__ ResPtrs res,
                             const __grid_constant__ FusedPrimes<NP> P, const __grid_constant__ CrtConsts k, int reduce) {
     using S = FastShape<LOGN>;
