@@ -392,6 +392,41 @@ int ntt_b200_is_prime64(uint64_t n);
 int ntt_b200_largest_prime_in_arithmetic_progression64(uint64_t factor, uint64_t offset,
                                                        uint64_t lo, uint64_t hi, uint64_t *out);
 
+/* ------------------------------------------------------------------------------------------
+ * custum_radix   (tfhe-ntt/src/custum_radix/mod.rs:1-22, exported at lib.rs:116)
+ * The fork's recursive CYCLIC transforms of u32 vectors: natural order in and out, over a caller-built
+ * table twiddles[k] = root^k mod p (root of order n).  `kind` names the reference routine; on such a
+ * table the three forward routines are one function, the inverse routines differ by the constant
+ * their bases apply (see csrc/capi_custum_radix.cu).  n must be a power of two (1 allowed) and the
+ * table at least n long (the reference indexes it modulo n): NTT_B200_ERR_LEN otherwise, where the
+ * reference overflows its stack or panics on an index.  The MultStats counters of fwd_1.rs are not
+ * produced (a statistic of the CPU recursion).
+ * ------------------------------------------------------------------------------------------ */
+#define NTT_B200_CR_RADIX2 0      /* fft_radix2_recursive fwd.rs:170-205 (= fwd_1.rs:190-230), ifft inv.rs:178-230 */
+#define NTT_B200_CR_RADIX4 1      /* fft_radix4_recursive fwd.rs:105-168 (= fwd_1.rs:102-188), ifft inv.rs:106-176 */
+#define NTT_B200_CR_SPLIT_RADIX 2 /* fft_split_radix_recursive fwd.rs:207-272 (= fwd_1.rs:232-294), ifft inv.rs:232-303 */
+#define NTT_B200_CR_RADIX4_MUT 3  /* inverse only: ifft_radix4_recursive_mut fwd_1.rs:296-379 */
+
+/* fft_*_recursive(a: &mut [u32], twiddles: &[u32], p: u32), host memory, in place */
+int ntt_b200_custum_radix_fft(int kind, uint32_t *a, size_t n, const uint32_t *twiddles,
+                              size_t tw_len, uint32_t p);
+/* ifft_*_recursive(a, inv_twiddles, p, n_inv, top) */
+int ntt_b200_custum_radix_ifft(int kind, uint32_t *a, size_t n, const uint32_t *inv_twiddles,
+                               size_t tw_len, uint32_t p, uint32_t n_inv, int top);
+/* NEW: `batch` contiguous vectors in host memory */
+int ntt_b200_custum_radix_fft_batch(int kind, uint32_t *host, size_t n, size_t batch,
+                                    const uint32_t *twiddles, size_t tw_len, uint32_t p);
+int ntt_b200_custum_radix_ifft_batch(int kind, uint32_t *host, size_t n, size_t batch,
+                                     const uint32_t *inv_twiddles, size_t tw_len, uint32_t p,
+                                     uint32_t n_inv, int top);
+/* NEW: device-resident vectors and table on the current device, asynchronous on `stream` */
+int ntt_b200_custum_radix_fft_device(int kind, uint32_t *dev, size_t n, size_t batch,
+                                     const uint32_t *twiddles_dev, size_t tw_len, uint32_t p,
+                                     void *stream);
+int ntt_b200_custum_radix_ifft_device(int kind, uint32_t *dev, size_t n, size_t batch,
+                                      const uint32_t *inv_twiddles_dev, size_t tw_len, uint32_t p,
+                                      uint32_t n_inv, int top, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -251,6 +251,29 @@ void tfo_convert_standard_lwe_bootstrap_key_to_ntt64(const tfo_plan64 *, const u
 int tfo_plan64_fwd_batch_simd(const tfo_plan64 *, uint64_t *buf, size_t batch, int threads);
 int tfo_plan64_inv_batch_simd(const tfo_plan64 *, uint64_t *buf, size_t batch, int threads);
 
+/* custum_radix (tfhe_ntt_custum_radix_oracle.c): the fork's recursive cyclic u32 transforms,
+ * tfhe-ntt/src/custum_radix/{fwd.rs,inv.rs,fwd_1.rs}.  tw[k] = root^k, natural order in and out. */
+typedef struct {
+    size_t nonzero_mults, skipped_mults; /* fwd_1.rs:3-7 MultStats */
+} tfo_mult_stats;
+uint32_t tfo_cr_pow_mod(uint32_t base, uint32_t exp, uint32_t p);
+uint32_t tfo_cr_mod_inverse(uint32_t a, uint32_t p);
+uint32_t tfo_cr_compute_primitive_root(uint32_t p);
+int tfo_cr_make_twiddles(size_t n, uint32_t p, uint32_t *tw);
+void tfo_cr_make_inv_twiddles(const uint32_t *tw, size_t n, uint32_t p, uint32_t *inv);
+void tfo_cr_fft_radix4_recursive(uint32_t *a, size_t n, const uint32_t *tw, uint32_t p);
+void tfo_cr_fft_radix2_recursive(uint32_t *a, size_t n, const uint32_t *tw, uint32_t p);
+void tfo_cr_fft_split_radix_recursive(uint32_t *a, size_t n, const uint32_t *tw, uint32_t p);
+void tfo_cr_ifft_radix4_recursive(uint32_t *a, size_t n, const uint32_t *inv_tw, uint32_t p, uint32_t n_inv, int top);
+void tfo_cr_ifft_radix2_recursive(uint32_t *a, size_t n, const uint32_t *inv_tw, uint32_t p, uint32_t n_inv, int top);
+void tfo_cr_ifft_split_radix_recursive(uint32_t *a, size_t n, const uint32_t *inv_tw, uint32_t p, uint32_t n_inv,
+                                       int top);
+void tfo_cr_fft_radix4_recursive_mut(uint32_t *a, size_t n, const uint32_t *tw, uint32_t p, tfo_mult_stats *st);
+void tfo_cr_fft_radix2_recursive_mut(uint32_t *a, size_t n, const uint32_t *tw, uint32_t p, tfo_mult_stats *st);
+void tfo_cr_fft_split_radix_recursive_mut(uint32_t *a, size_t n, const uint32_t *tw, uint32_t p, tfo_mult_stats *st);
+void tfo_cr_ifft_radix4_recursive_mut(uint32_t *a, size_t n, const uint32_t *inv_tw, uint32_t p, uint32_t n_inv,
+                                      int top, tfo_mult_stats *st);
+
 #ifdef __cplusplus
 }
 #endif

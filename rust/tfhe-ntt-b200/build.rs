@@ -11,7 +11,7 @@ fn main() {
     let sources = [
         "ntt_engine.cu", "ntt_fast_solinas.cu", "ntt_fast_shoup64.cu", "ntt_fast_shoup32.cu",
         "ntt_fast_exact.cu", "ntt_pbs_solinas.cu", "capi_prime.cu", "capi_native.cu", "capi_product.cu",
-        "capi_pbs.cu",
+        "capi_pbs.cu", "capi_custum_radix.cu",
     ];
     let mut objects = Vec::new();
     for src in sources {

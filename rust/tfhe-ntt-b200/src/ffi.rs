@@ -99,6 +99,13 @@ extern "C" {
     pub fn ntt_b200_native_inv(plan: *const ntt_b200_native_plan, value: *mut c_void, len: usize, residues: *const *mut c_void) -> c_int;
     pub fn ntt_b200_native_negacyclic_polymul(plan: *const ntt_b200_native_plan, prod: *mut c_void, prod_len: usize, lhs: *const c_void, lhs_len: usize, rhs: *const c_void, rhs_len: usize) -> c_int;
     pub fn ntt_b200_native_negacyclic_polymul_batch(plan: *const ntt_b200_native_plan, prod: *mut c_void, lhs: *const c_void, rhs: *const c_void, batch: usize) -> c_int;
+    // custum_radix (tfhe-ntt/src/custum_radix/mod.rs:1-22)
+    pub fn ntt_b200_custum_radix_fft(kind: c_int, a: *mut u32, n: usize, twiddles: *const u32, tw_len: usize, p: u32) -> c_int;
+    pub fn ntt_b200_custum_radix_ifft(kind: c_int, a: *mut u32, n: usize, inv_twiddles: *const u32, tw_len: usize, p: u32, n_inv: u32, top: c_int) -> c_int;
+    pub fn ntt_b200_custum_radix_fft_batch(kind: c_int, host: *mut u32, n: usize, batch: usize, twiddles: *const u32, tw_len: usize, p: u32) -> c_int;
+    pub fn ntt_b200_custum_radix_ifft_batch(kind: c_int, host: *mut u32, n: usize, batch: usize, inv_twiddles: *const u32, tw_len: usize, p: u32, n_inv: u32, top: c_int) -> c_int;
+    pub fn ntt_b200_custum_radix_fft_device(kind: c_int, dev: *mut u32, n: usize, batch: usize, twiddles_dev: *const u32, tw_len: usize, p: u32, stream: *mut c_void) -> c_int;
+    pub fn ntt_b200_custum_radix_ifft_device(kind: c_int, dev: *mut u32, n: usize, batch: usize, inv_twiddles_dev: *const u32, tw_len: usize, p: u32, n_inv: u32, top: c_int, stream: *mut c_void) -> c_int;
 }
 
 /// Status -> the reference's behaviour: length errors panic like `assert_eq!` (prime64.rs:898),

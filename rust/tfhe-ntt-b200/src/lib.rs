@@ -7,5 +7,6 @@ pub mod prime32;
 pub mod prime64;
 pub mod product;
 pub mod ntt64_pbs;
+pub mod custum_radix;
 mod native;
 pub use native::{native128, native32, native64, native_binary128, native_binary32, native_binary64};

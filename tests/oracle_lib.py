@@ -33,7 +33,7 @@ def build(native=False):
     target = "native" if native else "all"
     name = "libtfhe_ntt_oracle_native.so" if native else "libtfhe_ntt_oracle.so"
     so = os.path.join(_ORACLE_DIR, name)
-    src = [os.path.join(_ORACLE_DIR, f) for f in ("tfhe_ntt_oracle.c", "tfhe_ntt_simd.c", "tfhe_ntt_pbs_oracle.c",
+    src = [os.path.join(_ORACLE_DIR, f) for f in ("tfhe_ntt_oracle.c", "tfhe_ntt_simd.c", "tfhe_ntt_pbs_oracle.c", "tfhe_ntt_custum_radix_oracle.c",
                                                  "tfhe_ntt_oracle.h")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src)
     # the -march=native build is redone once per process: the file may have travelled from a

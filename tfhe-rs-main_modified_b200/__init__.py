@@ -37,4 +37,5 @@ from . import native_binary32, native_binary64, native_binary128  # noqa: F401
 from . import product  # noqa: F401
 from . import ntt64  # noqa: F401
 from . import ntt64_pbs  # noqa: F401
+from . import custum_radix  # noqa: F401
 from . import sharding  # noqa: F401

@@ -108,6 +108,12 @@ SIGNATURES = {
     "ntt_b200_product_mul_accumulate": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz]),
     "ntt_b200_product_fwd_device": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "ntt_b200_product_inv_device": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
+    "ntt_b200_custum_radix_fft": (_i, [_i, _vp, _sz, _vp, _sz, _u32]),
+    "ntt_b200_custum_radix_ifft": (_i, [_i, _vp, _sz, _vp, _sz, _u32, _u32, _i]),
+    "ntt_b200_custum_radix_fft_batch": (_i, [_i, _vp, _sz, _sz, _vp, _sz, _u32]),
+    "ntt_b200_custum_radix_ifft_batch": (_i, [_i, _vp, _sz, _sz, _vp, _sz, _u32, _u32, _i]),
+    "ntt_b200_custum_radix_fft_device": (_i, [_i, _vp, _sz, _sz, _vp, _sz, _u32, _vp]),
+    "ntt_b200_custum_radix_ifft_device": (_i, [_i, _vp, _sz, _sz, _vp, _sz, _u32, _u32, _i, _vp]),
     "ntt_b200_is_prime64": (_i, [_u64]),
     "ntt_b200_largest_prime_in_arithmetic_progression64": (_i, [_u64, _u64, _u64, _u64, C.POINTER(_u64)]),
 }

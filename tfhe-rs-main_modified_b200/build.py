@@ -14,7 +14,8 @@ OUT = os.path.join(HERE, "libtfhe_ntt_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
 SOURCES = ["ntt_engine.cu", "ntt_fast_solinas.cu", "ntt_fast_shoup64.cu", "ntt_fast_shoup32.cu",
-           "ntt_fast_exact.cu", "ntt_pbs_solinas.cu", "capi_prime.cu", "capi_native.cu", "capi_product.cu", "capi_pbs.cu"]
+           "ntt_fast_exact.cu", "ntt_pbs_solinas.cu", "capi_prime.cu", "capi_native.cu", "capi_product.cu", "capi_pbs.cu",
+           "capi_custum_radix.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

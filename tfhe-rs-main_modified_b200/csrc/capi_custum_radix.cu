@@ -1,0 +1,281 @@
+// custum_radix -- the fork's cyclic u32 transforms (reference: tfhe-ntt/src/custum_radix/{fwd.rs,inv.rs,fwd_1.rs}).
+//
+// The reference has three recursive formulations (radix-2, radix-4, split-radix) of ONE function: for a
+// table tw[k] = root^k (root of order n modulo p) each forward routine returns X[k] = sum_j a[j] root^(jk),
+// natural order in and out, canonical in [0, p); the inverse routines return the same sum over the inverse
+// table times a constant that depends on the routine (which of its bases scale).  Because every value is
+// canonical the formulation cannot be observed in the result, so the GPU runs one schedule for all of
+// them: the iterative form of the reference's radix-2 recursion (identical to it for ANY table, including
+// the multiplication-free size-2 base), a batch of vectors per launch, stages in shared memory.
+//
+// What the recursions add on top of the sum (restated in `final_factor`):
+//   ifft_radix2 / ifft_split_radix (inv.rs:178-303)  n_inv when `top`, except n <= 2 (the bases return early)
+//   ifft_radix4                    (inv.rs:106-176)  the size-2 base halves: 1/2 when log2 n is odd; n_inv
+//                                                    when `top` and n > 2
+//   ifft_radix4_recursive_mut      (fwd_1.rs:296-379) n_inv when `top`, every n
+// The MultStats counters of fwd_1.rs count zero operands inside each particular recursion; they are a
+// statistic of the CPU formulation and are not produced here.
+#include <algorithm>
+#include <cstring>
+
+#include "capi_common.cuh"
+
+using namespace nttb200;
+
+namespace {
+
+constexpr unsigned kLogBlockMax = 15;  // 2^15 u32 = 128 KiB of shared memory per CTA
+constexpr unsigned kThreads = 512;
+
+struct CrMod {
+    uint32_t p;
+    uint64_t mu;  // floor(2^64 / p)
+};
+
+// fwd.rs:1-19, literally
+NTT_DEVINL uint32_t cr_add(uint32_t a, uint32_t b, uint32_t p) {
+    uint64_t s = (uint64_t)a + b;
+    return s >= p ? (uint32_t)(s - p) : (uint32_t)s;
+}
+NTT_DEVINL uint32_t cr_sub(uint32_t a, uint32_t b, uint32_t p) {
+    return a >= b ? a - b : (uint32_t)((uint64_t)a + p - b);
+}
+// (a * b) % p without a division: q = floor(x * mu / 2^64) is floor(x / p) or one less
+NTT_DEVINL uint32_t cr_mul(uint32_t a, uint32_t b, const CrMod& m) {
+    uint64_t x = (uint64_t)a * b;
+    uint64_t r = x - __umul64hi(x, m.mu) * m.p;
+    if (r >= m.p) r -= m.p;
+    if (r >= m.p) r -= m.p;
+    return (uint32_t)r;
+}
+
+// One CTA owns `per_cta` blocks of 2^logb consecutive elements (a whole vector when logb == logn) and runs
+// the stages of length 2 .. 2^logb on them in shared memory.  logb == logn: the load applies the bit
+// reversal; longer vectors were permuted by cr_bitrev_kernel.  Stage `len` multiplies by
+// tw[k * (n / len)] -- the chain of subsampled tables of fwd.rs:188-192 -- and the size-2 stage does not
+// multiply (fwd.rs:173-178).  `factor` != 1 scales the outputs (only when logb == logn).
+__global__ void __launch_bounds__(kThreads)
+cr_block_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, unsigned logn, unsigned logb,
+                size_t total_blocks, unsigned per_cta, CrMod m, uint32_t factor) {
+    extern __shared__ uint32_t s[];
+    const unsigned B = 1u << logb;
+    const size_t first = (size_t)blockIdx.x * per_cta;
+    const unsigned here = (unsigned)min((size_t)per_cta, total_blocks - first);
+    uint32_t* base = data + first * B;
+    const unsigned elems = here * B;
+    const bool whole = logb == logn;
+    for (unsigned i = threadIdx.x; i < elems; i += blockDim.x) {
+        unsigned blk = i >> logb, j = i & (B - 1);
+        unsigned dst = whole ? (logb ? (__brev(j) >> (32 - logb)) : 0u) : j;
+        s[(blk << logb) + dst] = base[i];
+    }
+    __syncthreads();
+    const unsigned bf = elems >> 1;
+    for (unsigned ll = 1; ll <= logb; ++ll) {
+        const unsigned half = 1u << (ll - 1);
+        const unsigned shift = logn - ll;  // table stride n / len
+        for (unsigned t = threadIdx.x; t < bf; t += blockDim.x) {
+            unsigned k = t & (half - 1);
+            unsigned i0 = ((t >> (ll - 1)) << ll) + k, i1 = i0 + half;
+            uint32_t e = s[i0], o = s[i1];
+            uint32_t x = ll == 1 ? o : cr_mul(o, __ldg(tw + ((size_t)k << shift)), m);
+            s[i0] = cr_add(e, x, m.p);
+            s[i1] = cr_sub(e, x, m.p);
+        }
+        __syncthreads();
+    }
+    for (unsigned i = threadIdx.x; i < elems; i += blockDim.x) {
+        uint32_t v = s[i];
+        base[i] = factor != 1 ? cr_mul(v, factor, m) : v;
+    }
+}
+
+// in-place bit reversal of each vector (n > 2^kLogBlockMax)
+__global__ void cr_bitrev_kernel(uint32_t* __restrict__ data, unsigned logn, size_t total) {
+    const size_t n = (size_t)1 << logn;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+        size_t poly = g >> logn;
+        unsigned i = (unsigned)(g & (n - 1)), r = __brev(i) >> (32 - logn);
+        if (i < r) {
+            uint32_t* v = data + (poly << logn);
+            uint32_t t = v[i];
+            v[i] = v[r];
+            v[r] = t;
+        }
+    }
+}
+
+// one stage of length 2^ll in global memory (ll > kLogBlockMax); the last one applies `factor`
+__global__ void cr_global_stage_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, unsigned logn,
+                                       unsigned ll, size_t total_bf, CrMod m, uint32_t factor) {
+    const unsigned half_mask = (1u << (ll - 1)) - 1, shift = logn - ll;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_bf; t += (size_t)gridDim.x * blockDim.x) {
+        size_t k = t & half_mask;
+        size_t i0 = ((t >> (ll - 1)) << ll) + k, i1 = i0 + half_mask + 1;
+        uint32_t e = data[i0], x = cr_mul(data[i1], __ldg(tw + (k << shift)), m);
+        uint32_t y0 = cr_add(e, x, m.p), y1 = cr_sub(e, x, m.p);
+        if (factor != 1) {
+            y0 = cr_mul(y0, factor, m);
+            y1 = cr_mul(y1, factor, m);
+        }
+        data[i0] = y0;
+        data[i1] = y1;
+    }
+}
+
+// host restatement of fwd.rs:22-39
+uint32_t mulmod_h(uint32_t a, uint32_t b, uint32_t p) { return (uint32_t)(((uint64_t)a * b) % p); }
+uint32_t powmod_h(uint32_t base, uint32_t exp, uint32_t p) {
+    uint32_t res = 1;
+    base %= p;
+    while (exp > 0) {
+        if (exp & 1) res = mulmod_h(res, base, p);
+        base = mulmod_h(base, base, p);
+        exp >>= 1;
+    }
+    return res;
+}
+
+bool shape_ok(size_t n, size_t tw_len, uint32_t p, int kind, bool inverse, int* status) {
+    const int max_kind = inverse ? NTT_B200_CR_RADIX4_MUT : NTT_B200_CR_SPLIT_RADIX;
+    if (kind < 0 || kind > max_kind || p < 2) {
+        *status = NTT_B200_ERR_ARG;
+        return false;
+    }
+    // n = 0 recurses forever in the reference, other non-powers of two index out of bounds, and so does a
+    // table shorter than the vector
+    if (n == 0 || (n & (n - 1)) || n > (size_t(1) << 30) || (n > 2 && tw_len < n)) {
+        *status = NTT_B200_ERR_LEN;
+        return false;
+    }
+    return true;
+}
+
+uint32_t final_factor(int kind, size_t n, unsigned logn, uint32_t p, uint32_t n_inv, bool inverse, bool top) {
+    if (!inverse) return 1;
+    uint32_t f = 1;
+    if (kind == NTT_B200_CR_RADIX4_MUT) return top ? n_inv % p : 1;
+    if (kind == NTT_B200_CR_RADIX4 && (logn & 1)) f = powmod_h(2, p - 2, p);  // inv.rs:112-114
+    if (top && n > 2) f = mulmod_h(f, n_inv, p);
+    return f;
+}
+
+void enqueue(uint32_t* dev, size_t n, size_t batch, const uint32_t* tw_dev, uint32_t p, uint32_t factor,
+             cudaStream_t st) {
+    if (!batch || (n == 1 && factor == 1)) return;
+    unsigned logn = 0;
+    while ((size_t(1) << logn) < n) ++logn;
+    const CrMod m{p, ~0ull / p + ((~0ull % p) + 1 == p ? 1 : 0)};  // floor(2^64 / p), p >= 2
+    const unsigned logb = std::min(logn, kLogBlockMax);
+    const size_t B = size_t(1) << logb, total_blocks = batch * (n >> logb), total = batch * n;
+    if (logn > logb) {
+        size_t grid = std::min<size_t>((total + 255) / 256, size_t(148) * 32);
+        cr_bitrev_kernel<<<(unsigned)grid, 256, 0, st>>>(dev, logn, total);
+    }
+    // several short vectors per CTA so that a CTA has at least kThreads butterflies per stage
+    unsigned per_cta = (unsigned)std::max<size_t>(1, std::min<size_t>((2 * kThreads) / B, total_blocks));
+    const size_t smem = (size_t)per_cta * B * sizeof(uint32_t);
+    static bool opted[64] = {};
+    int device = 0;
+    NTT_CUDA_CHECK(cudaGetDevice(&device));
+    if (smem > 48 * 1024 && !opted[device & 63]) {
+        NTT_CUDA_CHECK(cudaFuncSetAttribute(cr_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((size_t(1) << kLogBlockMax) * sizeof(uint32_t))));
+        opted[device & 63] = true;
+    }
+    const size_t ctas = (total_blocks + per_cta - 1) / per_cta;
+    const unsigned threads = (unsigned)std::min<size_t>(kThreads, std::max<size_t>(32, per_cta * B / 2));
+    cr_block_kernel<<<(unsigned)ctas, threads, smem, st>>>(dev, tw_dev, logn, logb, total_blocks, per_cta, m,
+                                                           logn == logb ? factor : 1u);
+    for (unsigned ll = logb + 1; ll <= logn; ++ll) {
+        size_t bf = total / 2, grid = std::min<size_t>((bf + 255) / 256, size_t(148) * 32);
+        cr_global_stage_kernel<<<(unsigned)grid, 256, 0, st>>>(dev, tw_dev, logn, ll, bf, m, ll == logn ? factor : 1u);
+    }
+    NTT_CUDA_CHECK(cudaGetLastError());
+}
+
+int run_device(int kind, uint32_t* dev, size_t n, size_t batch, const uint32_t* tw_dev, size_t tw_len, uint32_t p,
+               uint32_t n_inv, bool inverse, bool top, void* stream) {
+    int status = NTT_B200_OK;
+    if (!shape_ok(n, tw_len, p, kind, inverse, &status)) return status;
+    if (batch && (!dev || (n > 2 && !tw_dev))) return NTT_B200_ERR_ARG;
+    return guarded([&] {
+        unsigned logn = 0;
+        while ((size_t(1) << logn) < n) ++logn;
+        enqueue(dev, n, batch, tw_dev, p, final_factor(kind, n, logn, p, n_inv, inverse, top),
+                static_cast<cudaStream_t>(stream));
+        return NTT_B200_OK;
+    });
+}
+
+// host vectors: table and data go up, the kernels run, data comes back (32 MiB chunks on one stream)
+int run_host(int kind, uint32_t* host, size_t n, size_t batch, const uint32_t* tw, size_t tw_len, uint32_t p,
+             uint32_t n_inv, bool inverse, bool top) {
+    int status = NTT_B200_OK;
+    if (!shape_ok(n, tw_len, p, kind, inverse, &status)) return status;
+    if (batch && (!host || (n > 2 && !tw))) return NTT_B200_ERR_ARG;
+    if (!batch) return NTT_B200_OK;
+    return guarded([&] {
+        int device = 0;
+        NTT_CUDA_CHECK(cudaGetDevice(&device));
+        keep_pool_cached(device);
+        cudaStream_t st = cached_stream(device);
+        unsigned logn = 0;
+        while ((size_t(1) << logn) < n) ++logn;
+        const uint32_t factor = final_factor(kind, n, logn, p, n_inv, inverse, top);
+        const size_t poly_bytes = n * sizeof(uint32_t);
+        const size_t chunk = std::min(batch, std::max<size_t>(1, (size_t(32) << 20) / poly_bytes));
+        struct Scratch {  // stream-ordered, released on every exit path
+            cudaStream_t st;
+            uint32_t* ptr = nullptr;
+            ~Scratch() {
+                if (ptr) cudaFreeAsync(ptr, st);
+            }
+        } s_tw{st}, s_d{st};
+        const size_t tw_bytes = (n > 2 ? n : 1) * sizeof(uint32_t);
+        NTT_CUDA_CHECK(cudaMallocAsync(&s_tw.ptr, tw_bytes, st));
+        NTT_CUDA_CHECK(cudaMallocAsync(&s_d.ptr, chunk * poly_bytes, st));
+        uint32_t *d_tw = s_tw.ptr, *d = s_d.ptr;
+        if (n > 2) NTT_CUDA_CHECK(cudaMemcpyAsync(d_tw, tw, tw_bytes, cudaMemcpyHostToDevice, st));
+        for (size_t b0 = 0; b0 < batch; b0 += chunk) {
+            const size_t nb = std::min(chunk, batch - b0);
+            uint32_t* h = host + b0 * n;
+            NTT_CUDA_CHECK(cudaMemcpyAsync(d, h, nb * poly_bytes, cudaMemcpyHostToDevice, st));
+            enqueue(d, n, nb, d_tw, p, factor, st);
+            NTT_CUDA_CHECK(cudaMemcpyAsync(h, d, nb * poly_bytes, cudaMemcpyDeviceToHost, st));
+        }
+        NTT_CUDA_CHECK(cudaStreamSynchronize(st));
+        return NTT_B200_OK;
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+int ntt_b200_custum_radix_fft(int kind, uint32_t* a, size_t n, const uint32_t* twiddles, size_t tw_len, uint32_t p) {
+    return run_host(kind, a, n, 1, twiddles, tw_len, p, 1, false, false);
+}
+int ntt_b200_custum_radix_ifft(int kind, uint32_t* a, size_t n, const uint32_t* inv_twiddles, size_t tw_len,
+                               uint32_t p, uint32_t n_inv, int top) {
+    return run_host(kind, a, n, 1, inv_twiddles, tw_len, p, n_inv, true, top != 0);
+}
+int ntt_b200_custum_radix_fft_batch(int kind, uint32_t* host, size_t n, size_t batch, const uint32_t* twiddles,
+                                    size_t tw_len, uint32_t p) {
+    return run_host(kind, host, n, batch, twiddles, tw_len, p, 1, false, false);
+}
+int ntt_b200_custum_radix_ifft_batch(int kind, uint32_t* host, size_t n, size_t batch, const uint32_t* inv_twiddles,
+                                     size_t tw_len, uint32_t p, uint32_t n_inv, int top) {
+    return run_host(kind, host, n, batch, inv_twiddles, tw_len, p, n_inv, true, top != 0);
+}
+int ntt_b200_custum_radix_fft_device(int kind, uint32_t* dev, size_t n, size_t batch, const uint32_t* twiddles_dev,
+                                     size_t tw_len, uint32_t p, void* stream) {
+    return run_device(kind, dev, n, batch, twiddles_dev, tw_len, p, 1, false, false, stream);
+}
+int ntt_b200_custum_radix_ifft_device(int kind, uint32_t* dev, size_t n, size_t batch,
+                                      const uint32_t* inv_twiddles_dev, size_t tw_len, uint32_t p, uint32_t n_inv,
+                                      int top, void* stream) {
+    return run_device(kind, dev, n, batch, inv_twiddles_dev, tw_len, p, n_inv, true, top != 0, stream);
+}
+
+}  // extern "C"
