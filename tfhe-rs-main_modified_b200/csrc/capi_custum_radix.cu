@@ -5,8 +5,11 @@
 // natural order in and out, canonical in [0, p); the inverse routines return the same sum over the inverse
 // table times a constant that depends on the routine (which of its bases scale).  Because every value is
 // canonical the formulation cannot be observed in the result, so the GPU runs one schedule for all of
-// them: the iterative form of the reference's radix-2 recursion (identical to it for ANY table, including
-// the multiplication-free size-2 base), a batch of vectors per launch, stages in shared memory.
+// them: the iterative form of the reference's radix-2 recursion (identical to it for ANY table of values
+// below p, including the multiplication-free size-2 base), a batch of vectors per launch.  Vectors of 8 to
+// 2^15 elements take `cr_fast_kernel` (radix-8 register passes, the bit reversal folded into the first
+// pass, Barrett reduction on the fly because the table is the caller's); shorter and longer ones take the
+// plain stage kernels below it.
 //
 // What the recursions add on top of the sum (restated in `final_factor`):
 //   ifft_radix2 / ifft_split_radix (inv.rs:178-303)  n_inv when `top`, except n <= 2 (the bases return early)
@@ -90,6 +93,161 @@ cr_block_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, un
     }
 }
 
+// ---- the main path: 8 <= n <= 2^15, one vector per n/8 threads, radix-8 register passes ----------------
+//
+// MODE picks the cheapest exact arithmetic for the modulus (every result is canonical, so they agree):
+//   0  3p < 2^32: one-word Barrett on the fly -- s = floor(d / 2^(k-1)), q = floor(s * mu / 2^32) with
+//      mu = floor(2^(k+31) / p) and k the bit length of p, q in [floor(d/p) - 2, floor(d/p)] for d < p^2
+//       -- remainder in one word
+//   1  p < 2^31: the same quotient, remainder in two words
+//   2  any p: the 64-bit Barrett of cr_mul, 64-bit sums
+struct CrFast {
+    uint32_t p, mu32, ks;  // ks = k - 1
+    CrMod wide;
+};
+template <int MODE>
+NTT_DEVINL uint32_t crf_add(uint32_t a, uint32_t b, const CrFast& m) {
+    if (MODE == 2) return cr_add(a, b, m.p);
+    uint32_t s = a + b;
+    return s >= m.p ? s - m.p : s;
+}
+template <int MODE>
+NTT_DEVINL uint32_t crf_sub(uint32_t a, uint32_t b, const CrFast& m) {
+    return a >= b ? a - b : a + m.p - b;  // wraps to the exact value also when a + p >= 2^32
+}
+template <int MODE>
+NTT_DEVINL uint32_t crf_mul(uint32_t a, uint32_t b, const CrFast& m) {
+    if (MODE == 2) return cr_mul(a, b, m.wide);
+    const uint64_t d = (uint64_t)a * b;
+    const uint32_t q = __umulhi((uint32_t)(d >> m.ks), m.mu32);
+    if (MODE == 0) {
+        uint32_t r = (uint32_t)d - q * m.p;
+        if (r >= m.p) r -= m.p;
+        if (r >= m.p) r -= m.p;
+        return r;
+    }
+    uint64_t r = d - (uint64_t)q * m.p;
+    if (r >= m.p) r -= m.p;
+    if (r >= m.p) r -= m.p;
+    return (uint32_t)r;
+}
+
+// one word of padding after every 8: tuple accesses of stride 1, 8, 64 ... spread over the banks
+NTT_DEVINL unsigned cr_pad(unsigned a) { return a + (a >> 3); }
+
+// Stages ll .. ll+R-1 of the reference's radix-2 recursion on the 2^R elements x[j] at positions
+// base + j * 2^(ll-1), base = group * 2^(ll-1+R) + k: in stage ll+q element j (bit q clear) pairs with
+// j + 2^q and sits at offset k + (j mod 2^q) * 2^(ll-1) of its group, which indexes the subsampled table
+// (fwd.rs:188-201).  The size-2 stage does not multiply (fwd.rs:173-178).
+template <int MODE, int R>
+NTT_DEVINL void cr_tuple(uint32_t (&x)[8], const uint32_t* __restrict__ tw, unsigned k, unsigned ll, unsigned logn,
+                         const CrFast& m) {
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        const unsigned shift = logn - (ll + q);
+#pragma unroll
+        for (int j = 0; j < (1 << R); ++j) {
+            if (j & (1 << q)) continue;
+            const unsigned kq = k + ((unsigned)(j & ((1 << q) - 1)) << (ll - 1));
+            const uint32_t e = x[j], o = x[j + (1 << q)];
+            const uint32_t t = (ll + q == 1) ? o : crf_mul<MODE>(o, __ldg(tw + ((size_t)kq << shift)), m);
+            x[j] = crf_add<MODE>(e, t, m);
+            x[j + (1 << q)] = crf_sub<MODE>(e, t, m);
+        }
+    }
+}
+
+template <int MODE, int R>
+NTT_DEVINL void cr_last_pass(uint32_t* __restrict__ g, const uint32_t* s, const uint32_t* __restrict__ tw,
+                             unsigned logn, unsigned ll, unsigned vectors, unsigned pn, const CrFast& m,
+                             uint32_t factor) {
+    const unsigned lt = logn - R, half = 1u << lt;  // the group is the whole vector: k = tuple index
+    for (unsigned t = threadIdx.x; t < (vectors << lt); t += blockDim.x) {
+        const unsigned v = t >> lt, k = t & (half - 1);
+        uint32_t x[8];
+#pragma unroll
+        for (int j = 0; j < (1 << R); ++j) x[j] = s[v * pn + cr_pad(k + ((unsigned)j << lt))];
+        cr_tuple<MODE, R>(x, tw, k, ll, logn, m);
+#pragma unroll
+        for (int j = 0; j < (1 << R); ++j)
+            g[((size_t)v << logn) + k + ((unsigned)j << lt)] = factor != 1 ? crf_mul<MODE>(x[j], factor, m) : x[j];
+    }
+}
+
+// The first pass reads the vector in place of the bit reversal: thread tl takes a[tl + brev3(j) * n/8], which
+// are the elements 8 * brev(tl) + j of the reversed order, runs stages 1-3 and parks them there; middle passes
+// run three stages each in shared memory; the last pass (1-3 stages) writes global memory, coalesced.
+template <int MODE>
+__global__ void __launch_bounds__(1024)
+cr_fast_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, unsigned logn, size_t total_vectors,
+               unsigned per_cta, CrFast m, uint32_t factor) {
+    extern __shared__ uint32_t s[];
+    const size_t first = (size_t)blockIdx.x * per_cta;
+    const unsigned vectors = (unsigned)min((size_t)per_cta, total_vectors - first);
+    uint32_t* g = data + (first << logn);
+    const unsigned lt = logn - 3, tmask = (1u << lt) - 1, pn = cr_pad(1u << logn);
+    const unsigned tuples = vectors << lt;
+    for (unsigned t = threadIdx.x; t < tuples; t += blockDim.x) {
+        const unsigned v = t >> lt, tl = t & tmask;
+        const uint32_t* src = g + ((size_t)v << logn) + tl;
+        uint32_t x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = src[(size_t)(((j & 1) << 2) | (j & 2) | (j >> 2)) << lt];
+        cr_tuple<MODE, 3>(x, tw, 0, 1, logn, m);
+        if (lt == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[(size_t)v * 8 + j] = factor != 1 ? crf_mul<MODE>(x[j], factor, m) : x[j];
+        } else {
+            const unsigned pos = __brev(tl) >> (32 - lt);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[v * pn + cr_pad(8 * pos + j)] = x[j];
+        }
+    }
+    if (lt == 0) return;
+    __syncthreads();
+    unsigned ll = 4;
+    for (; logn - ll + 1 > 3; ll += 3) {
+        const unsigned half = 1u << (ll - 1);
+        for (unsigned t = threadIdx.x; t < tuples; t += blockDim.x) {
+            const unsigned v = t >> lt, tl = t & tmask;
+            const unsigned k = tl & (half - 1), base = ((tl >> (ll - 1)) << (ll + 2)) + k;
+            uint32_t* sv = s + v * pn;
+            uint32_t x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = sv[cr_pad(base + ((unsigned)j << (ll - 1)))];
+            cr_tuple<MODE, 3>(x, tw, k, ll, logn, m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sv[cr_pad(base + ((unsigned)j << (ll - 1)))] = x[j];
+        }
+        __syncthreads();
+    }
+    switch (logn - ll + 1) {
+        case 1: cr_last_pass<MODE, 1>(g, s, tw, logn, ll, vectors, pn, m, factor); break;
+        case 2: cr_last_pass<MODE, 2>(g, s, tw, logn, ll, vectors, pn, m, factor); break;
+        default: cr_last_pass<MODE, 3>(g, s, tw, logn, ll, vectors, pn, m, factor); break;
+    }
+}
+
+template <int MODE>
+void launch_fast(uint32_t* dev, unsigned logn, size_t batch, const uint32_t* tw_dev, const CrFast& m, uint32_t factor,
+                 cudaStream_t st) {
+    const size_t n = size_t(1) << logn, tuples = n / 8;
+    // short vectors share a CTA (at least 256 tuples per CTA); long ones get up to 1024 threads
+    const unsigned per_cta = (unsigned)std::max<size_t>(1, std::min<size_t>(256 / tuples, batch));
+    const unsigned threads = (unsigned)std::min<size_t>(1024, std::max<size_t>(32, per_cta * tuples));
+    const size_t smem = (size_t)per_cta * (n + n / 8) * sizeof(uint32_t);
+    static bool opted[64] = {};
+    int device = 0;
+    NTT_CUDA_CHECK(cudaGetDevice(&device));
+    if (smem > 48 * 1024 && !opted[device & 63]) {
+        NTT_CUDA_CHECK(cudaFuncSetAttribute(cr_fast_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(((size_t(1) << kLogBlockMax) * 9 / 8) * sizeof(uint32_t))));
+        opted[device & 63] = true;
+    }
+    const size_t ctas = (batch + per_cta - 1) / per_cta;
+    cr_fast_kernel<MODE><<<(unsigned)ctas, threads, smem, st>>>(dev, tw_dev, logn, batch, per_cta, m, factor);
+}
+
 // in-place bit reversal of each vector (n > 2^kLogBlockMax)
 __global__ void cr_bitrev_kernel(uint32_t* __restrict__ data, unsigned logn, size_t total) {
     const size_t n = (size_t)1 << logn;
@@ -166,6 +324,20 @@ void enqueue(uint32_t* dev, size_t n, size_t batch, const uint32_t* tw_dev, uint
     unsigned logn = 0;
     while ((size_t(1) << logn) < n) ++logn;
     const CrMod m{p, ~0ull / p + ((~0ull % p) + 1 == p ? 1 : 0)};  // floor(2^64 / p), p >= 2
+    if (logn >= 3 && logn <= kLogBlockMax) {
+        unsigned k = 0;
+        while (k < 32 && (p >> k)) ++k;  // bit length of p
+        const bool narrow = p < (1u << 31) && (p & (p - 1)) != 0;  // mu32 fits one word
+        CrFast f{p, narrow ? (uint32_t)((uint64_t(1) << (k + 31)) / p) : 0u, k - 1, m};
+        if (!narrow)
+            launch_fast<2>(dev, logn, batch, tw_dev, f, factor, st);
+        else if ((uint64_t)p * 3 < (uint64_t(1) << 32))
+            launch_fast<0>(dev, logn, batch, tw_dev, f, factor, st);
+        else
+            launch_fast<1>(dev, logn, batch, tw_dev, f, factor, st);
+        NTT_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     const unsigned logb = std::min(logn, kLogBlockMax);
     const size_t B = size_t(1) << logb, total_blocks = batch * (n >> logb), total = batch * n;
     if (logn > logb) {
