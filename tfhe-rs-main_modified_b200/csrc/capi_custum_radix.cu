@@ -8,7 +8,7 @@
 // them: the iterative form of the reference's radix-2 recursion (identical to it for ANY table of values
 // below p, including the multiplication-free size-2 base), a batch of vectors per launch.  Vectors of 8 to
 // 2^15 elements take `cr_fast_kernel` (radix-8 register passes, the bit reversal folded into the first
-// pass, Barrett reduction on the fly because the table is the caller's); shorter and longer ones take the
+// pass, the caller's table turned into Shoup pairs once per call); shorter and longer ones take the
 // plain stage kernels below it.
 //
 // What the recursions add on top of the sum (restated in `final_factor`):
@@ -95,62 +95,79 @@ cr_block_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, un
 
 // ---- the main path: 8 <= n <= 2^15, one vector per n/8 threads, radix-8 register passes ----------------
 //
-// MODE picks the cheapest exact arithmetic for the modulus (every result is canonical, so they agree):
-//   0  3p < 2^32: one-word Barrett on the fly -- s = floor(d / 2^(k-1)), q = floor(s * mu / 2^32) with
-//      mu = floor(2^(k+31) / p) and k the bit length of p, q in [floor(d/p) - 2, floor(d/p)] for d < p^2
-//       -- remainder in one word
-//   1  p < 2^31: the same quotient, remainder in two words
-//   2  any p: the 64-bit Barrett of cr_mul, 64-bit sums
+// MODE 0 (p < 2^31): the caller's table is first turned into Shoup pairs {w, floor(w 2^32 / p)} in a
+// stream-ordered scratch array (cr_stage_table_kernel: one division per entry, once per call), after which a
+// product is IMAD.HI + two IMAD + one min in one-word arithmetic: r = o w - floor(o w' / 2^32) p lies in
+// [0, 2p) and 2p < 2^32.  MODE 2 (any p): plain entries and the 64-bit Barrett of cr_mul.  Every result
+// is canonical, so the two agree wherever both apply.
 struct CrFast {
-    uint32_t p, mu32, ks;  // ks = k - 1
-    CrMod wide;
+    uint32_t p, factor_shoup;
+    const uint2* stw;  // stage-compact table (cr_stage_table_kernel)
+    CrMod wide;        // MODE 2
 };
+template <int MODE>
+struct CrTw {
+    uint32_t w, ws;
+};
+template <int MODE>
+NTT_DEVINL CrTw<MODE> crf_ldtw(const CrFast& m, unsigned i) {
+    const uint2 v = __ldg(m.stw + i);
+    return CrTw<MODE>{v.x, v.y};
+}
 template <int MODE>
 NTT_DEVINL uint32_t crf_add(uint32_t a, uint32_t b, const CrFast& m) {
     if (MODE == 2) return cr_add(a, b, m.p);
-    uint32_t s = a + b;
-    return s >= m.p ? s - m.p : s;
+    const uint32_t s = a + b;
+    return min(s, s - m.p);
 }
 template <int MODE>
 NTT_DEVINL uint32_t crf_sub(uint32_t a, uint32_t b, const CrFast& m) {
-    return a >= b ? a - b : a + m.p - b;  // wraps to the exact value also when a + p >= 2^32
+    if (MODE == 2) return a >= b ? a - b : a + m.p - b;  // wraps to the exact value also when a + p >= 2^32
+    const uint32_t d = a - b;
+    return min(d, d + m.p);
 }
 template <int MODE>
-NTT_DEVINL uint32_t crf_mul(uint32_t a, uint32_t b, const CrFast& m) {
-    if (MODE == 2) return cr_mul(a, b, m.wide);
-    const uint64_t d = (uint64_t)a * b;
-    const uint32_t q = __umulhi((uint32_t)(d >> m.ks), m.mu32);
-    if (MODE == 0) {
-        uint32_t r = (uint32_t)d - q * m.p;
-        if (r >= m.p) r -= m.p;
-        if (r >= m.p) r -= m.p;
-        return r;
+NTT_DEVINL uint32_t crf_mul(uint32_t o, CrTw<MODE> w, const CrFast& m) {
+    if (MODE == 2) return cr_mul(o, w.w, m.wide);
+    const uint32_t r = o * w.w - __umulhi(o, w.ws) * m.p;
+    return min(r, r - m.p);
+}
+// Stage-compact copy of the caller's table: the stage of length 2h reads tw[k * n / (2h)], k < h (the
+// subsampled tables of fwd.rs:188-192), a stride of n / (2h) entries between neighbouring lanes; the copy holds
+// that stage's entries side by side at [h, 2h), so a warp's twiddle load is one or two wavefronts instead of
+// up to 32.  With `shoup` each entry carries floor(w 2^32 / p).
+__global__ void cr_stage_table_kernel(const uint32_t* __restrict__ tw, unsigned logn, uint32_t p, int shoup,
+                                      uint2* __restrict__ out) {
+    const unsigned n = 1u << logn;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i == 0) {
+            out[0] = make_uint2(0u, 0u);
+            continue;
+        }
+        const unsigned lh = 31 - __clz(i), k = i - (1u << lh);  // h = 2^lh, stage length 2^(lh+1)
+        const uint32_t w = tw[(size_t)k << (logn - lh - 1)];
+        out[i] = make_uint2(w, shoup ? (uint32_t)(((uint64_t)w << 32) / p) : 0u);
     }
-    uint64_t r = d - (uint64_t)q * m.p;
-    if (r >= m.p) r -= m.p;
-    if (r >= m.p) r -= m.p;
-    return (uint32_t)r;
 }
 
-// one word of padding after every 8: tuple accesses of stride 1, 8, 64 ... spread over the banks
-NTT_DEVINL unsigned cr_pad(unsigned a) { return a + (a >> 3); }
+// one word of padding after every 8 and one more after every 64: the tuple accesses of stride 1, 8, 64 ... and
+// the bit-reversed stores of the first pass spread over the banks
+NTT_DEVINL unsigned cr_pad(unsigned a) { return a + (a >> 3) + (a >> 6); }
 
 // Stages ll .. ll+R-1 of the reference's radix-2 recursion on the 2^R elements x[j] at positions
 // base + j * 2^(ll-1), base = group * 2^(ll-1+R) + k: in stage ll+q element j (bit q clear) pairs with
 // j + 2^q and sits at offset k + (j mod 2^q) * 2^(ll-1) of its group, which indexes the subsampled table
 // (fwd.rs:188-201).  The size-2 stage does not multiply (fwd.rs:173-178).
 template <int MODE, int R>
-NTT_DEVINL void cr_tuple(uint32_t (&x)[8], const uint32_t* __restrict__ tw, unsigned k, unsigned ll, unsigned logn,
-                         const CrFast& m) {
+NTT_DEVINL void cr_tuple(uint32_t (&x)[8], unsigned k, unsigned ll, const CrFast& m) {
 #pragma unroll
     for (int q = 0; q < R; ++q) {
-        const unsigned shift = logn - (ll + q);
 #pragma unroll
         for (int j = 0; j < (1 << R); ++j) {
             if (j & (1 << q)) continue;
             const unsigned kq = k + ((unsigned)(j & ((1 << q) - 1)) << (ll - 1));
             const uint32_t e = x[j], o = x[j + (1 << q)];
-            const uint32_t t = (ll + q == 1) ? o : crf_mul<MODE>(o, __ldg(tw + ((size_t)kq << shift)), m);
+            const uint32_t t = (ll + q == 1) ? o : crf_mul<MODE>(o, crf_ldtw<MODE>(m, (1u << (ll + q - 1)) + kq), m);
             x[j] = crf_add<MODE>(e, t, m);
             x[j + (1 << q)] = crf_sub<MODE>(e, t, m);
         }
@@ -158,8 +175,7 @@ NTT_DEVINL void cr_tuple(uint32_t (&x)[8], const uint32_t* __restrict__ tw, unsi
 }
 
 template <int MODE, int R>
-NTT_DEVINL void cr_last_pass(uint32_t* __restrict__ g, const uint32_t* s, const uint32_t* __restrict__ tw,
-                             unsigned logn, unsigned ll, unsigned vectors, unsigned pn, const CrFast& m,
+NTT_DEVINL void cr_last_pass(uint32_t* __restrict__ g, const uint32_t* s, unsigned logn, unsigned ll, unsigned vectors, unsigned pn, const CrFast& m,
                              uint32_t factor) {
     const unsigned lt = logn - R, half = 1u << lt;  // the group is the whole vector: k = tuple index
     for (unsigned t = threadIdx.x; t < (vectors << lt); t += blockDim.x) {
@@ -167,10 +183,10 @@ NTT_DEVINL void cr_last_pass(uint32_t* __restrict__ g, const uint32_t* s, const 
         uint32_t x[8];
 #pragma unroll
         for (int j = 0; j < (1 << R); ++j) x[j] = s[v * pn + cr_pad(k + ((unsigned)j << lt))];
-        cr_tuple<MODE, R>(x, tw, k, ll, logn, m);
+        cr_tuple<MODE, R>(x, k, ll, m);
 #pragma unroll
         for (int j = 0; j < (1 << R); ++j)
-            g[((size_t)v << logn) + k + ((unsigned)j << lt)] = factor != 1 ? crf_mul<MODE>(x[j], factor, m) : x[j];
+            g[((size_t)v << logn) + k + ((unsigned)j << lt)] = factor != 1 ? crf_mul<MODE>(x[j], CrTw<MODE>{factor, m.factor_shoup}, m) : x[j];
     }
 }
 
@@ -179,7 +195,7 @@ NTT_DEVINL void cr_last_pass(uint32_t* __restrict__ g, const uint32_t* s, const 
 // run three stages each in shared memory; the last pass (1-3 stages) writes global memory, coalesced.
 template <int MODE>
 __global__ void __launch_bounds__(1024)
-cr_fast_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, unsigned logn, size_t total_vectors,
+cr_fast_kernel(uint32_t* __restrict__ data, unsigned logn, size_t total_vectors,
                unsigned per_cta, CrFast m, uint32_t factor) {
     extern __shared__ uint32_t s[];
     const size_t first = (size_t)blockIdx.x * per_cta;
@@ -193,10 +209,10 @@ cr_fast_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, uns
         uint32_t x[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = src[(size_t)(((j & 1) << 2) | (j & 2) | (j >> 2)) << lt];
-        cr_tuple<MODE, 3>(x, tw, 0, 1, logn, m);
+        cr_tuple<MODE, 3>(x, 0, 1, m);
         if (lt == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[(size_t)v * 8 + j] = factor != 1 ? crf_mul<MODE>(x[j], factor, m) : x[j];
+            for (int j = 0; j < 8; ++j) g[(size_t)v * 8 + j] = factor != 1 ? crf_mul<MODE>(x[j], CrTw<MODE>{factor, m.factor_shoup}, m) : x[j];
         } else {
             const unsigned pos = __brev(tl) >> (32 - lt);
 #pragma unroll
@@ -215,37 +231,36 @@ cr_fast_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, uns
             uint32_t x[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = sv[cr_pad(base + ((unsigned)j << (ll - 1)))];
-            cr_tuple<MODE, 3>(x, tw, k, ll, logn, m);
+            cr_tuple<MODE, 3>(x, k, ll, m);
 #pragma unroll
             for (int j = 0; j < 8; ++j) sv[cr_pad(base + ((unsigned)j << (ll - 1)))] = x[j];
         }
         __syncthreads();
     }
     switch (logn - ll + 1) {
-        case 1: cr_last_pass<MODE, 1>(g, s, tw, logn, ll, vectors, pn, m, factor); break;
-        case 2: cr_last_pass<MODE, 2>(g, s, tw, logn, ll, vectors, pn, m, factor); break;
-        default: cr_last_pass<MODE, 3>(g, s, tw, logn, ll, vectors, pn, m, factor); break;
+        case 1: cr_last_pass<MODE, 1>(g, s, logn, ll, vectors, pn, m, factor); break;
+        case 2: cr_last_pass<MODE, 2>(g, s, logn, ll, vectors, pn, m, factor); break;
+        default: cr_last_pass<MODE, 3>(g, s, logn, ll, vectors, pn, m, factor); break;
     }
 }
 
 template <int MODE>
-void launch_fast(uint32_t* dev, unsigned logn, size_t batch, const uint32_t* tw_dev, const CrFast& m, uint32_t factor,
-                 cudaStream_t st) {
+void launch_fast(uint32_t* dev, unsigned logn, size_t batch, const CrFast& m, uint32_t factor, cudaStream_t st) {
     const size_t n = size_t(1) << logn, tuples = n / 8;
     // short vectors share a CTA (at least 256 tuples per CTA); long ones get up to 1024 threads
     const unsigned per_cta = (unsigned)std::max<size_t>(1, std::min<size_t>(256 / tuples, batch));
     const unsigned threads = (unsigned)std::min<size_t>(1024, std::max<size_t>(32, per_cta * tuples));
-    const size_t smem = (size_t)per_cta * (n + n / 8) * sizeof(uint32_t);
+    const size_t smem = (size_t)per_cta * (n + n / 8 + n / 64) * sizeof(uint32_t);
     static bool opted[64] = {};
     int device = 0;
     NTT_CUDA_CHECK(cudaGetDevice(&device));
     if (smem > 48 * 1024 && !opted[device & 63]) {
         NTT_CUDA_CHECK(cudaFuncSetAttribute(cr_fast_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(((size_t(1) << kLogBlockMax) * 9 / 8) * sizeof(uint32_t))));
+                                            (int)(((size_t(1) << kLogBlockMax) * 73 / 64) * sizeof(uint32_t))));
         opted[device & 63] = true;
     }
     const size_t ctas = (batch + per_cta - 1) / per_cta;
-    cr_fast_kernel<MODE><<<(unsigned)ctas, threads, smem, st>>>(dev, tw_dev, logn, batch, per_cta, m, factor);
+    cr_fast_kernel<MODE><<<(unsigned)ctas, threads, smem, st>>>(dev, logn, batch, per_cta, m, factor);
 }
 
 // in-place bit reversal of each vector (n > 2^kLogBlockMax)
@@ -325,16 +340,23 @@ void enqueue(uint32_t* dev, size_t n, size_t batch, const uint32_t* tw_dev, uint
     while ((size_t(1) << logn) < n) ++logn;
     const CrMod m{p, ~0ull / p + ((~0ull % p) + 1 == p ? 1 : 0)};  // floor(2^64 / p), p >= 2
     if (logn >= 3 && logn <= kLogBlockMax) {
-        unsigned k = 0;
-        while (k < 32 && (p >> k)) ++k;  // bit length of p
-        const bool narrow = p < (1u << 31) && (p & (p - 1)) != 0;  // mu32 fits one word
-        CrFast f{p, narrow ? (uint32_t)((uint64_t(1) << (k + 31)) / p) : 0u, k - 1, m};
-        if (!narrow)
-            launch_fast<2>(dev, logn, batch, tw_dev, f, factor, st);
-        else if ((uint64_t)p * 3 < (uint64_t(1) << 32))
-            launch_fast<0>(dev, logn, batch, tw_dev, f, factor, st);
-        else
-            launch_fast<1>(dev, logn, batch, tw_dev, f, factor, st);
+        CrFast f{p, 0u, nullptr, m};
+        const bool shoup = p < (1u << 31);
+        uint2* stw = nullptr;
+        int device = 0;
+        NTT_CUDA_CHECK(cudaGetDevice(&device));
+        keep_pool_cached(device);  // the scratch table comes from and returns to the cached pool
+        NTT_CUDA_CHECK(cudaMallocAsync(&stw, n * sizeof(uint2), st));
+        cr_stage_table_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148), 256, 0, st>>>(tw_dev, logn, p, shoup ? 1 : 0,
+                                                                                             stw);
+        f.stw = stw;
+        if (shoup) {
+            f.factor_shoup = (uint32_t)(((uint64_t)factor << 32) / p);
+            launch_fast<0>(dev, logn, batch, f, factor, st);
+        } else {
+            launch_fast<2>(dev, logn, batch, f, factor, st);
+        }
+        cudaFreeAsync(stw, st);
         NTT_CUDA_CHECK(cudaGetLastError());
         return;
     }
