@@ -110,11 +110,6 @@ struct CrTw {
     uint32_t w, ws;
 };
 template <int MODE>
-NTT_DEVINL CrTw<MODE> crf_ldtw(const CrFast& m, unsigned i) {
-    const uint2 v = __ldg(m.stw + i);
-    return CrTw<MODE>{v.x, v.y};
-}
-template <int MODE>
 NTT_DEVINL uint32_t crf_add(uint32_t a, uint32_t b, const CrFast& m) {
     if (MODE == 2) return cr_add(a, b, m.p);
     const uint32_t s = a + b;
@@ -158,109 +153,135 @@ NTT_DEVINL unsigned cr_pad(unsigned a) { return a + (a >> 3) + (a >> 6); }
 // base + j * 2^(ll-1), base = group * 2^(ll-1+R) + k: in stage ll+q element j (bit q clear) pairs with
 // j + 2^q and sits at offset k + (j mod 2^q) * 2^(ll-1) of its group, which indexes the subsampled table
 // (fwd.rs:188-201).  The size-2 stage does not multiply (fwd.rs:173-178).
-template <int MODE, int R>
-NTT_DEVINL void cr_tuple(uint32_t (&x)[8], unsigned k, unsigned ll, const CrFast& m) {
+template <int MODE, int R, int LL>
+NTT_DEVINL void cr_tuple(uint32_t (&x)[8], unsigned k, const CrFast& m) {
 #pragma unroll
     for (int q = 0; q < R; ++q) {
+        const uint2* __restrict__ stage = m.stw + (1u << (LL + q - 1)) + k;
 #pragma unroll
         for (int j = 0; j < (1 << R); ++j) {
             if (j & (1 << q)) continue;
-            const unsigned kq = k + ((unsigned)(j & ((1 << q) - 1)) << (ll - 1));
             const uint32_t e = x[j], o = x[j + (1 << q)];
-            const uint32_t t = (ll + q == 1) ? o : crf_mul<MODE>(o, crf_ldtw<MODE>(m, (1u << (ll + q - 1)) + kq), m);
+            uint32_t t = o;
+            if (LL + q != 1) {
+                const uint2 w = __ldg(stage + ((j & ((1 << q) - 1)) << (LL - 1)));  // immediate offset
+                t = crf_mul<MODE>(o, CrTw<MODE>{w.x, w.y}, m);
+            }
             x[j] = crf_add<MODE>(e, t, m);
             x[j + (1 << q)] = crf_sub<MODE>(e, t, m);
         }
     }
 }
 
-template <int MODE, int R>
-NTT_DEVINL void cr_last_pass(uint32_t* __restrict__ g, const uint32_t* s, unsigned logn, unsigned ll, unsigned vectors, unsigned pn, const CrFast& m,
-                             uint32_t factor) {
-    const unsigned lt = logn - R, half = 1u << lt;  // the group is the whole vector: k = tuple index
-    for (unsigned t = threadIdx.x; t < (vectors << lt); t += blockDim.x) {
-        const unsigned v = t >> lt, k = t & (half - 1);
-        uint32_t x[8];
+// Every pass works at half = 2^(LL-1) in {8, 64, 512, 4096}: the padding of base + j * half is then the
+// padding of base plus j times a constant, so a tuple's accesses use immediate offsets.
+template <int LL>
+struct CrStride {
+    static constexpr unsigned kHalf = 1u << (LL - 1);
+    static constexpr unsigned kPadded = kHalf + (kHalf >> 3) + (kHalf >> 6);
+};
+
+// stages LL .. LOGN: three per pass through shared memory, the last 1-3 out to global memory (coalesced)
+template <int MODE, int LOGN, int LL>
+NTT_DEVINL void cr_passes(uint32_t* __restrict__ g, uint32_t* s, unsigned vectors, const CrFast& m, uint32_t factor) {
+    constexpr int REM = LOGN - LL + 1;
+    constexpr unsigned PN = (1u << LOGN) + (1u << LOGN >> 3) + (1u << LOGN >> 6);
+    constexpr unsigned STEP = CrStride<LL>::kPadded, HALF = CrStride<LL>::kHalf;
+    if constexpr (REM > 3) {
+        constexpr unsigned LT = LOGN - 3;
+        for (unsigned t = threadIdx.x; t < (vectors << LT); t += blockDim.x) {
+            const unsigned v = t >> LT, tl = t & ((1u << LT) - 1);
+            const unsigned k = tl & (HALF - 1), base = ((tl >> (LL - 1)) << (LL + 2)) + k;
+            uint32_t* sv = s + v * PN + cr_pad(base);
+            uint32_t x[8];
 #pragma unroll
-        for (int j = 0; j < (1 << R); ++j) x[j] = s[v * pn + cr_pad(k + ((unsigned)j << lt))];
-        cr_tuple<MODE, R>(x, k, ll, m);
+            for (int j = 0; j < 8; ++j) x[j] = sv[j * STEP];
+            cr_tuple<MODE, 3, LL>(x, k, m);
 #pragma unroll
-        for (int j = 0; j < (1 << R); ++j)
-            g[((size_t)v << logn) + k + ((unsigned)j << lt)] = factor != 1 ? crf_mul<MODE>(x[j], CrTw<MODE>{factor, m.factor_shoup}, m) : x[j];
+            for (int j = 0; j < 8; ++j) sv[j * STEP] = x[j];
+        }
+        __syncthreads();
+        cr_passes<MODE, LOGN, LL + 3>(g, s, vectors, m, factor);
+    } else {
+        constexpr unsigned LT = LOGN - REM;  // the group is the whole vector: k = tuple index, HALF = 2^LT
+        for (unsigned t = threadIdx.x; t < (vectors << LT); t += blockDim.x) {
+            const unsigned v = t >> LT, k = t & (HALF - 1);
+            const uint32_t* sv = s + v * PN + cr_pad(k);
+            uint32_t x[8];
+#pragma unroll
+            for (int j = 0; j < (1 << REM); ++j) x[j] = sv[j * STEP];
+            cr_tuple<MODE, REM, LL>(x, k, m);
+            uint32_t* out = g + ((size_t)v << LOGN) + k;
+#pragma unroll
+            for (int j = 0; j < (1 << REM); ++j)
+                out[j * HALF] = factor != 1 ? crf_mul<MODE>(x[j], CrTw<MODE>{factor, m.factor_shoup}, m) : x[j];
+        }
     }
 }
 
 // The first pass reads the vector in place of the bit reversal: thread tl takes a[tl + brev3(j) * n/8], which
-// are the elements 8 * brev(tl) + j of the reversed order, runs stages 1-3 and parks them there; middle passes
-// run three stages each in shared memory; the last pass (1-3 stages) writes global memory, coalesced.
-template <int MODE>
-__global__ void __launch_bounds__(1024)
-cr_fast_kernel(uint32_t* __restrict__ data, unsigned logn, size_t total_vectors,
-               unsigned per_cta, CrFast m, uint32_t factor) {
+// are the elements 8 * brev(tl) + j of the reversed order, runs stages 1-3 and parks them there.
+template <int MODE, int LOGN>
+__global__ void __launch_bounds__(LOGN >= 13 ? 1024 : (LOGN >= 11 ? (1 << (LOGN - 3)) : 256))
+cr_fast_kernel(uint32_t* __restrict__ data, size_t total_vectors, unsigned per_cta, CrFast m, uint32_t factor) {
     extern __shared__ uint32_t s[];
+    constexpr unsigned LT = LOGN - 3, PN = (1u << LOGN) + (1u << LOGN >> 3) + (1u << LOGN >> 6);
     const size_t first = (size_t)blockIdx.x * per_cta;
     const unsigned vectors = (unsigned)min((size_t)per_cta, total_vectors - first);
-    uint32_t* g = data + (first << logn);
-    const unsigned lt = logn - 3, tmask = (1u << lt) - 1, pn = cr_pad(1u << logn);
-    const unsigned tuples = vectors << lt;
-    for (unsigned t = threadIdx.x; t < tuples; t += blockDim.x) {
-        const unsigned v = t >> lt, tl = t & tmask;
-        const uint32_t* src = g + ((size_t)v << logn) + tl;
+    uint32_t* g = data + (first << LOGN);
+    for (unsigned t = threadIdx.x; t < (vectors << LT); t += blockDim.x) {
+        const unsigned v = t >> LT, tl = t & ((1u << LT) - 1);
+        const uint32_t* src = g + ((size_t)v << LOGN) + tl;
         uint32_t x[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = src[(size_t)(((j & 1) << 2) | (j & 2) | (j >> 2)) << lt];
-        cr_tuple<MODE, 3>(x, 0, 1, m);
-        if (lt == 0) {
+        for (int j = 0; j < 8; ++j) x[j] = src[(size_t)(((j & 1) << 2) | (j & 2) | (j >> 2)) << LT];
+        cr_tuple<MODE, 3, 1>(x, 0, m);
+        if constexpr (LT == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[(size_t)v * 8 + j] = factor != 1 ? crf_mul<MODE>(x[j], CrTw<MODE>{factor, m.factor_shoup}, m) : x[j];
+            for (int j = 0; j < 8; ++j)
+                g[(size_t)v * 8 + j] = factor != 1 ? crf_mul<MODE>(x[j], CrTw<MODE>{factor, m.factor_shoup}, m) : x[j];
         } else {
-            const unsigned pos = __brev(tl) >> (32 - lt);
+            uint32_t* sv = s + v * PN + cr_pad(8 * (__brev(tl) >> (32 - LT)));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s[v * pn + cr_pad(8 * pos + j)] = x[j];
+            for (int j = 0; j < 8; ++j) sv[j] = x[j];
         }
     }
-    if (lt == 0) return;
-    __syncthreads();
-    unsigned ll = 4;
-    for (; logn - ll + 1 > 3; ll += 3) {
-        const unsigned half = 1u << (ll - 1);
-        for (unsigned t = threadIdx.x; t < tuples; t += blockDim.x) {
-            const unsigned v = t >> lt, tl = t & tmask;
-            const unsigned k = tl & (half - 1), base = ((tl >> (ll - 1)) << (ll + 2)) + k;
-            uint32_t* sv = s + v * pn;
-            uint32_t x[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = sv[cr_pad(base + ((unsigned)j << (ll - 1)))];
-            cr_tuple<MODE, 3>(x, k, ll, m);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sv[cr_pad(base + ((unsigned)j << (ll - 1)))] = x[j];
-        }
+    if constexpr (LT > 0) {
         __syncthreads();
+        cr_passes<MODE, LOGN, 4>(g, s, vectors, m, factor);
     }
-    switch (logn - ll + 1) {
-        case 1: cr_last_pass<MODE, 1>(g, s, logn, ll, vectors, pn, m, factor); break;
-        case 2: cr_last_pass<MODE, 2>(g, s, logn, ll, vectors, pn, m, factor); break;
-        default: cr_last_pass<MODE, 3>(g, s, logn, ll, vectors, pn, m, factor); break;
+}
+
+template <int MODE, int LOGN>
+void launch_fast_n(uint32_t* dev, size_t batch, const CrFast& m, uint32_t factor, cudaStream_t st) {
+    constexpr size_t n = size_t(1) << LOGN, tuples = n / 8;
+    // short vectors share a CTA (256 tuples per CTA); long ones get up to 1024 threads
+    const unsigned per_cta = (unsigned)std::max<size_t>(1, std::min<size_t>(256 / tuples, batch));
+    const unsigned threads = (unsigned)std::min<size_t>(1024, std::max<size_t>(32, per_cta * tuples));
+    const size_t smem = (size_t)per_cta * (n + n / 8 + n / 64) * sizeof(uint32_t);
+    if (smem > 48 * 1024) {
+        static bool opted[64] = {};
+        int device = 0;
+        NTT_CUDA_CHECK(cudaGetDevice(&device));
+        if (!opted[device & 63]) {
+            NTT_CUDA_CHECK(cudaFuncSetAttribute(cr_fast_kernel<MODE, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+            opted[device & 63] = true;
+        }
     }
+    const size_t ctas = (batch + per_cta - 1) / per_cta;
+    cr_fast_kernel<MODE, LOGN><<<(unsigned)ctas, threads, smem, st>>>(dev, batch, per_cta, m, factor);
 }
 
 template <int MODE>
 void launch_fast(uint32_t* dev, unsigned logn, size_t batch, const CrFast& m, uint32_t factor, cudaStream_t st) {
-    const size_t n = size_t(1) << logn, tuples = n / 8;
-    // short vectors share a CTA (at least 256 tuples per CTA); long ones get up to 1024 threads
-    const unsigned per_cta = (unsigned)std::max<size_t>(1, std::min<size_t>(256 / tuples, batch));
-    const unsigned threads = (unsigned)std::min<size_t>(1024, std::max<size_t>(32, per_cta * tuples));
-    const size_t smem = (size_t)per_cta * (n + n / 8 + n / 64) * sizeof(uint32_t);
-    static bool opted[64] = {};
-    int device = 0;
-    NTT_CUDA_CHECK(cudaGetDevice(&device));
-    if (smem > 48 * 1024 && !opted[device & 63]) {
-        NTT_CUDA_CHECK(cudaFuncSetAttribute(cr_fast_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(((size_t(1) << kLogBlockMax) * 73 / 64) * sizeof(uint32_t))));
-        opted[device & 63] = true;
+    switch (logn) {
+#define CR_CASE(L) case L: launch_fast_n<MODE, L>(dev, batch, m, factor, st); break;
+        CR_CASE(3) CR_CASE(4) CR_CASE(5) CR_CASE(6) CR_CASE(7) CR_CASE(8) CR_CASE(9) CR_CASE(10) CR_CASE(11)
+        CR_CASE(12) CR_CASE(13) CR_CASE(14) CR_CASE(15)
+#undef CR_CASE
+        default: throw CudaError("custum_radix: no single-CTA kernel for this length");
     }
-    const size_t ctas = (batch + per_cta - 1) / per_cta;
-    cr_fast_kernel<MODE><<<(unsigned)ctas, threads, smem, st>>>(dev, logn, batch, per_cta, m, factor);
 }
 
 // in-place bit reversal of each vector (n > 2^kLogBlockMax)
