@@ -385,4 +385,46 @@ inline void programmable_bootstrap_ntt64_bnf_lwe_ciphertext(const std::vector<ui
 }
 }  // namespace ntt64_pbs
 
+// custum_radix (tfhe-ntt/src/custum_radix/mod.rs:1-22): the fork's recursive cyclic u32 transforms over a
+// caller-built table twiddles[k] = root^k mod p, natural order in and out.  The forward `_mut` routines of
+// fwd_1.rs (values + MultStats counters of the CPU recursion) are not mirrored: the counters are not produced.
+namespace custum_radix {
+inline void fft_radix2_recursive(std::vector<uint32_t>& a, const std::vector<uint32_t>& twiddles, uint32_t p) {  // fwd.rs:170
+    check(ntt_b200_custum_radix_fft(NTT_B200_CR_RADIX2, a.data(), a.size(), twiddles.data(), twiddles.size(), p),
+          "fft_radix2_recursive");
+}
+inline void fft_radix4_recursive(std::vector<uint32_t>& a, const std::vector<uint32_t>& twiddles, uint32_t p) {  // fwd.rs:105
+    check(ntt_b200_custum_radix_fft(NTT_B200_CR_RADIX4, a.data(), a.size(), twiddles.data(), twiddles.size(), p),
+          "fft_radix4_recursive");
+}
+inline void fft_split_radix_recursive(std::vector<uint32_t>& a, const std::vector<uint32_t>& tw, uint32_t p) {  // fwd.rs:207
+    check(ntt_b200_custum_radix_fft(NTT_B200_CR_SPLIT_RADIX, a.data(), a.size(), tw.data(), tw.size(), p),
+          "fft_split_radix_recursive");
+}
+inline void ifft_radix2_recursive(std::vector<uint32_t>& a, const std::vector<uint32_t>& inv_twiddles, uint32_t p,
+                                  uint32_t n_inv, bool top) {  // inv.rs:178
+    check(ntt_b200_custum_radix_ifft(NTT_B200_CR_RADIX2, a.data(), a.size(), inv_twiddles.data(), inv_twiddles.size(), p,
+                                     n_inv, top),
+          "ifft_radix2_recursive");
+}
+inline void ifft_radix4_recursive(std::vector<uint32_t>& a, const std::vector<uint32_t>& inv_twiddles, uint32_t p,
+                                  uint32_t n_inv, bool top) {  // inv.rs:106 (halves when log2 n is odd)
+    check(ntt_b200_custum_radix_ifft(NTT_B200_CR_RADIX4, a.data(), a.size(), inv_twiddles.data(), inv_twiddles.size(), p,
+                                     n_inv, top),
+          "ifft_radix4_recursive");
+}
+inline void ifft_split_radix_recursive(std::vector<uint32_t>& a, const std::vector<uint32_t>& inv_tw, uint32_t p,
+                                       uint32_t n_inv, bool top) {  // inv.rs:232
+    check(ntt_b200_custum_radix_ifft(NTT_B200_CR_SPLIT_RADIX, a.data(), a.size(), inv_tw.data(), inv_tw.size(), p, n_inv,
+                                     top),
+          "ifft_split_radix_recursive");
+}
+inline void ifft_radix4_recursive_mut(std::vector<uint32_t>& a, const std::vector<uint32_t>& inv_twiddles, uint32_t p,
+                                      uint32_t n_inv, bool top) {  // fwd_1.rs:296, without the counters
+    check(ntt_b200_custum_radix_ifft(NTT_B200_CR_RADIX4_MUT, a.data(), a.size(), inv_twiddles.data(),
+                                     inv_twiddles.size(), p, n_inv, top),
+          "ifft_radix4_recursive_mut");
+}
+}  // namespace custum_radix
+
 }  // namespace tfhe_ntt
