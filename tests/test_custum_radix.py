@@ -269,3 +269,22 @@ def test_gpu_batches_host_and_device(n, batch):
         cr.ifft_device(cr.RADIX4_MUT, d, n, batch, d_inv, p, n_inv, True, stream=st)
     st.synchronize()
     assert np.array_equal(d.cpu().numpy().view(np.uint32), a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1 << 15, 1 << 16])
+def test_gpu_long_vectors_wide_prime(n):
+    """p >= 2^31 (plain table entries, 64-bit Barrett) on the largest single-CTA length and on the block + global-stage
+    path"""
+    import tfhe_ntt_b200.custum_radix as cr
+    p = 4293918721
+    rng = np.random.default_rng(n)
+    tw, inv = tables(n, p)
+    a = rng.integers(0, p, size=(3, n), dtype=np.uint64).astype(np.uint32)
+    got = a.copy()
+    cr.fft_batch(cr.RADIX2, got, tw, p)
+    assert np.array_equal(got[1], oracle_fft("radix2", a[1], tw, p))
+    n_inv = pow(n, p - 2, p)
+    want = oracle_ifft("radix4", got[2], inv, p, n_inv, True)
+    cr.ifft_batch(cr.RADIX4, got, inv, p, n_inv, True)
+    assert np.array_equal(got[2], want)

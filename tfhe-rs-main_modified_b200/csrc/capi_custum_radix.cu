@@ -8,8 +8,9 @@
 // them: the iterative form of the reference's radix-2 recursion (identical to it for ANY table of values
 // below p, including the multiplication-free size-2 base), a batch of vectors per launch.  Vectors of 8 to
 // 2^15 elements take `cr_fast_kernel` (radix-8 register passes, the bit reversal folded into the first
-// pass, the caller's table turned into Shoup pairs once per call); shorter and longer ones take the
-// plain stage kernels below it.
+// pass, the caller's table turned into stage-compact Shoup pairs once per call); longer ones are bit-reversed
+// in place, run the same kernel block by block and finish with one pass over global memory per further
+// stage; n = 1, 2, 4 take the plain stage kernel.
 //
 // What the recursions add on top of the sum (restated in `final_factor`):
 //   ifft_radix2 / ifft_split_radix (inv.rs:178-303)  n_inv when `top`, except n <= 2 (the bases return early)
@@ -27,7 +28,7 @@ using namespace nttb200;
 
 namespace {
 
-constexpr unsigned kLogBlockMax = 15;  // 2^15 u32 = 128 KiB of shared memory per CTA
+constexpr unsigned kLogBlockMax = 15;  // 2^15 u32 (+ padding) = 146 KiB of shared memory per CTA
 constexpr unsigned kThreads = 512;
 
 struct CrMod {
@@ -221,7 +222,9 @@ NTT_DEVINL void cr_passes(uint32_t* __restrict__ g, uint32_t* s, unsigned vector
 
 // The first pass reads the vector in place of the bit reversal: thread tl takes a[tl + brev3(j) * n/8], which
 // are the elements 8 * brev(tl) + j of the reversed order, runs stages 1-3 and parks them there.
-template <int MODE, int LOGN>
+// PRE: the "vector" is a 2^LOGN block of a longer vector that cr_bitrev_kernel already permuted, so the tuple
+// at position tl is read where it lies.
+template <int MODE, int LOGN, bool PRE>
 __global__ void __launch_bounds__(LOGN >= 13 ? 1024 : (LOGN >= 11 ? (1 << (LOGN - 3)) : 256))
 cr_fast_kernel(uint32_t* __restrict__ data, size_t total_vectors, unsigned per_cta, CrFast m, uint32_t factor) {
     extern __shared__ uint32_t s[];
@@ -231,17 +234,17 @@ cr_fast_kernel(uint32_t* __restrict__ data, size_t total_vectors, unsigned per_c
     uint32_t* g = data + (first << LOGN);
     for (unsigned t = threadIdx.x; t < (vectors << LT); t += blockDim.x) {
         const unsigned v = t >> LT, tl = t & ((1u << LT) - 1);
-        const uint32_t* src = g + ((size_t)v << LOGN) + tl;
+        const uint32_t* src = g + ((size_t)v << LOGN) + (PRE ? 8 * tl : tl);
         uint32_t x[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = src[(size_t)(((j & 1) << 2) | (j & 2) | (j >> 2)) << LT];
+        for (int j = 0; j < 8; ++j) x[j] = PRE ? src[j] : src[(size_t)(((j & 1) << 2) | (j & 2) | (j >> 2)) << LT];
         cr_tuple<MODE, 3, 1>(x, 0, m);
         if constexpr (LT == 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 g[(size_t)v * 8 + j] = factor != 1 ? crf_mul<MODE>(x[j], CrTw<MODE>{factor, m.factor_shoup}, m) : x[j];
         } else {
-            uint32_t* sv = s + v * PN + cr_pad(8 * (__brev(tl) >> (32 - LT)));
+            uint32_t* sv = s + v * PN + cr_pad(8 * (PRE ? tl : (__brev(tl) >> (32 - LT))));
 #pragma unroll
             for (int j = 0; j < 8; ++j) sv[j] = x[j];
         }
@@ -252,7 +255,7 @@ cr_fast_kernel(uint32_t* __restrict__ data, size_t total_vectors, unsigned per_c
     }
 }
 
-template <int MODE, int LOGN>
+template <int MODE, int LOGN, bool PRE = false>
 void launch_fast_n(uint32_t* dev, size_t batch, const CrFast& m, uint32_t factor, cudaStream_t st) {
     constexpr size_t n = size_t(1) << LOGN, tuples = n / 8;
     // short vectors share a CTA (256 tuples per CTA); long ones get up to 1024 threads
@@ -264,13 +267,13 @@ void launch_fast_n(uint32_t* dev, size_t batch, const CrFast& m, uint32_t factor
         int device = 0;
         NTT_CUDA_CHECK(cudaGetDevice(&device));
         if (!opted[device & 63]) {
-            NTT_CUDA_CHECK(cudaFuncSetAttribute(cr_fast_kernel<MODE, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            NTT_CUDA_CHECK(cudaFuncSetAttribute(cr_fast_kernel<MODE, LOGN, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)smem));
             opted[device & 63] = true;
         }
     }
     const size_t ctas = (batch + per_cta - 1) / per_cta;
-    cr_fast_kernel<MODE, LOGN><<<(unsigned)ctas, threads, smem, st>>>(dev, batch, per_cta, m, factor);
+    cr_fast_kernel<MODE, LOGN, PRE><<<(unsigned)ctas, threads, smem, st>>>(dev, batch, per_cta, m, factor);
 }
 
 template <int MODE>
@@ -299,22 +302,37 @@ __global__ void cr_bitrev_kernel(uint32_t* __restrict__ data, unsigned logn, siz
     }
 }
 
-// one stage of length 2^ll in global memory (ll > kLogBlockMax); the last one applies `factor`
-__global__ void cr_global_stage_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, unsigned logn,
-                                       unsigned ll, size_t total_bf, CrMod m, uint32_t factor) {
-    const unsigned half_mask = (1u << (ll - 1)) - 1, shift = logn - ll;
+// one stage of length 2^ll in global memory (ll > kLogBlockMax) over the stage-compact table; the last one
+// applies `factor`
+template <int MODE>
+__global__ void cr_global_stage_kernel(uint32_t* __restrict__ data, unsigned ll, size_t total_bf, CrFast m,
+                                       uint32_t factor) {
+    const unsigned half = 1u << (ll - 1);
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_bf; t += (size_t)gridDim.x * blockDim.x) {
-        size_t k = t & half_mask;
-        size_t i0 = ((t >> (ll - 1)) << ll) + k, i1 = i0 + half_mask + 1;
-        uint32_t e = data[i0], x = cr_mul(data[i1], __ldg(tw + (k << shift)), m);
-        uint32_t y0 = cr_add(e, x, m.p), y1 = cr_sub(e, x, m.p);
+        const unsigned k = (unsigned)t & (half - 1);
+        const size_t i0 = ((t >> (ll - 1)) << ll) + k, i1 = i0 + half;
+        const uint2 w = __ldg(m.stw + half + k);
+        const uint32_t e = data[i0], x = crf_mul<MODE>(data[i1], CrTw<MODE>{w.x, w.y}, m);
+        uint32_t y0 = crf_add<MODE>(e, x, m), y1 = crf_sub<MODE>(e, x, m);
         if (factor != 1) {
-            y0 = cr_mul(y0, factor, m);
-            y1 = cr_mul(y1, factor, m);
+            y0 = crf_mul<MODE>(y0, CrTw<MODE>{factor, m.factor_shoup}, m);
+            y1 = crf_mul<MODE>(y1, CrTw<MODE>{factor, m.factor_shoup}, m);
         }
         data[i0] = y0;
         data[i1] = y1;
     }
+}
+
+// vectors longer than 2^15: bit reversal in place, the stages up to 2^15 block by block in the single-CTA
+// kernel, one pass over global memory for every further stage
+template <int MODE>
+void launch_long(uint32_t* dev, unsigned logn, size_t batch, const CrFast& m, uint32_t factor, cudaStream_t st) {
+    const size_t total = batch << logn;
+    cr_bitrev_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, size_t(148) * 32), 256, 0, st>>>(dev, logn, total);
+    launch_fast_n<MODE, kLogBlockMax, true>(dev, batch << (logn - kLogBlockMax), m, 1u, st);
+    for (unsigned ll = kLogBlockMax + 1; ll <= logn; ++ll)
+        cr_global_stage_kernel<MODE><<<(unsigned)std::min<size_t>((total / 2 + 255) / 256, size_t(148) * 32), 256, 0, st>>>(
+            dev, ll, total / 2, m, ll == logn ? factor : 1u);
 }
 
 // host restatement of fwd.rs:22-39
@@ -360,52 +378,44 @@ void enqueue(uint32_t* dev, size_t n, size_t batch, const uint32_t* tw_dev, uint
     unsigned logn = 0;
     while ((size_t(1) << logn) < n) ++logn;
     const CrMod m{p, ~0ull / p + ((~0ull % p) + 1 == p ? 1 : 0)};  // floor(2^64 / p), p >= 2
-    if (logn >= 3 && logn <= kLogBlockMax) {
-        CrFast f{p, 0u, nullptr, m};
-        const bool shoup = p < (1u << 31);
-        uint2* stw = nullptr;
+    if (logn >= 3) {
+        struct Scratch {  // stream-ordered, released on every exit path
+            cudaStream_t st;
+            uint2* ptr = nullptr;
+            ~Scratch() {
+                if (ptr) cudaFreeAsync(ptr, st);
+            }
+        } table{st};
         int device = 0;
         NTT_CUDA_CHECK(cudaGetDevice(&device));
         keep_pool_cached(device);  // the scratch table comes from and returns to the cached pool
-        NTT_CUDA_CHECK(cudaMallocAsync(&stw, n * sizeof(uint2), st));
+        NTT_CUDA_CHECK(cudaMallocAsync(&table.ptr, n * sizeof(uint2), st));
+        const bool shoup = p < (1u << 31);
         cr_stage_table_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148), 256, 0, st>>>(tw_dev, logn, p, shoup ? 1 : 0,
-                                                                                             stw);
-        f.stw = stw;
-        if (shoup) {
-            f.factor_shoup = (uint32_t)(((uint64_t)factor << 32) / p);
-            launch_fast<0>(dev, logn, batch, f, factor, st);
+                                                                                             table.ptr);
+        const CrFast f{p, shoup ? (uint32_t)(((uint64_t)factor << 32) / p) : 0u, table.ptr, m};
+        if (logn <= kLogBlockMax) {
+            if (shoup)
+                launch_fast<0>(dev, logn, batch, f, factor, st);
+            else
+                launch_fast<2>(dev, logn, batch, f, factor, st);
         } else {
-            launch_fast<2>(dev, logn, batch, f, factor, st);
+            if (shoup)
+                launch_long<0>(dev, logn, batch, f, factor, st);
+            else
+                launch_long<2>(dev, logn, batch, f, factor, st);
         }
-        cudaFreeAsync(stw, st);
         NTT_CUDA_CHECK(cudaGetLastError());
         return;
     }
-    const unsigned logb = std::min(logn, kLogBlockMax);
-    const size_t B = size_t(1) << logb, total_blocks = batch * (n >> logb), total = batch * n;
-    if (logn > logb) {
-        size_t grid = std::min<size_t>((total + 255) / 256, size_t(148) * 32);
-        cr_bitrev_kernel<<<(unsigned)grid, 256, 0, st>>>(dev, logn, total);
-    }
-    // several short vectors per CTA so that a CTA has at least kThreads butterflies per stage
-    unsigned per_cta = (unsigned)std::max<size_t>(1, std::min<size_t>((2 * kThreads) / B, total_blocks));
+    // n = 1, 2, 4: a few vectors per CTA in the plain stage kernel
+    const unsigned logb = logn;
+    const size_t B = size_t(1) << logb, total_blocks = batch;
+    const unsigned per_cta = (unsigned)std::max<size_t>(1, std::min<size_t>((2 * kThreads) / B, total_blocks));
     const size_t smem = (size_t)per_cta * B * sizeof(uint32_t);
-    static bool opted[64] = {};
-    int device = 0;
-    NTT_CUDA_CHECK(cudaGetDevice(&device));
-    if (smem > 48 * 1024 && !opted[device & 63]) {
-        NTT_CUDA_CHECK(cudaFuncSetAttribute(cr_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)((size_t(1) << kLogBlockMax) * sizeof(uint32_t))));
-        opted[device & 63] = true;
-    }
     const size_t ctas = (total_blocks + per_cta - 1) / per_cta;
     const unsigned threads = (unsigned)std::min<size_t>(kThreads, std::max<size_t>(32, per_cta * B / 2));
-    cr_block_kernel<<<(unsigned)ctas, threads, smem, st>>>(dev, tw_dev, logn, logb, total_blocks, per_cta, m,
-                                                           logn == logb ? factor : 1u);
-    for (unsigned ll = logb + 1; ll <= logn; ++ll) {
-        size_t bf = total / 2, grid = std::min<size_t>((bf + 255) / 256, size_t(148) * 32);
-        cr_global_stage_kernel<<<(unsigned)grid, 256, 0, st>>>(dev, tw_dev, logn, ll, bf, m, ll == logn ? factor : 1u);
-    }
+    cr_block_kernel<<<(unsigned)ctas, threads, smem, st>>>(dev, tw_dev, logn, logb, total_blocks, per_cta, m, factor);
     NTT_CUDA_CHECK(cudaGetLastError());
 }
 
