@@ -10,7 +10,7 @@
 // 2^15 elements take `cr_fast_kernel` (radix-8 register passes, the bit reversal folded into the first
 // pass, the caller's table turned into stage-compact Shoup pairs once per call); longer ones are bit-reversed
 // in place, run the same kernel block by block and finish with one pass over global memory per further
-// stage; n = 1, 2, 4 take the plain stage kernel.
+// stage; n = 1, 2, 4 are done by one thread per vector.
 //
 // What the recursions add on top of the sum (restated in `final_factor`):
 //   ifft_radix2 / ifft_split_radix (inv.rs:178-303)  n_inv when `top`, except n <= 2 (the bases return early)
@@ -29,7 +29,6 @@ using namespace nttb200;
 namespace {
 
 constexpr unsigned kLogBlockMax = 15;  // 2^15 u32 (+ padding) = 146 KiB of shared memory per CTA
-constexpr unsigned kThreads = 512;
 
 struct CrMod {
     uint32_t p;
@@ -53,44 +52,28 @@ NTT_DEVINL uint32_t cr_mul(uint32_t a, uint32_t b, const CrMod& m) {
     return (uint32_t)r;
 }
 
-// One CTA owns `per_cta` blocks of 2^logb consecutive elements (a whole vector when logb == logn) and runs
-// the stages of length 2 .. 2^logb on them in shared memory.  logb == logn: the load applies the bit
-// reversal; longer vectors were permuted by cr_bitrev_kernel.  Stage `len` multiplies by
-// tw[k * (n / len)] -- the chain of subsampled tables of fwd.rs:188-192 -- and the size-2 stage does not
-// multiply (fwd.rs:173-178).  `factor` != 1 scales the outputs (only when logb == logn).
-__global__ void __launch_bounds__(kThreads)
-cr_block_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, unsigned logn, unsigned logb,
-                size_t total_blocks, unsigned per_cta, CrMod m, uint32_t factor) {
-    extern __shared__ uint32_t s[];
-    const unsigned B = 1u << logb;
-    const size_t first = (size_t)blockIdx.x * per_cta;
-    const unsigned here = (unsigned)min((size_t)per_cta, total_blocks - first);
-    uint32_t* base = data + first * B;
-    const unsigned elems = here * B;
-    const bool whole = logb == logn;
-    for (unsigned i = threadIdx.x; i < elems; i += blockDim.x) {
-        unsigned blk = i >> logb, j = i & (B - 1);
-        unsigned dst = whole ? (logb ? (__brev(j) >> (32 - logb)) : 0u) : j;
-        s[(blk << logb) + dst] = base[i];
-    }
-    __syncthreads();
-    const unsigned bf = elems >> 1;
-    for (unsigned ll = 1; ll <= logb; ++ll) {
-        const unsigned half = 1u << (ll - 1);
-        const unsigned shift = logn - ll;  // table stride n / len
-        for (unsigned t = threadIdx.x; t < bf; t += blockDim.x) {
-            unsigned k = t & (half - 1);
-            unsigned i0 = ((t >> (ll - 1)) << ll) + k, i1 = i0 + half;
-            uint32_t e = s[i0], o = s[i1];
-            uint32_t x = ll == 1 ? o : cr_mul(o, __ldg(tw + ((size_t)k << shift)), m);
-            s[i0] = cr_add(e, x, m.p);
-            s[i1] = cr_sub(e, x, m.p);
+// n = 1, 2, 4: one thread per vector, in registers.  n = 4 is the size-2 bases on (a0, a2) and (a1, a3) followed by
+// the combine with tw[0] and tw[1] (fwd.rs:170-205); the size-2 base does not multiply (fwd.rs:173-178).
+__global__ void cr_tiny_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, unsigned logn, size_t batch,
+                               CrMod m, uint32_t factor) {
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < batch; v += (size_t)gridDim.x * blockDim.x) {
+        uint32_t* a = data + (v << logn);
+        uint32_t x[4] = {a[0], 0u, 0u, 0u};
+        for (unsigned i = 1; i < (1u << logn); ++i) x[i] = a[i];
+        if (logn == 1) {
+            const uint32_t e = x[0], o = x[1];
+            x[0] = cr_add(e, o, m.p);
+            x[1] = cr_sub(e, o, m.p);
+        } else if (logn == 2) {
+            const uint32_t e0 = cr_add(x[0], x[2], m.p), e1 = cr_sub(x[0], x[2], m.p);
+            const uint32_t o0 = cr_add(x[1], x[3], m.p), o1 = cr_sub(x[1], x[3], m.p);
+            const uint32_t t0 = cr_mul(o0, __ldg(tw), m), t1 = cr_mul(o1, __ldg(tw + 1), m);
+            x[0] = cr_add(e0, t0, m.p);
+            x[1] = cr_add(e1, t1, m.p);
+            x[2] = cr_sub(e0, t0, m.p);
+            x[3] = cr_sub(e1, t1, m.p);
         }
-        __syncthreads();
-    }
-    for (unsigned i = threadIdx.x; i < elems; i += blockDim.x) {
-        uint32_t v = s[i];
-        base[i] = factor != 1 ? cr_mul(v, factor, m) : v;
+        for (unsigned i = 0; i < (1u << logn); ++i) a[i] = factor != 1 ? cr_mul(x[i], factor, m) : x[i];
     }
 }
 
@@ -408,14 +391,9 @@ void enqueue(uint32_t* dev, size_t n, size_t batch, const uint32_t* tw_dev, uint
         NTT_CUDA_CHECK(cudaGetLastError());
         return;
     }
-    // n = 1, 2, 4: a few vectors per CTA in the plain stage kernel
-    const unsigned logb = logn;
-    const size_t B = size_t(1) << logb, total_blocks = batch;
-    const unsigned per_cta = (unsigned)std::max<size_t>(1, std::min<size_t>((2 * kThreads) / B, total_blocks));
-    const size_t smem = (size_t)per_cta * B * sizeof(uint32_t);
-    const size_t ctas = (total_blocks + per_cta - 1) / per_cta;
-    const unsigned threads = (unsigned)std::min<size_t>(kThreads, std::max<size_t>(32, per_cta * B / 2));
-    cr_block_kernel<<<(unsigned)ctas, threads, smem, st>>>(dev, tw_dev, logn, logb, total_blocks, per_cta, m, factor);
+    // n = 1, 2, 4
+    cr_tiny_kernel<<<(unsigned)std::min<size_t>((batch + 255) / 256, size_t(148) * 8), 256, 0, st>>>(dev, tw_dev, logn, batch,
+                                                                                                 m, factor);
     NTT_CUDA_CHECK(cudaGetLastError());
 }
 
