@@ -288,3 +288,39 @@ def test_gpu_long_vectors_wide_prime(n):
     want = oracle_ifft("radix4", got[2], inv, p, n_inv, True)
     cr.ifft_batch(cr.RADIX4, got, inv, p, n_inv, True)
     assert np.array_equal(got[2], want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [256, 2048, 1 << 16])
+def test_gpu_device_calls_are_cuda_graph_capturable(n):
+    """the device entry points only enqueue stream-ordered work (the scratch table is a stream-ordered allocation), so a
+    forward + inverse pair can be captured once in a CUDA graph and replayed"""
+    import torch
+    import tfhe_ntt_b200.custum_radix as cr
+    p = 2013265921
+    rng = np.random.default_rng(n + 11)
+    tw, inv = tables(n, p)
+    batch = 5
+    a = rng.integers(0, p, size=(batch, n), dtype=np.uint64).astype(np.uint32)
+    d = torch.from_numpy(a.view(np.int32)).cuda()
+    d_tw = torch.from_numpy(tw.view(np.int32)).cuda()
+    d_inv = torch.from_numpy(inv.view(np.int32)).cuda()
+    snap = torch.empty_like(d)
+    n_inv = pow(n, p - 2, p)
+    warm = torch.cuda.Stream()
+    with torch.cuda.stream(warm):  # first use outside capture (shared-memory attributes are set once)
+        cr.fft_device(cr.RADIX2, d, n, batch, d_tw, p, stream=warm)
+        cr.ifft_device(cr.RADIX2, d, n, batch, d_inv, p, n_inv, True, stream=warm)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy().view(np.uint32), a)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        st = torch.cuda.current_stream()
+        cr.fft_device(cr.SPLIT_RADIX, d, n, batch, d_tw, p, stream=st)
+        snap.copy_(d)
+        cr.ifft_device(cr.SPLIT_RADIX, d, n, batch, d_inv, p, n_inv, True, stream=st)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(snap.cpu().numpy().view(np.uint32)[2], oracle_fft("split_radix", a[2], tw, p))
+    assert np.array_equal(d.cpu().numpy().view(np.uint32), a)
