@@ -462,3 +462,30 @@ def convert_standard_bsk(plan, standard, input_width=0, normalize=False):
     plan.lib.tfo_convert_standard_lwe_bootstrap_key_to_ntt64(plan.h, _ptr(standard), _ptr(out), standard.size // plan.n,
                                                              input_width, int(normalize))
     return out
+
+
+# ---- custum_radix (oracle/tfhe_ntt_custum_radix_oracle.c) ------------------------------------------
+
+def cr_tables(n, p):
+    """make_twiddles / make_inv_twiddles of custum_radix/fwd.rs:72-103"""
+    L = lib()
+    L.tfo_cr_make_twiddles.argtypes = [C.c_size_t, C.c_uint32, C.c_void_p]
+    L.tfo_cr_make_twiddles.restype = C.c_int
+    L.tfo_cr_make_inv_twiddles.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+    L.tfo_cr_make_inv_twiddles.restype = None
+    tw = np.zeros(n, dtype=np.uint32)
+    if not L.tfo_cr_make_twiddles(n, p, tw.ctypes.data):
+        raise ValueError("n must be a power of two dividing p - 1")
+    inv = np.zeros_like(tw)
+    L.tfo_cr_make_inv_twiddles(tw.ctypes.data, n, p, inv.ctypes.data)
+    return tw, inv
+
+
+def cr_fft(kind, a, tw, p):
+    """fft_{radix2,radix4,split_radix}_recursive on a copy"""
+    L = lib()
+    fn = getattr(L, "tfo_cr_fft_%s_recursive" % kind)
+    fn.argtypes, fn.restype = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32], None
+    out = np.ascontiguousarray(a, dtype=np.uint32).copy()
+    fn(out.ctypes.data, out.size, tw.ctypes.data, p)
+    return out
