@@ -158,6 +158,28 @@ def test_oracle_mult_stats():
     assert (st.nonzero_mults, st.skipped_mults) == (0, 32 * 5)
 
 
+def golden_cases():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "custum_radix_golden.json")) as f:
+        return json.load(f)["cases"]
+
+
+def test_oracle_reproduces_the_golden_fixture():
+    """tests/golden/custum_radix_golden.json is computed from the definition alone (make_custum_radix_golden.py)"""
+    for c in golden_cases():
+        n, p = c["n"], c["p"]
+        tw, inv = tables(n, p)
+        assert int(tw[1]) == c["root"], c["name"]
+        a = np.array(c["input"], dtype=np.uint32)
+        for kind in ("radix2", "radix4", "split_radix"):
+            assert [int(x) for x in oracle_fft(kind, a, tw, p)] == c["fft"], (c["name"], kind)
+        n_inv = pow(n, p - 2, p)
+        assert [int(x) for x in oracle_ifft("radix2", a, inv, p, n_inv, True)] == c["ifft_radix2_top"], c["name"]
+        assert [int(x) for x in oracle_ifft("split_radix", a, inv, p, n_inv, True)] == c["ifft_radix2_top"], c["name"]
+        assert [int(x) for x in oracle_ifft("radix4", a, inv, p, n_inv, True)] == c["ifft_radix4_top"], c["name"]
+
+
 def test_rejections_need_no_gpu():
     """bad shapes are refused before any CUDA call (the reference overflows its stack / panics on an index)"""
     import tfhe_ntt_b200.custum_radix as cr
@@ -324,3 +346,22 @@ def test_gpu_device_calls_are_cuda_graph_capturable(n):
     torch.cuda.synchronize()
     assert np.array_equal(snap.cpu().numpy().view(np.uint32)[2], oracle_fft("split_radix", a[2], tw, p))
     assert np.array_equal(d.cpu().numpy().view(np.uint32), a)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_the_golden_fixture():
+    import tfhe_ntt_b200.custum_radix as cr
+    for c in golden_cases():
+        n, p = c["n"], c["p"]
+        tw = cr.make_twiddles(n, p)
+        inv = cr.make_inv_twiddles(tw, p)
+        n_inv = pow(n, p - 2, p)
+        for fn in (cr.fft_radix2_recursive, cr.fft_radix4_recursive, cr.fft_split_radix_recursive):
+            a = np.array(c["input"], dtype=np.uint32)
+            fn(a, tw, p)
+            assert [int(x) for x in a] == c["fft"], (c["name"], fn.__name__)
+        for fn, key in ((cr.ifft_radix2_recursive, "ifft_radix2_top"), (cr.ifft_split_radix_recursive, "ifft_radix2_top"),
+                        (cr.ifft_radix4_recursive, "ifft_radix4_top")):
+            a = np.array(c["input"], dtype=np.uint32)
+            fn(a, inv, p, n_inv, True)
+            assert [int(x) for x in a] == c[key], (c["name"], fn.__name__)
