@@ -45,6 +45,28 @@ int main() {
     nat->negacyclic_polymul(prod.data(), 64, l.data(), 64, r.data(), 64);
     for (auto v : prod)
         if (v != 15) return 7;
+    // custum_radix: the sequence of the fork's test (custum_radix/fwd_1.rs:433-463), here with the inverse table
+    // so that it is a round trip: n = 8, p = 17, root = 3^2 = 9 of order 8, tw[k] = 9^k, inv[k] = tw[k]^-1
+    {
+        const uint32_t q = 17;
+        std::vector<uint32_t> tw{1, 9, 13, 15, 16, 8, 4, 2}, inv{1, 2, 4, 8, 16, 15, 13, 9};
+        std::vector<uint32_t> v{5, 11, 3, 12, 8, 13, 2, 14}, w = v, u;
+        custum_radix::fft_split_radix_recursive(w, tw, q);
+        u = v;
+        custum_radix::fft_radix4_recursive(u, tw, q);
+        if (u != w) return 8;  // one function on a power table
+        uint32_t sum = 0;
+        for (auto x : v) sum = (sum + x) % q;
+        if (w[0] != sum) return 9;  // X[0] = sum of the inputs
+        custum_radix::ifft_radix2_recursive(w, inv, q, 15 /* 8^-1 mod 17 */, true);
+        if (w != v) return 10;
+        std::vector<uint32_t> bad(6);
+        try {
+            custum_radix::fft_radix2_recursive(bad, tw, q);
+            return 11;
+        } catch (const std::logic_error&) {
+        }
+    }
     std::puts("cpp example ok");
     return 0;
 }
