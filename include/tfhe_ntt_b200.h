@@ -399,8 +399,7 @@ int ntt_b200_largest_prime_in_arithmetic_progression64(uint64_t factor, uint64_t
  * table the three forward routines are one function, the inverse routines differ by the constant
  * their bases apply (see csrc/capi_custum_radix.cu).  n must be a power of two (1 allowed) and the
  * table at least n long (the reference indexes it modulo n): NTT_B200_ERR_LEN otherwise, where the
- * reference overflows its stack or panics on an index.  The MultStats counters of fwd_1.rs are not
- * produced (a statistic of the CPU recursion).
+ * reference overflows its stack or panics on an index.
  * ------------------------------------------------------------------------------------------ */
 #define NTT_B200_CR_RADIX2 0      /* fft_radix2_recursive fwd.rs:170-205 (= fwd_1.rs:190-230), ifft inv.rs:178-230 */
 #define NTT_B200_CR_RADIX4 1      /* fft_radix4_recursive fwd.rs:105-168 (= fwd_1.rs:102-188), ifft inv.rs:106-176 */
@@ -413,6 +412,16 @@ int ntt_b200_custum_radix_fft(int kind, uint32_t *a, size_t n, const uint32_t *t
 /* ifft_*_recursive(a, inv_twiddles, p, n_inv, top) */
 int ntt_b200_custum_radix_ifft(int kind, uint32_t *a, size_t n, const uint32_t *inv_twiddles,
                                size_t tw_len, uint32_t p, uint32_t n_inv, int top);
+/* fft_{radix2,radix4,split_radix}_recursive_mut(a, twiddles, p, stats: &mut MultStats)   fwd_1.rs:102-294
+ * and ifft_radix4_recursive_mut(a, inv_twiddles, p, n_inv, top, stats)                  fwd_1.rs:296-379:
+ * the values of the routines above plus the fork's multiplication counters, ADDED onto stats[0]
+ * (MultStats::nonzero_mults) and stats[1] (skipped_mults), fwd_1.rs:3-7, :28-37.  One vector per call,
+ * n <= 4096 (all levels of the transform are kept in shared memory); NTT_B200_ERR_LEN above that. */
+int ntt_b200_custum_radix_fft_mut(int kind, uint32_t *a, size_t n, const uint32_t *twiddles,
+                                  size_t tw_len, uint32_t p, uint64_t *stats);
+int ntt_b200_custum_radix_ifft_radix4_mut(uint32_t *a, size_t n, const uint32_t *inv_twiddles,
+                                          size_t tw_len, uint32_t p, uint32_t n_inv, int top,
+                                          uint64_t *stats);
 /* NEW: `batch` contiguous vectors in host memory */
 int ntt_b200_custum_radix_fft_batch(int kind, uint32_t *host, size_t n, size_t batch,
                                     const uint32_t *twiddles, size_t tw_len, uint32_t p);

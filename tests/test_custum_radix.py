@@ -365,3 +365,57 @@ def test_gpu_reproduces_the_golden_fixture():
             a = np.array(c["input"], dtype=np.uint32)
             fn(a, inv, p, n_inv, True)
             assert [int(x) for x in a] == c[key], (c["name"], fn.__name__)
+
+
+def oracle_stats(kind, a, tw, p, n_inv=0, top=False):
+    st, out = MultStats(), a.copy()
+    if kind == "ifft_radix4":
+        L.tfo_cr_ifft_radix4_recursive_mut(ptr(out), out.size, ptr(tw), p, n_inv, int(top), C.byref(st))
+    else:
+        getattr(L, "tfo_cr_fft_%s_recursive_mut" % kind)(ptr(out), out.size, ptr(tw), p, C.byref(st))
+    return out, (st.nonzero_mults, st.skipped_mults)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p", [65537, 2013265921, 4293918721])
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 64, 128, 512, 2048, 4096])
+def test_gpu_mult_stats_match_the_oracle(n, p):
+    """the MultStats counters of fwd_1.rs (values too), on dense, sparse and structured inputs"""
+    import tfhe_ntt_b200.custum_radix as cr
+    rng = np.random.default_rng(n * 3 + p % 11)
+    tw, inv = tables(n, p)
+    dense = rng.integers(1, p, size=n, dtype=np.uint64).astype(np.uint32)
+    sparse = dense.copy()
+    sparse[rng.random(n) < 0.7] = 0
+    const = np.full(n, 7, dtype=np.uint32)          # transform has a single non-zero: many zero operands inside
+    delta = np.zeros(n, dtype=np.uint32)
+    delta[n // 3] = 5
+    inputs = [dense, sparse, const, delta, np.zeros(n, dtype=np.uint32)]
+    if n == 64 and p == 65537:
+        inputs.append(np.array(REFERENCE_TEST_INPUT, dtype=np.uint32))
+    n_inv = pow(n, p - 2, p)
+    for a in inputs:
+        for kind, fn in (("radix2", cr.fft_radix2_recursive_mut), ("radix4", cr.fft_radix4_recursive_mut),
+                         ("split_radix", cr.fft_split_radix_recursive_mut)):
+            want, counts = oracle_stats(kind, a, tw, p)
+            st, got = cr.MultStats(), a.copy()
+            st.nonzero_mults, st.skipped_mults = 10, 20  # the counters accumulate like `&mut MultStats`
+            fn(got, tw, p, st)
+            assert np.array_equal(got, want), kind
+            assert (st.nonzero_mults - 10, st.skipped_mults - 20) == counts, (kind, n, counts)
+        for top in (False, True):
+            want, counts = oracle_stats("ifft_radix4", a, inv, p, n_inv, top)
+            st, got = cr.MultStats(), a.copy()
+            cr.ifft_radix4_recursive_mut(got, inv, p, n_inv, top, st)
+            assert np.array_equal(got, want), top
+            assert (st.nonzero_mults, st.skipped_mults) == counts, ("ifft_radix4", n, top, counts)
+
+
+def test_mult_stats_rejections_need_no_gpu():
+    import tfhe_ntt_b200.custum_radix as cr
+    st = cr.MultStats()
+    with pytest.raises(AssertionError):  # the counting kernel keeps every level in shared memory: n <= 4096
+        cr.fft_radix2_recursive_mut(np.zeros(8192, dtype=np.uint32), np.ones(8192, dtype=np.uint32), 17, st)
+    with pytest.raises(AssertionError):
+        cr.fft_split_radix_recursive_mut(np.zeros(12, dtype=np.uint32), np.ones(16, dtype=np.uint32), 17, st)
+    assert (st.nonzero_mults, st.skipped_mults) == (0, 0)

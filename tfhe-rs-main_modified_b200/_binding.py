@@ -110,6 +110,8 @@ SIGNATURES = {
     "ntt_b200_product_inv_device": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
     "ntt_b200_custum_radix_fft": (_i, [_i, _vp, _sz, _vp, _sz, _u32]),
     "ntt_b200_custum_radix_ifft": (_i, [_i, _vp, _sz, _vp, _sz, _u32, _u32, _i]),
+    "ntt_b200_custum_radix_fft_mut": (_i, [_i, _vp, _sz, _vp, _sz, _u32, C.POINTER(_u64)]),
+    "ntt_b200_custum_radix_ifft_radix4_mut": (_i, [_vp, _sz, _vp, _sz, _u32, _u32, _i, C.POINTER(_u64)]),
     "ntt_b200_custum_radix_fft_batch": (_i, [_i, _vp, _sz, _sz, _vp, _sz, _u32]),
     "ntt_b200_custum_radix_ifft_batch": (_i, [_i, _vp, _sz, _sz, _vp, _sz, _u32, _u32, _i]),
     "ntt_b200_custum_radix_fft_device": (_i, [_i, _vp, _sz, _sz, _vp, _sz, _u32, _vp]),

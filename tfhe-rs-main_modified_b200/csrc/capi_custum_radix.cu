@@ -318,6 +318,117 @@ void launch_long(uint32_t* dev, unsigned logn, size_t batch, const CrFast& m, ui
             dev, ll, total / 2, m, ll == logn ? factor : 1u);
 }
 
+// ---- fwd_1.rs: the `_mut` routines with their MultStats counters ------------------------------------------
+//
+// Every counted product of the three forward recursions (and of ifft_radix4_recursive_mut) has operands that
+// are sub-transforms of the input: S_m^(r)[k], the size-m transform of a[r], a[r + n/m], ... -- exactly what the
+// radix-2 schedule holds after its stage of length m (block brev(r)).  One CTA per vector keeps ALL levels in
+// shared memory (level l at lv + l * n; n <= 4096), then counts per routine:
+//   radix-2 (fwd_1.rs:190-230)      every butterfly above the size-2 base: (tw, odd); the base counts a[1] != 0
+//   split-radix (:232-294)          nodes reached by tokens {0, 10, 11} of the residue; per k < m/4:
+//                                   (w^k, A1), (w^3k, A2), (J, w^k A1 - w^3k A2), A1 / A2 = the 1 / 3 mod 4 children
+//   radix-4 (:102-188)              nodes at even depth; size-4 base: (tw[1], x1 - x3); above it per k < m/4:
+//                                   (w^k, A1), (w^2k, A2), (w^3k, A3), (w^(m/4), w^k A1 - w^3k A3)
+//   inverse radix-4 (:296-379)      nodes at even depth, m >= 4; per i < m/4 and output e = i + s m/4:
+//                                   (w^e, A1), (w^2e, A2), (w^3e, A3)
+// A product counts as `nonzero` when both operands are non-zero, else as `skipped` (fwd_1.rs:28-37).
+constexpr unsigned kStatsLogMax = 12;
+#define NTT_B200_CR_STATS_IFFT_RADIX4 3
+
+struct CrCount {
+    unsigned long long nz = 0, sk = 0;
+    NTT_DEVINL void add(uint32_t x, uint32_t y) {
+        if (x != 0 && y != 0)
+            ++nz;
+        else
+            ++sk;
+    }
+};
+
+__global__ void __launch_bounds__(256)
+cr_stats_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, unsigned logn, int kind, CrMod m,
+                uint32_t factor, unsigned long long* __restrict__ stats) {
+    extern __shared__ uint32_t lv[];
+    __shared__ unsigned long long tot[2];
+    const unsigned n = 1u << logn;
+    uint32_t* a = data + ((size_t)blockIdx.x << logn);
+    if (threadIdx.x < 2) tot[threadIdx.x] = 0;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) lv[logn ? (__brev(i) >> (32 - logn)) : 0u] = a[i];
+    __syncthreads();
+    for (unsigned l = 1; l <= logn; ++l) {  // level l from level l - 1 (fwd.rs:170-205)
+        const uint32_t *src = lv + (size_t)(l - 1) * n;
+        uint32_t* dst = lv + (size_t)l * n;
+        const unsigned half = 1u << (l - 1);
+        for (unsigned t = threadIdx.x; t < n / 2; t += blockDim.x) {
+            const unsigned k = t & (half - 1), i0 = ((t >> (l - 1)) << l) + k, i1 = i0 + half;
+            const uint32_t e = src[i0], o = src[i1];
+            const uint32_t x = l == 1 ? o : cr_mul(o, __ldg(tw + ((size_t)k << (logn - l))), m);
+            dst[i0] = cr_add(e, x, m.p);
+            dst[i1] = cr_sub(e, x, m.p);
+        }
+        __syncthreads();
+    }
+    CrCount c;
+    auto T = [&](unsigned l, unsigned i) { return __ldg(tw + ((size_t)(i & ((1u << l) - 1)) << (logn - l))); };  // T_m[i % m]
+    if (kind == NTT_B200_CR_RADIX2) {
+        for (unsigned t = threadIdx.x; t < n / 2; t += blockDim.x) c.nz += lv[2 * t + 1] != 0;
+        for (unsigned l = 2; l <= logn; ++l) {
+            const uint32_t* src = lv + (size_t)(l - 1) * n;
+            const unsigned half = 1u << (l - 1);
+            for (unsigned t = threadIdx.x; t < n / 2; t += blockDim.x) {
+                const unsigned k = t & (half - 1);
+                c.add(T(l, k), src[((t >> (l - 1)) << l) + k + half]);
+            }
+        }
+    } else {
+        for (unsigned l = 2; l <= logn; ++l) {
+            const unsigned L = logn - l, q = 1u << (l - 2);
+            if (kind != NTT_B200_CR_SPLIT_RADIX && (L & 1)) continue;  // radix-4 nodes sit at even depth
+            const uint32_t* sub = lv + (size_t)(l - 2) * n;
+            for (unsigned t = threadIdx.x; t < n / 4; t += blockDim.x) {  // (node b, k)
+                const unsigned b = t >> (l - 2), k = t & (q - 1);
+                if (kind == NTT_B200_CR_SPLIT_RADIX) {
+                    const unsigned r = L ? (__brev(b) >> (32 - L)) : 0u;
+                    unsigned pos = 0;
+                    while (pos < L) pos += ((r >> pos) & 1u) ? 2 : 1;
+                    if (pos != L) continue;  // not a node of the split-radix recursion
+                }
+                const uint32_t* node = sub + ((size_t)b << l);
+                const uint32_t a1 = node[2 * q + k], a2 = node[q + k], a3 = node[3 * q + k];  // classes 1, 2, 3 mod 4
+                if (kind == NTT_B200_CR_SPLIT_RADIX) {
+                    const uint32_t wk = T(l, k), w3 = T(l, 3 * k);
+                    c.add(wk, a1);
+                    c.add(w3, a3);
+                    c.add(T(l, q), cr_sub(cr_mul(a1, wk, m), cr_mul(a3, w3, m), m.p));
+                } else if (kind == NTT_B200_CR_RADIX4) {
+                    if (l == 2) {  // the size-4 base works on the inputs: x1 - x3
+                        c.add(T(2, 1), cr_sub(lv[4 * b + 2], lv[4 * b + 3], m.p));
+                    } else {
+                        const uint32_t w1 = T(l, k), w3 = T(l, 3 * k);
+                        c.add(w1, a1);
+                        c.add(T(l, 2 * k), a2);
+                        c.add(w3, a3);
+                        c.add(T(l, q), cr_sub(cr_mul(w1, a1, m), cr_mul(w3, a3, m), m.p));
+                    }
+                } else {
+                    for (unsigned s4 = 0; s4 < 4; ++s4) {
+                        const unsigned e = k + s4 * q;
+                        c.add(T(l, e), a1);
+                        c.add(T(l, 2 * e), a2);
+                        c.add(T(l, 3 * e), a3);
+                    }
+                }
+            }
+        }
+    }
+    atomicAdd(&tot[0], c.nz);
+    atomicAdd(&tot[1], c.sk);
+    const uint32_t* res = lv + (size_t)logn * n;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) a[i] = factor != 1 ? cr_mul(res[i], factor, m) : res[i];
+    __syncthreads();
+    if (threadIdx.x < 2) stats[2 * blockIdx.x + threadIdx.x] = tot[threadIdx.x];
+}
+
 // host restatement of fwd.rs:22-39
 uint32_t mulmod_h(uint32_t a, uint32_t b, uint32_t p) { return (uint32_t)(((uint64_t)a * b) % p); }
 uint32_t powmod_h(uint32_t base, uint32_t exp, uint32_t p) {
@@ -452,6 +563,53 @@ int run_host(int kind, uint32_t* host, size_t n, size_t batch, const uint32_t* t
     });
 }
 
+// the `_mut` routines: one vector, values and counters (added onto stats[0] = nonzero, stats[1] = skipped)
+int run_stats(int kind, uint32_t* host, size_t n, const uint32_t* tw, size_t tw_len, uint32_t p, uint32_t factor,
+              uint64_t* stats) {
+    if (kind < 0 || kind > NTT_B200_CR_STATS_IFFT_RADIX4 || p < 2 || !stats) return NTT_B200_ERR_ARG;
+    if (n == 0 || (n & (n - 1)) || n > (size_t(1) << kStatsLogMax) || (n > 2 && tw_len < n)) return NTT_B200_ERR_LEN;
+    if (!host || (n > 2 && !tw)) return NTT_B200_ERR_ARG;
+    return guarded([&] {
+        int device = 0;
+        NTT_CUDA_CHECK(cudaGetDevice(&device));
+        keep_pool_cached(device);
+        cudaStream_t st = cached_stream(device);
+        unsigned logn = 0;
+        while ((size_t(1) << logn) < n) ++logn;
+        struct Scratch {
+            cudaStream_t st;
+            void* ptr = nullptr;
+            ~Scratch() {
+                if (ptr) cudaFreeAsync(ptr, st);
+            }
+        } buf{st};
+        const size_t words = 2 * n + 4;  // vector, table, two 64-bit counters
+        NTT_CUDA_CHECK(cudaMallocAsync(&buf.ptr, words * sizeof(uint32_t), st));
+        unsigned long long* d_stats = static_cast<unsigned long long*>(buf.ptr);
+        uint32_t* d = reinterpret_cast<uint32_t*>(d_stats + 2);
+        uint32_t* d_tw = d + n;
+        NTT_CUDA_CHECK(cudaMemcpyAsync(d, host, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (n > 2) NTT_CUDA_CHECK(cudaMemcpyAsync(d_tw, tw, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        const size_t smem = (size_t)(logn + 1) * n * sizeof(uint32_t);
+        static bool opted[64] = {};
+        if (smem > 48 * 1024 && !opted[device & 63]) {
+            NTT_CUDA_CHECK(cudaFuncSetAttribute(cr_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)((kStatsLogMax + 1) * (sizeof(uint32_t) << kStatsLogMax))));
+            opted[device & 63] = true;
+        }
+        const CrMod m{p, ~0ull / p + ((~0ull % p) + 1 == p ? 1 : 0)};
+        cr_stats_kernel<<<1, 256, smem, st>>>(d, d_tw, logn, kind, m, factor, d_stats);
+        NTT_CUDA_CHECK(cudaGetLastError());
+        unsigned long long got[2] = {0, 0};
+        NTT_CUDA_CHECK(cudaMemcpyAsync(host, d, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        NTT_CUDA_CHECK(cudaMemcpyAsync(got, d_stats, sizeof(got), cudaMemcpyDeviceToHost, st));
+        NTT_CUDA_CHECK(cudaStreamSynchronize(st));
+        stats[0] += got[0];
+        stats[1] += got[1];
+        return NTT_B200_OK;
+    });
+}
+
 }  // namespace
 
 extern "C" {
@@ -479,6 +637,17 @@ int ntt_b200_custum_radix_ifft_device(int kind, uint32_t* dev, size_t n, size_t 
                                       const uint32_t* inv_twiddles_dev, size_t tw_len, uint32_t p, uint32_t n_inv,
                                       int top, void* stream) {
     return run_device(kind, dev, n, batch, inv_twiddles_dev, tw_len, p, n_inv, true, top != 0, stream);
+}
+
+int ntt_b200_custum_radix_fft_mut(int kind, uint32_t* a, size_t n, const uint32_t* twiddles, size_t tw_len, uint32_t p,
+                                  uint64_t* stats) {
+    if (kind == NTT_B200_CR_RADIX4_MUT) return NTT_B200_ERR_ARG;
+    return run_stats(kind, a, n, twiddles, tw_len, p, 1u, stats);
+}
+int ntt_b200_custum_radix_ifft_radix4_mut(uint32_t* a, size_t n, const uint32_t* inv_twiddles, size_t tw_len, uint32_t p,
+                                          uint32_t n_inv, int top, uint64_t* stats) {
+    if (p < 2) return NTT_B200_ERR_ARG;
+    return run_stats(NTT_B200_CR_STATS_IFFT_RADIX4, a, n, inv_twiddles, tw_len, p, top ? n_inv % p : 1u, stats);
 }
 
 }  // extern "C"

@@ -4,8 +4,8 @@ fwd.rs, inv.rs, fwd_1.rs), same function names and argument order.
 `a` is a C-contiguous numpy uint32 vector transformed in place, `twiddles[k] = root^k mod p`.  On such a table
 the radix-2, radix-4 and split-radix routines are one function, so one CUDA schedule serves all of them; the
 inverse routines differ by the constant their recursion bases apply, which the library restates
-(csrc/capi_custum_radix.cu).  The forward `_mut` routines of fwd_1.rs return the same values plus MultStats
-counters of the CPU recursion; the counters are not produced, so those names are not mirrored.
+(csrc/capi_custum_radix.cu).  The `_mut` routines of fwd_1.rs return the same values plus the fork's MultStats
+counters, which a dedicated kernel reproduces from the levels of the transform (one vector per call, n <= 4096).
 """
 import numpy as np
 
@@ -60,9 +60,52 @@ def ifft_radix2_recursive_mut(a, inv_twiddles, p, n_inv, top):
     _ifft(RADIX2, a, inv_twiddles, p, n_inv, top)
 
 
-def ifft_radix4_recursive_mut(a, inv_twiddles, p, n_inv, top):
-    """fwd_1.rs:296-379 without the counters: the bases scale when `top`, nothing is halved"""
-    _ifft(RADIX4_MUT, a, inv_twiddles, p, n_inv, top)
+def ifft_radix4_recursive_mut(a, inv_twiddles, p, n_inv, top, stats=None):
+    """fwd_1.rs:296-379: the bases scale when `top`, nothing is halved; `stats` (a MultStats) receives the counters"""
+    if stats is None:
+        _ifft(RADIX4_MUT, a, inv_twiddles, p, n_inv, top)
+        return
+    import ctypes as C
+    buf = (C.c_uint64 * 2)(stats.nonzero_mults, stats.skipped_mults)
+    B.check(B.lib().ntt_b200_custum_radix_ifft_radix4_mut(B.host_ptr(a, np.uint32, True), a.size,
+                                                          B.host_ptr(inv_twiddles, np.uint32), inv_twiddles.size, p,
+                                                          n_inv, 1 if top else 0, buf), "in ifft_radix4_recursive_mut")
+    stats.nonzero_mults, stats.skipped_mults = int(buf[0]), int(buf[1])
+
+
+class MultStats:
+    """fwd_1.rs:3-7"""
+
+    def __init__(self):
+        self.nonzero_mults = 0  # nonzero * nonzero
+        self.skipped_mults = 0  # multiplications with zero
+
+    def __repr__(self):
+        return "MultStats { nonzero_mults: %d, skipped_mults: %d }" % (self.nonzero_mults, self.skipped_mults)
+
+
+def _fft_mut(kind, a, twiddles, p, stats):
+    import ctypes as C
+    buf = (C.c_uint64 * 2)(stats.nonzero_mults, stats.skipped_mults)
+    B.check(B.lib().ntt_b200_custum_radix_fft_mut(kind, B.host_ptr(a, np.uint32, True), a.size,
+                                                  B.host_ptr(twiddles, np.uint32), twiddles.size, p, buf),
+            "in custum_radix fft_mut")
+    stats.nonzero_mults, stats.skipped_mults = int(buf[0]), int(buf[1])
+
+
+def fft_radix4_recursive_mut(a, twiddles, p, stats):
+    """fwd_1.rs:102-188"""
+    _fft_mut(RADIX4, a, twiddles, p, stats)
+
+
+def fft_radix2_recursive_mut(a, twiddles, p, stats):
+    """fwd_1.rs:190-230"""
+    _fft_mut(RADIX2, a, twiddles, p, stats)
+
+
+def fft_split_radix_recursive_mut(a, twiddles, p, stats):
+    """fwd_1.rs:232-294"""
+    _fft_mut(SPLIT_RADIX, a, twiddles, p, stats)
 
 
 # ---- new: batched and device-resident forms -------------------------------------------------
