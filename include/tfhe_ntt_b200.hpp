@@ -386,8 +386,8 @@ inline void programmable_bootstrap_ntt64_bnf_lwe_ciphertext(const std::vector<ui
 }  // namespace ntt64_pbs
 
 // custum_radix (tfhe-ntt/src/custum_radix/mod.rs:1-22): the fork's recursive cyclic u32 transforms over a
-// caller-built table twiddles[k] = root^k mod p, natural order in and out.  The forward `_mut` routines of
-// fwd_1.rs (values + MultStats counters of the CPU recursion) are not mirrored: the counters are not produced.
+// caller-built table twiddles[k] = root^k mod p, natural order in and out; the `_mut` routines of fwd_1.rs also
+// return the fork's MultStats counters.
 namespace custum_radix {
 inline void fft_radix2_recursive(std::vector<uint32_t>& a, const std::vector<uint32_t>& twiddles, uint32_t p) {  // fwd.rs:170
     check(ntt_b200_custum_radix_fft(NTT_B200_CR_RADIX2, a.data(), a.size(), twiddles.data(), twiddles.size(), p),
@@ -419,11 +419,39 @@ inline void ifft_split_radix_recursive(std::vector<uint32_t>& a, const std::vect
                                      top),
           "ifft_split_radix_recursive");
 }
+// fwd_1.rs:3-7
+struct MultStats {
+    size_t nonzero_mults = 0;  // nonzero * nonzero
+    size_t skipped_mults = 0;  // multiplications with zero
+};
+namespace detail {
+inline void fft_mut(int kind, std::vector<uint32_t>& a, const std::vector<uint32_t>& tw, uint32_t p, MultStats& st,
+                    const char* what) {
+    uint64_t raw[2] = {st.nonzero_mults, st.skipped_mults};
+    check(ntt_b200_custum_radix_fft_mut(kind, a.data(), a.size(), tw.data(), tw.size(), p, raw), what);
+    st.nonzero_mults = (size_t)raw[0];
+    st.skipped_mults = (size_t)raw[1];
+}
+}  // namespace detail
+// fwd_1.rs:102 / :190 / :232 -- values and counters (one vector per call, n <= 4096)
+inline void fft_radix4_recursive_mut(std::vector<uint32_t>& a, const std::vector<uint32_t>& tw, uint32_t p, MultStats& st) {
+    detail::fft_mut(NTT_B200_CR_RADIX4, a, tw, p, st, "fft_radix4_recursive_mut");
+}
+inline void fft_radix2_recursive_mut(std::vector<uint32_t>& a, const std::vector<uint32_t>& tw, uint32_t p, MultStats& st) {
+    detail::fft_mut(NTT_B200_CR_RADIX2, a, tw, p, st, "fft_radix2_recursive_mut");
+}
+inline void fft_split_radix_recursive_mut(std::vector<uint32_t>& a, const std::vector<uint32_t>& tw, uint32_t p,
+                                          MultStats& st) {
+    detail::fft_mut(NTT_B200_CR_SPLIT_RADIX, a, tw, p, st, "fft_split_radix_recursive_mut");
+}
 inline void ifft_radix4_recursive_mut(std::vector<uint32_t>& a, const std::vector<uint32_t>& inv_twiddles, uint32_t p,
-                                      uint32_t n_inv, bool top) {  // fwd_1.rs:296, without the counters
-    check(ntt_b200_custum_radix_ifft(NTT_B200_CR_RADIX4_MUT, a.data(), a.size(), inv_twiddles.data(),
-                                     inv_twiddles.size(), p, n_inv, top),
+                                      uint32_t n_inv, bool top, MultStats& st) {  // fwd_1.rs:296
+    uint64_t raw[2] = {st.nonzero_mults, st.skipped_mults};
+    check(ntt_b200_custum_radix_ifft_radix4_mut(a.data(), a.size(), inv_twiddles.data(), inv_twiddles.size(), p, n_inv,
+                                                top, raw),
           "ifft_radix4_recursive_mut");
+    st.nonzero_mults = (size_t)raw[0];
+    st.skipped_mults = (size_t)raw[1];
 }
 }  // namespace custum_radix
 

@@ -102,6 +102,8 @@ extern "C" {
     // custum_radix (tfhe-ntt/src/custum_radix/mod.rs:1-22)
     pub fn ntt_b200_custum_radix_fft(kind: c_int, a: *mut u32, n: usize, twiddles: *const u32, tw_len: usize, p: u32) -> c_int;
     pub fn ntt_b200_custum_radix_ifft(kind: c_int, a: *mut u32, n: usize, inv_twiddles: *const u32, tw_len: usize, p: u32, n_inv: u32, top: c_int) -> c_int;
+    pub fn ntt_b200_custum_radix_fft_mut(kind: c_int, a: *mut u32, n: usize, twiddles: *const u32, tw_len: usize, p: u32, stats: *mut u64) -> c_int;
+    pub fn ntt_b200_custum_radix_ifft_radix4_mut(a: *mut u32, n: usize, inv_twiddles: *const u32, tw_len: usize, p: u32, n_inv: u32, top: c_int, stats: *mut u64) -> c_int;
     pub fn ntt_b200_custum_radix_fft_batch(kind: c_int, host: *mut u32, n: usize, batch: usize, twiddles: *const u32, tw_len: usize, p: u32) -> c_int;
     pub fn ntt_b200_custum_radix_ifft_batch(kind: c_int, host: *mut u32, n: usize, batch: usize, inv_twiddles: *const u32, tw_len: usize, p: u32, n_inv: u32, top: c_int) -> c_int;
     pub fn ntt_b200_custum_radix_fft_device(kind: c_int, dev: *mut u32, n: usize, batch: usize, twiddles_dev: *const u32, tw_len: usize, p: u32, stream: *mut c_void) -> c_int;

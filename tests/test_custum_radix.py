@@ -2,7 +2,8 @@
 
 CPU half: the oracle's literal recursions against an arbitrary-precision restatement of the definition and
 against each other, on the input of the reference's only test (fwd_1.rs:433-463, which prints and asserts
-nothing) and on random vectors.  GPU half: the CUDA path through the C ABI, bit for bit against the oracle.
+nothing) and on random vectors.  GPU half: the CUDA path through the C ABI, bit for bit against the oracle,
+values and MultStats counters.
 """
 import ctypes as C
 

@@ -19,7 +19,7 @@ Module, type and method names follow the reference:
                                    blind_rotate_ntt64[_bnf]_assign,
                                    programmable_bootstrap_ntt64[_bnf]_lwe_ciphertext
     custum_radix                   the fork's recursive cyclic u32 transforms: fft_/ifft_{radix2,radix4,split_radix}_recursive,
-                                   ifft_radix{2,4}_recursive_mut (+ fft_batch / ifft_batch / *_device)
+                                   fft_*_recursive_mut / ifft_radix{2,4}_recursive_mut with MultStats (+ fft_batch / ifft_batch / *_device)
 
 Host calls take numpy arrays and work in place exactly like the reference's `&mut [T]` slices.
 New, alongside: `*_batch` (host arrays holding many polynomials) and `*_device` (device pointers

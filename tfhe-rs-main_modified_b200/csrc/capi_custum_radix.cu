@@ -17,8 +17,8 @@
 //   ifft_radix4                    (inv.rs:106-176)  the size-2 base halves: 1/2 when log2 n is odd; n_inv
 //                                                    when `top` and n > 2
 //   ifft_radix4_recursive_mut      (fwd_1.rs:296-379) n_inv when `top`, every n
-// The MultStats counters of fwd_1.rs count zero operands inside each particular recursion; they are a
-// statistic of the CPU formulation and are not produced here.
+// The MultStats counters of fwd_1.rs count zero operands inside each particular recursion; `cr_stats_kernel`
+// reproduces them from the levels of the radix-2 schedule (see the section before the host code).
 #include <algorithm>
 #include <cstring>
 
