@@ -60,6 +60,13 @@ int main() {
         if (w[0] != sum) return 9;  // X[0] = sum of the inputs
         custum_radix::ifft_radix2_recursive(w, inv, q, 15 /* 8^-1 mod 17 */, true);
         if (w != v) return 10;
+        // the `_mut` routines count their products (fwd_1.rs:3-37): radix-2 on 8 non-zero inputs = 4 size-2 bases
+        // + 4 butterflies on each of the two levels above
+        custum_radix::MultStats st;
+        u = v;
+        custum_radix::fft_radix2_recursive_mut(u, tw, q, st);
+        custum_radix::fft_split_radix_recursive(w = v, tw, q);
+        if (u != w || st.nonzero_mults + st.skipped_mults != 12) return 12;
         std::vector<uint32_t> bad(6);
         try {
             custum_radix::fft_radix2_recursive(bad, tw, q);
