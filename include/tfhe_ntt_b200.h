@@ -419,6 +419,12 @@ int ntt_b200_custum_radix_ifft(int kind, uint32_t *a, size_t n, const uint32_t *
  * n <= 4096 (all levels of the transform are kept in shared memory); NTT_B200_ERR_LEN above that. */
 int ntt_b200_custum_radix_fft_mut(int kind, uint32_t *a, size_t n, const uint32_t *twiddles,
                                   size_t tw_len, uint32_t p, uint64_t *stats);
+/* NEW: the same for `batch` contiguous vectors in one launch (one CTA per vector): the counters of vector v
+ * are added onto stats[2v] and stats[2v + 1] -- the shape of the fork's dataset builder (examples/model/Dataset.rs),
+ * which runs the three routines over many inputs. */
+int ntt_b200_custum_radix_fft_mut_batch(int kind, uint32_t *host, size_t n, size_t batch,
+                                        const uint32_t *twiddles, size_t tw_len, uint32_t p,
+                                        uint64_t *stats);
 int ntt_b200_custum_radix_ifft_radix4_mut(uint32_t *a, size_t n, const uint32_t *inv_twiddles,
                                           size_t tw_len, uint32_t p, uint32_t n_inv, int top,
                                           uint64_t *stats);

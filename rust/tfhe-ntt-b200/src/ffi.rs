@@ -103,6 +103,7 @@ extern "C" {
     pub fn ntt_b200_custum_radix_fft(kind: c_int, a: *mut u32, n: usize, twiddles: *const u32, tw_len: usize, p: u32) -> c_int;
     pub fn ntt_b200_custum_radix_ifft(kind: c_int, a: *mut u32, n: usize, inv_twiddles: *const u32, tw_len: usize, p: u32, n_inv: u32, top: c_int) -> c_int;
     pub fn ntt_b200_custum_radix_fft_mut(kind: c_int, a: *mut u32, n: usize, twiddles: *const u32, tw_len: usize, p: u32, stats: *mut u64) -> c_int;
+    pub fn ntt_b200_custum_radix_fft_mut_batch(kind: c_int, host: *mut u32, n: usize, batch: usize, twiddles: *const u32, tw_len: usize, p: u32, stats: *mut u64) -> c_int;
     pub fn ntt_b200_custum_radix_ifft_radix4_mut(a: *mut u32, n: usize, inv_twiddles: *const u32, tw_len: usize, p: u32, n_inv: u32, top: c_int, stats: *mut u64) -> c_int;
     pub fn ntt_b200_custum_radix_fft_batch(kind: c_int, host: *mut u32, n: usize, batch: usize, twiddles: *const u32, tw_len: usize, p: u32) -> c_int;
     pub fn ntt_b200_custum_radix_ifft_batch(kind: c_int, host: *mut u32, n: usize, batch: usize, inv_twiddles: *const u32, tw_len: usize, p: u32, n_inv: u32, top: c_int) -> c_int;

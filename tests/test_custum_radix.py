@@ -420,3 +420,23 @@ def test_mult_stats_rejections_need_no_gpu():
     with pytest.raises(AssertionError):
         cr.fft_split_radix_recursive_mut(np.zeros(12, dtype=np.uint32), np.ones(16, dtype=np.uint32), 17, st)
     assert (st.nonzero_mults, st.skipped_mults) == (0, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,batch", [(64, 300), (1024, 41), (4096, 9)])
+def test_gpu_mult_stats_batch(n, batch):
+    """one launch for many vectors: values and per-vector counters against the oracle"""
+    import tfhe_ntt_b200.custum_radix as cr
+    p = 2013265921
+    rng = np.random.default_rng(batch)
+    tw, _ = tables(n, p)
+    a = rng.integers(0, p, size=(batch, n), dtype=np.uint64).astype(np.uint32)
+    a[rng.random((batch, n)) < 0.5] = 0
+    a[batch // 2] = 0
+    for kind_id, kind in ((cr.RADIX2, "radix2"), (cr.RADIX4, "radix4"), (cr.SPLIT_RADIX, "split_radix")):
+        got = a.copy()
+        stats = cr.fft_mut_batch(kind_id, got, tw, p)
+        for r in sorted({0, 1, batch // 2, batch - 1}):
+            want, counts = oracle_stats(kind, a[r], tw, p)
+            assert np.array_equal(got[r], want), (kind, r)
+            assert (int(stats[r, 0]), int(stats[r, 1])) == counts, (kind, r)

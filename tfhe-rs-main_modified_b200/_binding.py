@@ -111,6 +111,7 @@ SIGNATURES = {
     "ntt_b200_custum_radix_fft": (_i, [_i, _vp, _sz, _vp, _sz, _u32]),
     "ntt_b200_custum_radix_ifft": (_i, [_i, _vp, _sz, _vp, _sz, _u32, _u32, _i]),
     "ntt_b200_custum_radix_fft_mut": (_i, [_i, _vp, _sz, _vp, _sz, _u32, C.POINTER(_u64)]),
+    "ntt_b200_custum_radix_fft_mut_batch": (_i, [_i, _vp, _sz, _sz, _vp, _sz, _u32, _vp]),
     "ntt_b200_custum_radix_ifft_radix4_mut": (_i, [_vp, _sz, _vp, _sz, _u32, _u32, _i, C.POINTER(_u64)]),
     "ntt_b200_custum_radix_fft_batch": (_i, [_i, _vp, _sz, _sz, _vp, _sz, _u32]),
     "ntt_b200_custum_radix_ifft_batch": (_i, [_i, _vp, _sz, _sz, _vp, _sz, _u32, _u32, _i]),

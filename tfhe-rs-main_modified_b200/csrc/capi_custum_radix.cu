@@ -21,6 +21,7 @@
 // reproduces them from the levels of the radix-2 schedule (see the section before the host code).
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "capi_common.cuh"
 
@@ -563,12 +564,14 @@ int run_host(int kind, uint32_t* host, size_t n, size_t batch, const uint32_t* t
     });
 }
 
-// the `_mut` routines: one vector, values and counters (added onto stats[0] = nonzero, stats[1] = skipped)
-int run_stats(int kind, uint32_t* host, size_t n, const uint32_t* tw, size_t tw_len, uint32_t p, uint32_t factor,
-              uint64_t* stats) {
-    if (kind < 0 || kind > NTT_B200_CR_STATS_IFFT_RADIX4 || p < 2 || !stats) return NTT_B200_ERR_ARG;
+// the `_mut` routines: values and counters of `batch` vectors, one CTA each; the counters of vector v are ADDED onto
+// stats[2v] (nonzero) and stats[2v + 1] (skipped)
+int run_stats(int kind, uint32_t* host, size_t n, size_t batch, const uint32_t* tw, size_t tw_len, uint32_t p,
+              uint32_t factor, uint64_t* stats) {
+    if (kind < 0 || kind > NTT_B200_CR_STATS_IFFT_RADIX4 || p < 2 || (batch && !stats)) return NTT_B200_ERR_ARG;
     if (n == 0 || (n & (n - 1)) || n > (size_t(1) << kStatsLogMax) || (n > 2 && tw_len < n)) return NTT_B200_ERR_LEN;
-    if (!host || (n > 2 && !tw)) return NTT_B200_ERR_ARG;
+    if (batch && (!host || (n > 2 && !tw))) return NTT_B200_ERR_ARG;
+    if (!batch) return NTT_B200_OK;
     return guarded([&] {
         int device = 0;
         NTT_CUDA_CHECK(cudaGetDevice(&device));
@@ -583,13 +586,6 @@ int run_stats(int kind, uint32_t* host, size_t n, const uint32_t* tw, size_t tw_
                 if (ptr) cudaFreeAsync(ptr, st);
             }
         } buf{st};
-        const size_t words = 2 * n + 4;  // vector, table, two 64-bit counters
-        NTT_CUDA_CHECK(cudaMallocAsync(&buf.ptr, words * sizeof(uint32_t), st));
-        unsigned long long* d_stats = static_cast<unsigned long long*>(buf.ptr);
-        uint32_t* d = reinterpret_cast<uint32_t*>(d_stats + 2);
-        uint32_t* d_tw = d + n;
-        NTT_CUDA_CHECK(cudaMemcpyAsync(d, host, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        if (n > 2) NTT_CUDA_CHECK(cudaMemcpyAsync(d_tw, tw, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         const size_t smem = (size_t)(logn + 1) * n * sizeof(uint32_t);
         static bool opted[64] = {};
         if (smem > 48 * 1024 && !opted[device & 63]) {
@@ -598,14 +594,25 @@ int run_stats(int kind, uint32_t* host, size_t n, const uint32_t* tw, size_t tw_
             opted[device & 63] = true;
         }
         const CrMod m{p, ~0ull / p + ((~0ull % p) + 1 == p ? 1 : 0)};
-        cr_stats_kernel<<<1, 256, smem, st>>>(d, d_tw, logn, kind, m, factor, d_stats);
-        NTT_CUDA_CHECK(cudaGetLastError());
-        unsigned long long got[2] = {0, 0};
-        NTT_CUDA_CHECK(cudaMemcpyAsync(host, d, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        NTT_CUDA_CHECK(cudaMemcpyAsync(got, d_stats, sizeof(got), cudaMemcpyDeviceToHost, st));
-        NTT_CUDA_CHECK(cudaStreamSynchronize(st));
-        stats[0] += got[0];
-        stats[1] += got[1];
+        const size_t chunk = std::min(batch, std::max<size_t>(1, (size_t(32) << 20) / (n * sizeof(uint32_t))));
+        // counters (64-bit, first), vectors, table
+        NTT_CUDA_CHECK(cudaMallocAsync(&buf.ptr, chunk * 2 * sizeof(uint64_t) + (chunk + 1) * n * sizeof(uint32_t), st));
+        unsigned long long* d_stats = static_cast<unsigned long long*>(buf.ptr);
+        uint32_t* d = reinterpret_cast<uint32_t*>(d_stats + 2 * chunk);
+        uint32_t* d_tw = d + chunk * n;
+        if (n > 2) NTT_CUDA_CHECK(cudaMemcpyAsync(d_tw, tw, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        std::vector<unsigned long long> got(2 * chunk);
+        for (size_t b0 = 0; b0 < batch; b0 += chunk) {
+            const size_t nb = std::min(chunk, batch - b0);
+            uint32_t* h = host + b0 * n;
+            NTT_CUDA_CHECK(cudaMemcpyAsync(d, h, nb * n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            cr_stats_kernel<<<(unsigned)nb, 256, smem, st>>>(d, d_tw, logn, kind, m, factor, d_stats);
+            NTT_CUDA_CHECK(cudaGetLastError());
+            NTT_CUDA_CHECK(cudaMemcpyAsync(h, d, nb * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            NTT_CUDA_CHECK(cudaMemcpyAsync(got.data(), d_stats, nb * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            NTT_CUDA_CHECK(cudaStreamSynchronize(st));
+            for (size_t i = 0; i < 2 * nb; ++i) stats[2 * b0 + i] += got[i];
+        }
         return NTT_B200_OK;
     });
 }
@@ -642,12 +649,17 @@ int ntt_b200_custum_radix_ifft_device(int kind, uint32_t* dev, size_t n, size_t 
 int ntt_b200_custum_radix_fft_mut(int kind, uint32_t* a, size_t n, const uint32_t* twiddles, size_t tw_len, uint32_t p,
                                   uint64_t* stats) {
     if (kind == NTT_B200_CR_RADIX4_MUT) return NTT_B200_ERR_ARG;
-    return run_stats(kind, a, n, twiddles, tw_len, p, 1u, stats);
+    return run_stats(kind, a, n, 1, twiddles, tw_len, p, 1u, stats);
+}
+int ntt_b200_custum_radix_fft_mut_batch(int kind, uint32_t* host, size_t n, size_t batch, const uint32_t* twiddles,
+                                        size_t tw_len, uint32_t p, uint64_t* stats) {
+    if (kind == NTT_B200_CR_RADIX4_MUT) return NTT_B200_ERR_ARG;
+    return run_stats(kind, host, n, batch, twiddles, tw_len, p, 1u, stats);
 }
 int ntt_b200_custum_radix_ifft_radix4_mut(uint32_t* a, size_t n, const uint32_t* inv_twiddles, size_t tw_len, uint32_t p,
                                           uint32_t n_inv, int top, uint64_t* stats) {
     if (p < 2) return NTT_B200_ERR_ARG;
-    return run_stats(NTT_B200_CR_STATS_IFFT_RADIX4, a, n, inv_twiddles, tw_len, p, top ? n_inv % p : 1u, stats);
+    return run_stats(NTT_B200_CR_STATS_IFFT_RADIX4, a, n, 1, inv_twiddles, tw_len, p, top ? n_inv % p : 1u, stats);
 }
 
 }  // extern "C"

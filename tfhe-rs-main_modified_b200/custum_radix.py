@@ -108,6 +108,17 @@ def fft_split_radix_recursive_mut(a, twiddles, p, stats):
     _fft_mut(SPLIT_RADIX, a, twiddles, p, stats)
 
 
+def fft_mut_batch(kind, a, twiddles, p):
+    """New: the `_mut` routine `kind` over every row of the (batch, n) array `a` in one launch; returns a (batch, 2) uint64
+    array of (nonzero_mults, skipped_mults) per row -- the shape of the fork's dataset builder (examples/model/Dataset.rs)."""
+    batch, n = a.shape
+    stats = np.zeros((batch, 2), dtype=np.uint64)
+    B.check(B.lib().ntt_b200_custum_radix_fft_mut_batch(kind, B.host_ptr(a, np.uint32, True), n, batch,
+                                                        B.host_ptr(twiddles, np.uint32), twiddles.size, p,
+                                                        stats.ctypes.data), "in fft_mut_batch")
+    return stats
+
+
 # ---- new: batched and device-resident forms -------------------------------------------------
 
 def fft_batch(kind, a, twiddles, p):
