@@ -63,5 +63,34 @@ def main():
         del d
 
 
+def stats_bench():
+    """the `_mut` routines with MultStats: host arrays in, values and counters out (one launch per 32 MiB chunk)"""
+    import oracle_lib as O
+    L = O.lib()
+
+    class MS(C.Structure):
+        _fields_ = [("nz", C.c_size_t), ("sk", C.c_size_t)]
+    L.tfo_cr_fft_split_radix_recursive_mut.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.POINTER(MS)]
+    L.tfo_cr_fft_split_radix_recursive_mut.restype = None
+    p = 2013265921
+    for n, batch in [(64, 65536), (1024, 8192), (4096, 2048)]:
+        tw = cr.make_twiddles(n, p)
+        a = np.random.default_rng(2).integers(0, p, size=(batch, n), dtype=np.uint64).astype(np.uint32)
+        cr.fft_mut_batch(cr.SPLIT_RADIX, a.copy(), tw, p)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            cr.fft_mut_batch(cr.SPLIT_RADIX, a.copy(), tw, p)
+        gpu = reps * batch / (time.perf_counter() - t0)
+        v, st, k, t0 = a[0].copy(), MS(), 0, time.perf_counter()
+        while time.perf_counter() - t0 < 1.0:
+            L.tfo_cr_fft_split_radix_recursive_mut(v.ctypes.data, n, tw.ctypes.data, p, C.byref(st))
+            k += 1
+        cpu = k / (time.perf_counter() - t0)
+        print("split-radix _mut with MultStats, n=%-5d batch=%-6d host call: %8.1f K vectors/s   (oracle recursion, 1 core: "
+              "%.1f K/s)" % (n, batch, gpu / 1e3, cpu / 1e3), flush=True)
+
+
 if __name__ == "__main__":
     main()
+    stats_bench()
