@@ -34,10 +34,21 @@ NCU_TRAFFIC_PER_LAUNCH = {"fwd": 2.1099e9, "inv": 2.0913e9}  # dram read+write b
 # ntt_fast_{fwd,inv}_kernel<Solinas64,11,1,2> weighted by the measured issue costs of
 # profiles/r01_int_pipe_microbench.txt (IMAD.WIDE 4 clk, other IMAD 2 clk on the FMA-heavy pipe; IADD3 / LOP3 /
 # SEL / ISETP 2 clk on the ALU pipe); a polynomial pair is 8 warps.
-PIPE_CLK_PER_THREAD = {"fwd": {"fmaheavy": 2790, "alu": 2690}, "inv": {"fmaheavy": 2820, "alu": 3082}}
+PIPE_CLK_PER_THREAD = {"fwd": {"fmaheavy": 2800, "alu": 2692}, "inv": {"fmaheavy": 2828, "alu": 3082}}  # profiles/r02_sass_hist_shipped_solinas2048.txt
+# Busy fraction of the busier integer pipe that the shipped butterfly sustains when nothing else runs (register-resident
+# loop, profiles/r02_solinas_bf_variants.md: 33.75 pipe clocks needed per warp-butterfly, 39.9 measured): the ceiling of
+# roofline_int.
+INT_PIPE_PEAK_FRAC = 33.75 / 39.9
 METRIC = "fwd+inv NTTs/sec, N=2048 u64 prime, batched"
 UNIT = "NTT/s"
 WORKLOAD = "prime64 Solinas p=2^64-2^32+1 N=2048, batch %d polynomials per GPU, fwd then inv (in place, HBM-resident)" % BATCH_PER_GPU
+
+
+def workload_config(world):
+    """The `config` object, identical in the GPU arm and the reference arm (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH_PER_GPU, "n": N, "modulus": SOLINAS_P,
+            "l2_policy": "inputs (1 GiB per GPU) far larger than the 126 MB L2",
+            "parallelism": "batch sharded over %d GPU(s), no collective" % world}
 
 
 def measured_peaks():
@@ -153,6 +164,47 @@ def cpu_leg(sample_polys, repeats, threads):
     return 2.0 * sample_polys * repeats / dt, dt
 
 
+PBS_PARAMS = {"n_lwe": 742, "n": N, "k": 1, "base_log": 23, "level": 1}  # tfhe test/mod.rs:106-130 (TEST_PARAMS_3_BITS_SOLINAS_U64)
+
+
+def pbs_inputs(batch, seed=1):
+    """Random NTT-domain key, ciphertexts and LUT of the reference's parameter set (the timing does not depend on the
+    values; parity of the same call is tests/test_pbs_gpu.py)."""
+    rng = np.random.default_rng(seed)
+    n_lwe, gs, level = PBS_PARAMS["n_lwe"], PBS_PARAMS["k"] + 1, PBS_PARAMS["level"]
+    p = np.uint64(SOLINAS_P)
+    bsk = (rng.integers(0, 1 << 63, n_lwe * level * gs * gs * N, dtype=np.uint64) * np.uint64(2)) % p
+    lut = rng.integers(0, 1 << 62, gs * N, dtype=np.uint64)
+    lwe = rng.integers(1, 1 << 62, (batch, n_lwe + 1), dtype=np.uint64)
+    return bsk, lut, lwe
+
+
+def pbs_cpu_leg(threads, seconds=8.0):
+    """The PBS on the host cores: the oracle's restatement of programmable_bootstrap_ntt64_lwe_ciphertext with the
+    vectorised transforms, independent ciphertexts over all host threads (static contiguous chunks)."""
+    import oracle_lib
+    lib = oracle_lib._load(native=True)
+    plan = oracle_lib.OraclePlan(64, N, SOLINAS_P, _lib=lib)
+    gs = PBS_PARAMS["k"] + 1
+    bsk, lut, lwe = pbs_inputs(threads)
+    pbs = oracle_lib.OraclePbs(plan, bsk, PBS_PARAMS["n_lwe"], gs, PBS_PARAMS["base_log"], PBS_PARAMS["level"])
+    lib.tfo_use_simd_transforms(1)
+    try:
+        t0 = time.perf_counter()
+        pbs.pbs_batch(lwe, lut, threads)  # one ciphertext per thread: sizes the sample
+        one = time.perf_counter() - t0
+        rounds = int(max(1, min(64, seconds / max(one, 1e-3))))
+        t0 = time.perf_counter()
+        for _ in range(rounds):
+            pbs.pbs_batch(lwe, lut, threads)
+        dt = time.perf_counter() - t0
+    finally:
+        lib.tfo_use_simd_transforms(0)
+    return {"value": threads * rounds / dt, "unit": "PBS/s", "cores": threads, "kind": "port", "isa": CPU_ISA[0],
+            "sample": "%d rounds x %d ciphertexts (one per thread), %.1f s" % (rounds, threads, dt),
+            "config": dict(PBS_PARAMS, workload="programmable_bootstrap_ntt64_lwe_ciphertext (classic)")}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -181,12 +233,17 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "cpu_sample": sample_txt},
+        "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt,
                          "isa": CPU_ISA[0], "note": CPU_NOTE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_pbs:
+        try:
+            line["pbs"] = pbs_cpu_leg(threads)
+        except Exception as e:
+            line["pbs"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
 
 
@@ -277,6 +334,38 @@ def run_gpu(args):
     chunk = 32 << 20  # staging chunk of the host pipeline (csrc/capi_prime.cu chunk_bytes())
     e2e_launches = e2e_steps * ((eb * N * 8 + chunk - 1) // chunk)
 
+    # ---- sustained leg: the same step back to back for >= 2 s, clocks sampled throughout ----
+    sustained = None
+    if not args.no_sustained:
+        per = max(args.steps, 20)
+        with ClockSampler(local) as sclk:
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            done, t_s = 0, time.perf_counter()
+            while time.perf_counter() - t_s < args.sustained_seconds:
+                for _ in range(per):
+                    plan.fwd_device(d, batch, stream=stream)
+                    plan.inv_device(d, batch, stream=stream)
+                done += per
+                torch.cuda.synchronize()
+            s1.record(stream)
+            barrier()
+        sus_ms = s0.elapsed_time(s1)
+        ts = torch.tensor([sus_ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sustained = {"seconds": float(ts.item()) * 1e-3, "steps": done, "value": 2.0 * batch * world * done / (float(ts.item()) * 1e-3),
+                     "unit": UNIT, "ms_per_step": float(ts.item()) / done, "clocks": sclk.summary()}
+
+    # ---- C1: the per-polynomial drop-in call (Plan::fwd on one host polynomial, N = 1024) next to one CPU core ----
+    c1 = None
+    if rank == 0 and not args.no_cpu:
+        try:
+            c1 = c1_latency_leg(T)
+        except Exception as e:
+            c1 = {"error": repr(e)}
+
     if rank == 0:
         peaks, which = measured_peaks()
         hbm = float(peaks["hbm_gbs"])
@@ -297,9 +386,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "n": N, "modulus": SOLINAS_P,
-                       "l2_policy": "inputs (1 GiB per GPU) far larger than the 126 MB L2",
-                       "parallelism": "batch sharded over %d GPU(s), no collective" % world},
+            "config": workload_config(world),
             "roofline": {"bound": "hbm", "kernel": "ntt %s (N=2048 Solinas)" % dom, "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm, "traffic": NCU_TRAFFIC_PER_LAUNCH[dom], "peak_source": which,
                          "traffic_source": "profiles/r01_ncu_full_solinas2048_v4_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
@@ -311,6 +398,15 @@ def run_gpu(args):
                                           "a two-pipe mix tops out at 0.76 in profiles/r01_int_pipe_microbench.txt",
                          "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                          "algorithmic_bytes_per_launch": batch * ALG_BYTES_PER_NTT},
+            # the binding roofline: the busier integer pipe of the dominant kernel against what the same butterfly
+            # sustains register-resident (no memory, no barriers)
+            "roofline_int": {"bound": "integer issue (ALU + FMA-heavy pipes)", "kernel": "ntt %s (N=2048 Solinas)" % dom,
+                             "achieved": max(int_pipes[dom].values()), "peak": INT_PIPE_PEAK_FRAC,
+                             "unit": "busy fraction of the busier pipe", "frac": max(int_pipes[dom].values()) / INT_PIPE_PEAK_FRAC,
+                             "peak_source": "profiles/microbench/solinas_bf_variants.cu (V0, register resident): "
+                                            "profiles/r02_solinas_bf_variants.md; pipe issue costs from profiles/microbench/int_pipe.cu"},
+            "sustained": sustained,
+            "c1_latency": c1,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,
                     "api": "prime64.Plan.fwd_mac_inv_batch (C ABI ntt_b200_plan64_fwd_mac_inv_batch) on pinned host "
                            "buffers: %d polynomials in, fwd + pointwise + inv, %d polynomials out per step" % (eb, eb),
@@ -330,28 +426,62 @@ def run_gpu(args):
                     "sample": "%d x (fwd+inv over 2048 polynomials), %.1f s of CPU work, %d threads" % (reps, dt, threads)}
             except Exception as e:  # the GPU numbers stand on their own
                 line["cpu_baseline"] = {"error": repr(e)}
-        if world == 1 and not args.no_pbs:
-            try:  # informational: the NTT-PBS that calls the hot path (not the headline metric)
-                line["pbs"] = pbs_leg(plan, torch)
-            except Exception as e:
-                line["pbs"] = {"error": repr(e)}
+    # ---- the consumer of the hot path: NTT-PBS, ciphertexts sharded over the ranks like the polynomials ----
+    pbs = None
+    if not args.no_pbs:
+        try:
+            pbs = pbs_leg(plan, torch, dist if world > 1 else None, world, barrier)
+        except Exception as e:
+            pbs = {"error": repr(e)}
+    if rank == 0:
+        if pbs is not None:
+            if world == 1 and not args.no_cpu and "error" not in pbs:
+                try:
+                    pbs["cpu_baseline"] = pbs_cpu_leg(os.cpu_count() or 1)
+                except Exception as e:
+                    pbs["cpu_baseline"] = {"error": repr(e)}
+            line["pbs"] = pbs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def pbs_leg(plan, torch, batch=888, n_lwe=742, base_log=23, level=1, reps=3):
-    """Programmable bootstraps per second at the reference's parameter set (tfhe test/mod.rs:106-130:
-    n_lwe 742, k 1, N 2048, base_log 23, level 1, Solinas prime), device resident, random key."""
-    import numpy as np
+def c1_latency_leg(T, n=1024, reps=400):
+    """BASELINE config C1: Plan::fwd on ONE host polynomial (N = 1024, Solinas) through the C ABI mirror, wall clock per
+    call, and the CPU port of the reference doing the same transform on one core."""
+    import oracle_lib
+    plan = T.prime64.Plan.try_new(n, SOLINAS_P)
+    buf = (np.arange(n, dtype=np.uint64) * np.uint64(12345)) % np.uint64(SOLINAS_P)
+    for _ in range(50):
+        plan.fwd(buf)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        plan.fwd(buf)
+    gpu_us = (time.perf_counter() - t0) / reps * 1e6
+    lib = oracle_lib._load(native=True)
+    ref = oracle_lib.OraclePlan(64, n, SOLINAS_P, _lib=lib)
+    isa = ref.fwd_batch_inplace(buf, 1, simd=True)
+    t0 = time.perf_counter()
+    for _ in range(4 * reps):
+        ref.fwd_batch_inplace(buf, 1, simd=True)
+    cpu_us = (time.perf_counter() - t0) / (4 * reps) * 1e6
+    return {"gpu_us": gpu_us, "cpu_us": cpu_us, "cpu_isa": isa, "n": n,
+            "call": "prime64::Plan::fwd on one host polynomial (ntt_b200_plan64_fwd; mapped pinned staging, one launch)",
+            "note": "a single small call is launch- and PCIe-latency-bound; profiles/r02_latency.txt has the batch sizes from which the GPU path is ahead"}
+
+
+def pbs_leg(plan, torch, dist, world, barrier, batch=888, reps=3, host_batch=1776):
+    """Programmable bootstraps per second at the reference's parameter set, per GPU `batch` ciphertexts device
+    resident (value) and `host_batch` ciphertexts through the host-buffer call
+    programmable_bootstrap_ntt64_lwe_ciphertext (e2e: LWE in, LWE out, copies inside the timed region)."""
     from tfhe_ntt_b200 import ntt64_pbs as G
-    rng = np.random.default_rng(1)
-    n, gs = plan.ntt_size(), 2
-    bsk = (rng.integers(0, 1 << 63, n_lwe * level * gs * gs * n, dtype=np.uint64) * np.uint64(2)) % np.uint64(SOLINAS_P)
+    n_lwe, gs, base_log, level = PBS_PARAMS["n_lwe"], PBS_PARAMS["k"] + 1, PBS_PARAMS["base_log"], PBS_PARAMS["level"]
+    n = plan.ntt_size()
+    bsk, lut_h, lwe_h = pbs_inputs(max(batch, host_batch))
     key = G.NttLweBootstrapKey.from_container(plan, bsk, n_lwe, gs, base_log, level)
     dev = torch.device("cuda", torch.cuda.current_device())
-    lut = torch.from_numpy(rng.integers(0, 1 << 62, gs * n, dtype=np.uint64).view(np.int64)).to(dev)
-    lwe = torch.from_numpy(rng.integers(1, 1 << 62, (batch, n_lwe + 1), dtype=np.uint64).view(np.int64)).to(dev)
+    lut = torch.from_numpy(lut_h.view(np.int64)).to(dev)
+    lwe = torch.from_numpy(lwe_h[:batch].view(np.int64)).to(dev)
     acc = torch.empty((batch, gs * n), dtype=torch.int64, device=dev)
     out = torch.empty((batch, (gs - 1) * n + 1), dtype=torch.int64, device=dev)
     st = torch.cuda.current_stream()
@@ -362,18 +492,35 @@ def pbs_leg(plan, torch, batch=888, n_lwe=742, base_log=23, level=1, reps=3):
 
     for _ in range(2):
         step()
-    torch.cuda.synchronize()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
         step()
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     ms = e0.elapsed_time(e1) / reps
-    return {"value": batch / ms * 1e3, "unit": "PBS/s", "ms_per_batch": ms,
-            "config": {"workload": "programmable_bootstrap_ntt64 (classic), persistent two-CTA-cluster blind rotation + sample extraction",
-                       "batch": batch, "n_lwe": n_lwe, "n": n, "k": 1, "base_log": base_log, "level": level},
-            "ntt_per_s_inside": batch * n_lwe * 4 / ms * 1e3}
+    # host-buffer call
+    lwe_in = np.ascontiguousarray(lwe_h[:host_batch]).reshape(-1)
+    lwe_out = np.zeros(host_batch * ((gs - 1) * n + 1), dtype=np.uint64)
+    G.programmable_bootstrap_ntt64_lwe_ciphertext(lwe_in, lwe_out, lut_h, key)
+    barrier()
+    t0 = time.perf_counter()
+    G.programmable_bootstrap_ntt64_lwe_ciphertext(lwe_in, lwe_out, lut_h, key)
+    barrier()
+    host_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([ms, host_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, host_s = float(t[0].item()), float(t[1].item())
+    return {"value": batch * world / ms * 1e3, "unit": "PBS/s", "ms_per_batch": ms, "n_gpus": world,
+            "config": dict(PBS_PARAMS, workload="programmable_bootstrap_ntt64 (classic), persistent two-CTA-cluster blind "
+                                                "rotation + sample extraction; ciphertexts sharded over the GPUs, no collective",
+                           batch_per_gpu=batch),
+            "ntt_per_s_inside": batch * world * n_lwe * 4 / ms * 1e3,
+            "e2e": {"value": host_batch * world / host_s, "unit": "PBS/s", "batch_per_gpu": host_batch,
+                    "h2d_bytes_per_step": int(lwe_in.nbytes + lut_h.nbytes), "d2h_bytes_per_step": int(lwe_out.nbytes),
+                    "api": "ntt64_pbs.programmable_bootstrap_ntt64_lwe_ciphertext (C ABI ntt_b200_programmable_bootstrap_ntt64) on host buffers"}}
 
 
 def main():
@@ -385,6 +532,8 @@ def main():
     ap.add_argument("--normalize", action="store_true", help="also run normalize in warm-up steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-pbs", action="store_true", help="skip the informational NTT-PBS leg")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s back-to-back leg")
+    ap.add_argument("--sustained-seconds", type=float, default=2.2)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

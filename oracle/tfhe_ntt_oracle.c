@@ -1741,6 +1741,18 @@ void tfo_product_mul_accumulate(const tfo_product_plan *pl, uint64_t *acc, const
 
 /* mode 0: forward (:89-95); 1: forward_normalized (:97-108); 2: forward_from_decomp (:218-238);
  * 3: forward_from_power_of_two_modulus(width) (:201-214 with the modswitch :165-177) */
+/* CPU-baseline switch (see the header): vectorised transforms inside the Ntt64View / PBS restatement */
+static int g_simd_transforms = 0;
+void tfo_use_simd_transforms(int on) { g_simd_transforms = on; }
+static void view_fwd(const tfo_plan64 *pl, uint64_t *buf) {
+    if (g_simd_transforms && tfo_plan64_fwd_simd1(pl, buf)) return;
+    tfo_plan64_fwd(pl, buf);
+}
+static void view_inv(const tfo_plan64 *pl, uint64_t *buf) {
+    if (g_simd_transforms && tfo_plan64_inv_simd1(pl, buf)) return;
+    tfo_plan64_inv(pl, buf);
+}
+
 void tfo_ntt64_forward(const tfo_plan64 *pl, uint64_t *ntt, const uint64_t *standard, int mode,
                        uint32_t width) {
     size_t n = pl->n;
@@ -1755,7 +1767,7 @@ void tfo_ntt64_forward(const tfo_plan64 *pl, uint64_t *ntt, const uint64_t *stan
             ntt[i] = (uint64_t)(((v * (u128)p) + ((u128)1 << (width - 1))) >> width);
         }
     }
-    tfo_plan64_fwd(pl, ntt);
+    view_fwd(pl, ntt);
     if (mode == 1) tfo_plan64_normalize(pl, ntt, n);
 }
 
@@ -1766,7 +1778,7 @@ void tfo_ntt64_add_backward(const tfo_plan64 *pl, uint64_t *standard, uint64_t *
                             uint32_t width) {
     size_t n = pl->n;
     uint64_t p = pl->p;
-    tfo_plan64_inv(pl, ntt);
+    view_inv(pl, ntt);
     if (mode == 0) {
         for (size_t i = 0; i < n; i++) {
             /* wrapping_add_custom_mod = a - neg(b) (mod p), tfhe .../numeric/unsigned.rs:174-190, :219-225 */

@@ -249,6 +249,20 @@ void tfo_convert_standard_lwe_bootstrap_key_to_ntt64(const tfo_plan64 *, const u
  * Return 1 when the SIMD path ran, 0 when the CPU / build has no AVX-512F+DQ or p is not the
  * Solinas prime (the caller then uses the scalar batch helpers). */
 int tfo_plan64_fwd_batch_simd(const tfo_plan64 *, uint64_t *buf, size_t batch, int threads);
+/* one polynomial on the calling thread; 0 = no vector path on this host / for this plan (nothing done) */
+int tfo_plan64_fwd_simd1(const tfo_plan64 *, uint64_t *buf);
+int tfo_plan64_inv_simd1(const tfo_plan64 *, uint64_t *buf);
+/* CPU BASELINE ONLY (bench.py): when on, tfo_ntt64_forward / tfo_ntt64_add_backward -- the transforms
+ * inside the PBS restatement -- run the vectorised Solinas port where the host has AVX-512 (same bits
+ * as the scalar path, tests/test_oracle_simd.py).  Off by default: the parity tests use the scalar path. */
+void tfo_use_simd_transforms(int on);
+/* batch of programmable bootstraps (classic) over `threads` host threads in static contiguous chunks,
+ * the decomposition the reference's callers use with rayon; accumulator [acc_count][(k+1)N], acc_count 1 or batch */
+void tfo_programmable_bootstrap_ntt64_batch(const tfo_plan64 *, const uint64_t *bsk, size_t n_lwe,
+                                            size_t glwe_size, uint32_t base_log, uint32_t level,
+                                            const uint64_t *lwe_in, uint64_t *lwe_out,
+                                            const uint64_t *accumulator, size_t acc_count, size_t batch,
+                                            int threads);
 int tfo_plan64_inv_batch_simd(const tfo_plan64 *, uint64_t *buf, size_t batch, int threads);
 
 /* custum_radix (tfhe_ntt_custum_radix_oracle.c): the fork's recursive cyclic u32 transforms,

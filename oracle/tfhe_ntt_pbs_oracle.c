@@ -17,6 +17,7 @@
  */
 #include "tfhe_ntt_oracle.h"
 
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -303,6 +304,50 @@ void tfo_programmable_bootstrap_ntt64(const tfo_plan64 *pl, const uint64_t *bsk,
     tfo_blind_rotate_ntt64_assign(pl, bsk, n_lwe, glwe_size, base_log, level, lwe_in, local);
     tfo_extract_lwe_sample(local, glwe_size, pl->n, 0, pl->p, lwe_out);
     free(local);
+}
+
+/* A batch of the above over host threads, static contiguous chunks (how the reference's callers
+ * parallelise independent ciphertexts with rayon, e.g. lwe_bootstrap_key_conversion.rs:419-447):
+ * bench.py's CPU arm for the PBS. */
+typedef struct {
+    const tfo_plan64 *pl;
+    const uint64_t *bsk, *lwe_in, *accumulator;
+    uint64_t *lwe_out;
+    size_t n_lwe, glwe_size, acc_count, begin, end;
+    uint32_t base_log, level;
+} pbs_job;
+static void *pbs_worker(void *arg) {
+    pbs_job *j = (pbs_job *)arg;
+    size_t per = j->glwe_size * j->pl->n, out = (j->glwe_size - 1) * j->pl->n + 1;
+    for (size_t b = j->begin; b < j->end; b++)
+        tfo_programmable_bootstrap_ntt64(j->pl, j->bsk, j->n_lwe, j->glwe_size, j->base_log, j->level,
+                                         j->lwe_in + b * (j->n_lwe + 1), j->lwe_out + b * out,
+                                         j->accumulator + (j->acc_count == 1 ? 0 : b) * per);
+    return NULL;
+}
+void tfo_programmable_bootstrap_ntt64_batch(const tfo_plan64 *pl, const uint64_t *bsk, size_t n_lwe,
+                                            size_t glwe_size, uint32_t base_log, uint32_t level,
+                                            const uint64_t *lwe_in, uint64_t *lwe_out,
+                                            const uint64_t *accumulator, size_t acc_count, size_t batch,
+                                            int threads) {
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > batch) threads = batch ? (int)batch : 1;
+    pthread_t *tid = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    pbs_job *jobs = (pbs_job *)calloc((size_t)threads, sizeof(pbs_job));
+    size_t chunk = (batch + (size_t)threads - 1) / (size_t)threads;
+    for (int t = 0; t < threads; t++) {
+        size_t b = (size_t)t * chunk, e = b + chunk;
+        if (b > batch) b = batch;
+        if (e > batch) e = batch;
+        jobs[t] = (pbs_job){pl, bsk, lwe_in, accumulator, lwe_out, n_lwe, glwe_size, acc_count, b, e, base_log, level};
+        if (t == threads - 1)
+            pbs_worker(&jobs[t]);
+        else
+            pthread_create(&tid[t], NULL, pbs_worker, &jobs[t]);
+    }
+    for (int t = 0; t + 1 < threads; t++) pthread_join(tid[t], NULL);
+    free(tid);
+    free(jobs);
 }
 
 /* programmable_bootstrap_ntt64_bnf_lwe_ciphertext_mem_optimized, ntt64_bnf_pbs.rs:469-539 */

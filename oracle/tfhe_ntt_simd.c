@@ -180,6 +180,19 @@ static int run_simd(const tfo_plan64 *pl, uint64_t *buf, size_t batch, int threa
     free(jobs);
     return 1;
 }
+static int simd_ok(const tfo_plan64 *pl) {
+    return pl->p == SOLINAS_P && pl->n >= 16 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq");
+}
+int tfo_plan64_fwd_simd1(const tfo_plan64 *pl, uint64_t *buf) {
+    if (!simd_ok(pl)) return 0;
+    fwd_solinas_avx512(buf, pl->n, pl->twid);
+    return 1;
+}
+int tfo_plan64_inv_simd1(const tfo_plan64 *pl, uint64_t *buf) {
+    if (!simd_ok(pl)) return 0;
+    inv_solinas_avx512(buf, pl->n, pl->inv_twid);
+    return 1;
+}
 int tfo_plan64_fwd_batch_simd(const tfo_plan64 *pl, uint64_t *buf, size_t batch, int threads) {
     return run_simd(pl, buf, batch, threads, 0);
 }
@@ -187,6 +200,14 @@ int tfo_plan64_inv_batch_simd(const tfo_plan64 *pl, uint64_t *buf, size_t batch,
     return run_simd(pl, buf, batch, threads, 1);
 }
 #else
+int tfo_plan64_fwd_simd1(const tfo_plan64 *pl, uint64_t *buf) {
+    (void)pl; (void)buf;
+    return 0;
+}
+int tfo_plan64_inv_simd1(const tfo_plan64 *pl, uint64_t *buf) {
+    (void)pl; (void)buf;
+    return 0;
+}
 int tfo_plan64_fwd_batch_simd(const tfo_plan64 *pl, uint64_t *buf, size_t batch, int threads) {
     (void)pl; (void)buf; (void)batch; (void)threads;
     return 0;

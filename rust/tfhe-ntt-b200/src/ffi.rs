@@ -39,6 +39,7 @@ extern "C" {
     pub fn ntt_b200_plan64_inv_device(plan: *const ntt_b200_plan64, dev: *mut u64, batch: usize, stream: *mut c_void) -> c_int;
 
     pub fn ntt_b200_plan64_normalize_device(plan: *const ntt_b200_plan64, dev: *mut u64, len: usize, stream: *mut c_void) -> c_int;
+    pub fn ntt_b200_plan64_mul_assign_normalize_device(plan: *const ntt_b200_plan64, lhs: *mut u64, len: usize, rhs: *const u64, rhs_len: usize, stream: *mut c_void) -> c_int;
     pub fn ntt_b200_plan64_mul_accumulate_device(plan: *const ntt_b200_plan64, acc: *mut u64, len: usize, lhs: *const u64, lhs_len: usize, rhs: *const u64, rhs_len: usize, stream: *mut c_void) -> c_int;
     pub fn ntt_b200_plan64_fwd_mac_inv_device(plan: *const ntt_b200_plan64, out: *mut u64, lhs: *const u64, rhs: *const u64, rhs_polys: usize, acc: *const u64, acc_polys: usize, batch: usize, stream: *mut c_void) -> c_int;
     pub fn ntt_b200_plan64_fwd_mac_inv_batch(plan: *const ntt_b200_plan64, out: *mut u64, lhs: *const u64, rhs: *const u64, rhs_polys: usize, acc: *const u64, acc_polys: usize, batch: usize) -> c_int;
@@ -60,6 +61,10 @@ extern "C" {
     pub fn ntt_b200_plan32_fwd_batch_multi_gpu(plans: *const *const ntt_b200_plan32, n_plans: usize, host: *mut u32, batch: usize) -> c_int;
     pub fn ntt_b200_plan32_inv_batch_multi_gpu(plans: *const *const ntt_b200_plan32, n_plans: usize, host: *mut u32, batch: usize) -> c_int;
 
+    pub fn ntt_b200_plan32_normalize_device(plan: *const ntt_b200_plan32, dev: *mut u32, len: usize, stream: *mut c_void) -> c_int;
+    pub fn ntt_b200_plan32_mul_assign_normalize_device(plan: *const ntt_b200_plan32, lhs: *mut u32, len: usize, rhs: *const u32, rhs_len: usize, stream: *mut c_void) -> c_int;
+    pub fn ntt_b200_plan32_mul_accumulate_device(plan: *const ntt_b200_plan32, acc: *mut u32, len: usize, lhs: *const u32, lhs_len: usize, rhs: *const u32, rhs_len: usize, stream: *mut c_void) -> c_int;
+    pub fn ntt_b200_plan32_fwd_mac_inv_device(plan: *const ntt_b200_plan32, out: *mut u32, lhs: *const u32, rhs: *const u32, rhs_polys: usize, acc: *const u32, acc_polys: usize, batch: usize, stream: *mut c_void) -> c_int;
     pub fn ntt_b200_plan32_fwd_device(plan: *const ntt_b200_plan32, dev: *mut u32, batch: usize, stream: *mut c_void) -> c_int;
     pub fn ntt_b200_plan32_inv_device(plan: *const ntt_b200_plan32, dev: *mut u32, batch: usize, stream: *mut c_void) -> c_int;
 

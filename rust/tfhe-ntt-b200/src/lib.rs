@@ -2,7 +2,10 @@
 //! Module tree, type names and method signatures are the reference's; batched and
 //! device-resident entry points are added alongside.  There is no CPU fallback.
 pub mod ffi;
+pub mod fastdiv;
 pub mod prime;
+mod primes;
+pub use primes::{primes32, primes52};
 pub mod prime32;
 pub mod prime64;
 pub mod product;

@@ -78,6 +78,31 @@ impl Plan {
     pub unsafe fn inv_device(&self, dev: *mut u32, batch: usize, stream: *mut core::ffi::c_void) {
         check(ffi::ntt_b200_plan32_inv_device(self.raw, dev, batch, stream), "inv_device")
     }
+    /// New: `Plan::normalize` on device memory (prime32.rs normalize), asynchronous on `stream`.
+    /// # Safety
+    /// `dev` must point at `len` elements on the plan's GPU.
+    pub unsafe fn normalize_device(&self, dev: *mut u32, len: usize, stream: *mut core::ffi::c_void) {
+        check(ffi::ntt_b200_plan32_normalize_device(self.raw, dev, len, stream), "normalize_device")
+    }
+    /// New: `Plan::mul_assign_normalize` on device memory; `rhs` may be shorter than `lhs` (its length
+    /// divides `len`: one operand shared by a batch).
+    /// # Safety
+    /// device pointers on the plan's GPU with `len` / `rhs_len` elements.
+    pub unsafe fn mul_assign_normalize_device(&self, lhs: *mut u32, len: usize, rhs: *const u32, rhs_len: usize, stream: *mut core::ffi::c_void) {
+        check(ffi::ntt_b200_plan32_mul_assign_normalize_device(self.raw, lhs, len, rhs, rhs_len, stream), "mul_assign_normalize_device")
+    }
+    /// New: `Plan::mul_accumulate` on device memory; `lhs` / `rhs` may be batch-shared (their lengths divide `len`).
+    /// # Safety
+    /// device pointers on the plan's GPU with `len` / `lhs_len` / `rhs_len` elements.
+    pub unsafe fn mul_accumulate_device(&self, acc: *mut u32, len: usize, lhs: *const u32, lhs_len: usize, rhs: *const u32, rhs_len: usize, stream: *mut core::ffi::c_void) {
+        check(ffi::ntt_b200_plan32_mul_accumulate_device(self.raw, acc, len, lhs, lhs_len, rhs, rhs_len, stream), "mul_accumulate_device")
+    }
+    /// New: `out = inv(acc + fwd(lhs) * rhs)` on device memory in one kernel (`acc` may be null).
+    /// # Safety
+    /// device pointers on the plan's GPU; `rhs_polys` / `acc_polys` divide `batch`.
+    pub unsafe fn fwd_mac_inv_device(&self, out: *mut u32, lhs: *const u32, rhs: *const u32, rhs_polys: usize, acc: *const u32, acc_polys: usize, batch: usize, stream: *mut core::ffi::c_void) {
+        check(ffi::ntt_b200_plan32_fwd_mac_inv_device(self.raw, out, lhs, rhs, rhs_polys, acc, acc_polys, batch, stream), "fwd_mac_inv_device")
+    }
     pub(crate) unsafe fn borrowed(raw: *const ffi::ntt_b200_plan32) -> core::mem::ManuallyDrop<Self> {
         core::mem::ManuallyDrop::new(Self { raw: raw as *mut _ })
     }

@@ -152,6 +152,10 @@ def _load(native=False):
         "tfo_convert_standard_lwe_bootstrap_key_to_ntt64": (None, [P64, vp, vp, sz, u32, i]),
         "tfo_plan64_fwd_batch_simd": (i, [P64, vp, sz, i]),
         "tfo_plan64_inv_batch_simd": (i, [P64, vp, sz, i]),
+        "tfo_plan64_fwd_simd1": (i, [P64, vp]),
+        "tfo_plan64_inv_simd1": (i, [P64, vp]),
+        "tfo_use_simd_transforms": (None, [i]),
+        "tfo_programmable_bootstrap_ntt64_batch": (None, [P64, vp, sz, sz, u32, u32, vp, vp, vp, sz, sz, i]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -444,6 +448,19 @@ class OraclePbs:
         out = np.zeros((self.glwe_size - 1) * self.n + 1, dtype=np.uint64)
         self.lib.tfo_programmable_bootstrap_ntt64(self.plan.h, _ptr(self.bsk), self.n_lwe, self.glwe_size,
                                                   self.base_log, self.level, _ptr(lwe_in), _ptr(out), _ptr(acc))
+        return out
+
+    def pbs_batch(self, lwe_in, accumulator, threads):
+        """classic PBS of lwe_in [batch][n_lwe+1] over `threads` host threads (bench.py's CPU arm);
+        accumulator: one LUT [(k+1)N] or one per ciphertext"""
+        lwe_in = np.ascontiguousarray(lwe_in, dtype=np.uint64).reshape(-1, self.n_lwe + 1)
+        acc = np.ascontiguousarray(accumulator, dtype=np.uint64).reshape(-1, self.glwe_size * self.n)
+        batch = lwe_in.shape[0]
+        assert acc.shape[0] in (1, batch)
+        out = np.zeros((batch, (self.glwe_size - 1) * self.n + 1), dtype=np.uint64)
+        self.lib.tfo_programmable_bootstrap_ntt64_batch(self.plan.h, _ptr(self.bsk), self.n_lwe, self.glwe_size,
+                                                        self.base_log, self.level, _ptr(lwe_in), _ptr(out), _ptr(acc),
+                                                        acc.shape[0], batch, threads)
         return out
 
     def pbs_bnf(self, lwe_in, accumulator, width=64):

@@ -38,6 +38,28 @@ def dev_rand_below(torch, p, shape, bits, seed):
     return v
 
 
+def dev_rand_full64(torch, p, shape, seed, edge_rows=True):
+    """Canonical residues over the WHOLE range [0, p) of a 64-bit prime, [2^63, p) included, generated on
+    the device in int64 storage; the first rows are replaced by the edge rows p-1, 0, 1."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    hi = torch.randint(0, 1 << 32, shape, dtype=torch.int64, device="cuda", generator=g)
+    lo = torch.randint(0, 1 << 32, shape, dtype=torch.int64, device="cuda", generator=g)
+    v = (hi << 32) | lo  # uniform 64-bit patterns (two's complement storage)
+    if p < (1 << 63):
+        v = (v & ((1 << 63) - 1)) % p
+    else:
+        ps = p - (1 << 64)  # p as an int64 bit pattern
+        minv = -(1 << 63)
+        ge = (v ^ minv) >= (ps ^ minv)  # unsigned v >= p
+        v = torch.where(ge, v - ps, v)  # 2^64 - p < p: one subtraction is enough
+    if edge_rows and len(shape) >= 2 and shape[0] >= 4:
+        v[0] = p - 1 - (1 << 64) if p >= (1 << 63) else p - 1
+        v[1] = 0
+        v[2] = 1
+        v[-1] = p - 1 - (1 << 64) if p >= (1 << 63) else p - 1
+    return v
+
+
 def to_u(t, bits):
     a = t.cpu().numpy()
     return a.view(np.uint64 if bits == 64 else np.uint32)
@@ -123,6 +145,67 @@ def test_c3_prime64_solinas_pbs_shaped(T, torch):
     assert torch.equal(ntt, dig)
 
 
+def test_headline_solinas_n2048_batch65536_full_size(T, torch):
+    # the bench.py workload itself: 65536 x 2048, Solinas, coefficients over the whole of [0, p)
+    n, p, batch = 2048, SOLINAS_P, 65536
+    plan, ref = T.prime64.Plan.try_new(n, p), OraclePlan(64, n, p)
+    x = dev_rand_full64(torch, p, (batch, n), 31)
+    assert int((x < 0).sum()) > batch * n // 4  # really covers [2^63, p)
+    y = x.clone()
+    st = torch.cuda.current_stream()
+    plan.fwd_device(y, stream=st)
+    torch.cuda.synchronize()
+    # first / last CTA (two polynomials each), the edge rows, and rows spread over the grid
+    idx = [0, 1, 2, 3, 4, 5, 255, 256, 4097, 12345, 32767, 32768, 40001, 54321, 65532, 65533, 65534, 65535]
+    X, F = to_u(x[idx], 64), to_u(y[idx], 64)
+    assert (F == ref.fwd(X)).all()
+    assert int(to_u(y, 64).max()) < p  # canonical over the whole batch
+    plan.inv_device(y, stream=st)
+    torch.cuda.synchronize()
+    assert (to_u(y[idx], 64) == ref.inv(F)).all()
+    plan.normalize_device(y, stream=st)
+    assert torch.equal(y, x)  # inv(fwd(x)) / n == x over the whole batch
+
+
+def test_c3_full_size_fused_external_product(T, torch):
+    # C3 through the FUSED kernel (ntt_fast_ext_product_kernel, the one the bench and the PBS use) at
+    # full size, against the unfused device calls over the whole batch and the oracle on sampled LWEs.
+    n, p, lwes, k1, l = 2048, SOLINAS_P, 4096, 2, 2
+    rows, cols = k1 * l, k1
+    plan, ref = T.prime64.Plan.try_new(n, p), OraclePlan(64, n, p)
+    st = torch.cuda.current_stream()
+    for variant in ("digits", "full_range"):
+        if variant == "digits":  # small signed digits mapped into [0, p) like ntt64.rs:231-238
+            g = torch.Generator(device="cuda").manual_seed(5)
+            d = torch.randint(-(1 << 22), 1 << 22, (lwes, rows, n), dtype=torch.int64, device="cuda", generator=g)
+            inp = torch.where(d < 0, d + torch.tensor(p - (1 << 64), dtype=torch.int64, device="cuda"), d)
+        else:
+            inp = dev_rand_full64(torch, p, (lwes, rows, n), 6)
+        ggsw = dev_rand_full64(torch, p, (rows, cols, n), 7)
+        out = torch.zeros((lwes, cols, n), dtype=torch.int64, device="cuda")
+        plan.ext_product_device(out, inp, ggsw, rows, cols, stream=st)
+        # unfused: fwd, rows * cols mul_accumulate, inv
+        ntt = inp.clone()
+        plan.fwd_device(ntt, lwes * rows, stream=st)
+        acc = torch.zeros((lwes, cols, n), dtype=torch.int64, device="cuda")
+        for r in range(rows):
+            lhs_row = ntt[:, r, :].contiguous()
+            for c in range(cols):
+                a = acc[:, c, :].contiguous()
+                plan.mul_accumulate_device(a, lhs_row, ggsw[r, c].contiguous(), stream=st)
+                acc[:, c, :] = a
+        plan.inv_device(acc, lwes * cols, stream=st)
+        torch.cuda.synchronize()
+        assert torch.equal(out, acc), variant
+        for lwe in (0, 1, 2, 3, 1234, 2048, 4094, 4095):
+            f = ref.fwd(to_u(inp[lwe], 64))
+            for c in range(cols):
+                want = np.zeros(n, dtype=np.uint64)
+                for r in range(rows):
+                    want = ref.mul_accumulate(want, f[r], to_u(ggsw[r, c], 64))
+                assert (to_u(out[lwe, c], 64) == ref.inv(want)).all(), (variant, lwe, c)
+
+
 def test_c4_native64_plan32_n4096_batch16384(T, torch):
     n, batch = 4096, 16384
     plan, ref = T.native64.Plan32.try_new(n), OracleNativePlan(O.NATIVE64_PLAN32, n)
@@ -146,12 +229,12 @@ def test_c4_native64_plan32_n4096_batch16384(T, torch):
 def test_c5_prime64_n65536_batch1024(T, torch):
     n, p, batch = 65536, SOLINAS_P, 1024
     plan, ref = T.prime64.Plan.try_new(n, p), OraclePlan(64, n, p)
-    x = dev_rand_below(torch, p, (batch, n), 64, 21)
+    x = dev_rand_full64(torch, p, (batch, n), 21)
     y = x.clone()
     st = torch.cuda.current_stream()
     plan.fwd_device(y, stream=st)
     torch.cuda.synchronize()
-    for b in (0, 1023):
+    for b in (0, 1, 2, 511, 1022, 1023):
         assert (to_u(y[b], 64) == ref.fwd(to_u(x[b], 64))).all()
     plan.inv_device(y, stream=st)
     plan.normalize_device(y, stream=st)

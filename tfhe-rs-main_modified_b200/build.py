@@ -1,6 +1,6 @@
 """Builds libtfhe_ntt_b200.so (hand-written sm_100a CUDA + the C ABI) in-tree with nvcc.
 
-Usage: python build.py [--force]
+Usage: python build.py [--force] [--nvtx]
 The shared object is git-ignored but travels to the GPU box with the repo snapshot.
 """
 import os
@@ -41,8 +41,11 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, nvtx=False):
+    """nvtx=True (python build.py --nvtx): NVTX ranges around the host entry points (-DNTT_B200_NVTX)."""
     deps = _deps()
+    flags = NVCC_FLAGS + (["-DNTT_B200_NVTX"] if nvtx else [])
+    force = force or nvtx
     if not force and not _stale(OUT, deps):
         return OUT
     os.makedirs(OBJ_DIR, exist_ok=True)
@@ -52,7 +55,7 @@ def build(force=False, verbose=False):
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
         if force or _stale(obj, deps):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+            cmd = [nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
             if verbose:
                 print(" ".join(cmd))
             subprocess.run(cmd, check=True)
@@ -66,4 +69,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, nvtx="--nvtx" in sys.argv))

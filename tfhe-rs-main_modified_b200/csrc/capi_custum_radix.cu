@@ -246,16 +246,8 @@ void launch_fast_n(uint32_t* dev, size_t batch, const CrFast& m, uint32_t factor
     const unsigned per_cta = (unsigned)std::max<size_t>(1, std::min<size_t>(256 / tuples, batch));
     const unsigned threads = (unsigned)std::min<size_t>(1024, std::max<size_t>(32, per_cta * tuples));
     const size_t smem = (size_t)per_cta * (n + n / 8 + n / 64) * sizeof(uint32_t);
-    if (smem > 48 * 1024) {
-        static bool opted[64] = {};
-        int device = 0;
-        NTT_CUDA_CHECK(cudaGetDevice(&device));
-        if (!opted[device & 63]) {
-            NTT_CUDA_CHECK(cudaFuncSetAttribute(cr_fast_kernel<MODE, LOGN, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)smem));
-            opted[device & 63] = true;
-        }
-    }
+    // (smem is the same for every call of this instantiation that needs the opt-in: per_cta is 1 there)
+    allow_dynamic_smem<cr_fast_kernel<MODE, LOGN, PRE>>(smem);
     const size_t ctas = (batch + per_cta - 1) / per_cta;
     cr_fast_kernel<MODE, LOGN, PRE><<<(unsigned)ctas, threads, smem, st>>>(dev, batch, per_cta, m, factor);
 }
@@ -587,12 +579,8 @@ int run_stats(int kind, uint32_t* host, size_t n, size_t batch, const uint32_t* 
             }
         } buf{st};
         const size_t smem = (size_t)(logn + 1) * n * sizeof(uint32_t);
-        static bool opted[64] = {};
-        if (smem > 48 * 1024 && !opted[device & 63]) {
-            NTT_CUDA_CHECK(cudaFuncSetAttribute(cr_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)((kStatsLogMax + 1) * (sizeof(uint32_t) << kStatsLogMax))));
-            opted[device & 63] = true;
-        }
+        if (smem > 48 * 1024)
+            allow_dynamic_smem<cr_stats_kernel>((kStatsLogMax + 1) * (sizeof(uint32_t) << kStatsLogMax));
         const CrMod m{p, ~0ull / p + ((~0ull % p) + 1 == p ? 1 : 0)};
         const size_t chunk = std::min(batch, std::max<size_t>(1, (size_t(32) << 20) / (n * sizeof(uint32_t))));
         // counters (64-bit, first), vectors, table

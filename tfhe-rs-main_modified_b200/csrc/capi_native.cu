@@ -749,8 +749,8 @@ int ntt_b200_native_try_new(int kind, size_t n, ntt_b200_native_plan** out) {
     });
 }
 void ntt_b200_native_free(ntt_b200_native_plan* plan) { delete plan; }
-size_t ntt_b200_native_ntt_size(const ntt_b200_native_plan* plan) { return plan->n; }
-int ntt_b200_native_kind_of(const ntt_b200_native_plan* plan) { return plan->kind; }
+size_t ntt_b200_native_ntt_size(const ntt_b200_native_plan* plan) { return plan ? plan->n : 0; }
+int ntt_b200_native_kind_of(const ntt_b200_native_plan* plan) { return plan ? plan->kind : -1; }
 const void* ntt_b200_native_ntt_i(const ntt_b200_native_plan* plan, int i) {
     if (!plan || i < 0 || i >= plan->info.num_primes) return nullptr;
     return plan->info.residue_bytes == 4 ? (const void*)&plan->p32[i] : (const void*)&plan->p64[i];

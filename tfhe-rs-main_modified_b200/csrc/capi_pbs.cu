@@ -249,6 +249,14 @@ void make_twiddle_form(ntt_b200_bsk* key) {
 int check_key(const ntt_b200_bsk* key, int bnf, unsigned width) {
     if (!key) return NTT_B200_ERR_ARG;
     if (bnf && (width == 0 || width > 64)) return NTT_B200_ERR_ARG;
+    if (!bnf) {
+        // the classic decomposer keeps base_log * level bits of a ceil(log2 p)-bit value
+        // (init_state_non_native shifts by their difference; the reference's
+        // SignedDecomposerNonNative::new asserts the same bound, decomposer.rs:487-520)
+        const uint64_t p = key->plan->p;
+        const unsigned ceil_log2_p = 64 - (unsigned)__builtin_clzll(p - 1);
+        if ((uint64_t)key->base_log * key->level > ceil_log2_p) return NTT_B200_ERR_ARG;
+    }
     return NTT_B200_OK;
 }
 
@@ -260,6 +268,7 @@ int host_blind_rotate(const ntt_b200_bsk* key, const uint64_t* lwe, uint64_t* lu
                       unsigned width, int raw_bnf_input, int path) {
     // lut_inout != null: blind_rotate_*_assign (per-ciphertext lut, rotated in place);
     // else the PBS: accumulator[acc_count] -> lwe_out
+    NTT_NVTX("ntt_b200::host_blind_rotate / programmable_bootstrap");
     return guarded([&] {
         if (!batch) return NTT_B200_OK;
         const PrimePlan* pl = key->plan.get();
@@ -409,12 +418,12 @@ int ntt_b200_convert_standard_lwe_bootstrap_key_to_ntt64(const ntt_b200_plan64* 
 }
 
 void ntt_b200_bsk_free(ntt_b200_bsk* key) { delete key; }
-size_t ntt_b200_bsk_input_lwe_dimension(const ntt_b200_bsk* key) { return key->n_lwe; }
-size_t ntt_b200_bsk_glwe_size(const ntt_b200_bsk* key) { return key->glwe_size; }
-size_t ntt_b200_bsk_polynomial_size(const ntt_b200_bsk* key) { return key->plan->n; }
-uint32_t ntt_b200_bsk_decomposition_base_log(const ntt_b200_bsk* key) { return key->base_log; }
-uint32_t ntt_b200_bsk_decomposition_level_count(const ntt_b200_bsk* key) { return key->level; }
-const uint64_t* ntt_b200_bsk_device_data(const ntt_b200_bsk* key) { return key->d_bsk; }
+size_t ntt_b200_bsk_input_lwe_dimension(const ntt_b200_bsk* key) { return key ? key->n_lwe : 0; }
+size_t ntt_b200_bsk_glwe_size(const ntt_b200_bsk* key) { return key ? key->glwe_size : 0; }
+size_t ntt_b200_bsk_polynomial_size(const ntt_b200_bsk* key) { return key ? key->plan->n : 0; }
+uint32_t ntt_b200_bsk_decomposition_base_log(const ntt_b200_bsk* key) { return key ? key->base_log : 0; }
+uint32_t ntt_b200_bsk_decomposition_level_count(const ntt_b200_bsk* key) { return key ? key->level : 0; }
+const uint64_t* ntt_b200_bsk_device_data(const ntt_b200_bsk* key) { return key ? key->d_bsk : nullptr; }
 
 int ntt_b200_bsk_read(const ntt_b200_bsk* key, uint64_t* out, size_t len) {
     if (!key || !out) return NTT_B200_ERR_ARG;

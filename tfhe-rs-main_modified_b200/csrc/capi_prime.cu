@@ -71,21 +71,23 @@ int stream_count() {
 #define kChunkBytes chunk_bytes()
 #define kStreams stream_count()
 
-struct Stage {
-    cudaStream_t st = nullptr;
-    void* d = nullptr;
-};
-
 // Per-thread, per-device resources for the small host calls (the reference's per-polynomial Plan::fwd /
 // inv / normalize / mul_* on one slice): a stream, a device buffer and a pinned staging buffer that are
-// created once and reused, so a call is two memcpy's into / out of pinned memory, two async copies, the
-// kernel and one synchronise instead of a stream creation, stream-ordered allocations and pageable
-// copies (137 -> see tools/latency_bench.py).  Thread-local, so calls stay re-entrant on a shared plan;
-// never freed (a thread-exit destructor could run after the CUDA context is gone).
+// created once and reused.  Thread-local, so calls stay re-entrant on a shared plan; never freed (a
+// thread-exit destructor could run after the CUDA context is gone).
+//
+// Calls of at most kZeroCopyBytes whose transform is ONE kernel (n <= 4096) skip the device buffer and
+// both DMA copies: the pinned staging buffer is mapped into the device's address space (cudaMallocHost
+// under unified addressing), so the kernel reads the polynomial over PCIe with its first-pass loads and
+// writes the result back with its last-pass stores -- one launch and one wait per call
+// (profiles/r02_latency.txt).  Larger small calls (<= kSmallBytes) stage through the cached device buffer.
 struct SmallCtx {
     cudaStream_t st = nullptr;
     char *d = nullptr, *h = nullptr;
     size_t cap = 0;
+    // (a stream-ordered flag write + host spin instead of cudaStreamSynchronize was measured slower:
+    // 20.3 against 17.5 us per call, profiles/r02_latency.txt)
+    void wait_done() { NTT_CUDA_CHECK(cudaStreamSynchronize(st)); }
     void ensure(size_t bytes) {
         if (!st) NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         if (bytes <= cap) return;
@@ -99,34 +101,47 @@ struct SmallCtx {
         cap = want;
     }
 };
-constexpr size_t kSmallBytes = size_t(2) << 20;  // calls up to this size take the cached path
+constexpr size_t kSmallBytes = size_t(2) << 20;      // calls up to this size take the cached path
+constexpr size_t kZeroCopyBytes = size_t(64) << 10;  // ... and up to this size the mapped-pinned path
+bool zero_copy_enabled() {
+    static const bool v = [] {
+        const char* e = std::getenv("NTT_B200_ZERO_COPY");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
 SmallCtx& small_ctx(int device) {
-    thread_local SmallCtx ctx[16];
-    return ctx[device & 15];
+    thread_local std::vector<SmallCtx> ctx;
+    if ((size_t)device >= ctx.size()) ctx.resize((size_t)device + 1);
+    return ctx[device];
 }
 
 int host_transform_small(const PrimePlan* pl, void* host, size_t batch, bool inverse) {
+    NTT_NVTX("ntt_b200::host_transform_small");
     return guarded([&] {
         DeviceGuard g(pl->device);
         const size_t bytes = batch * pl->n * (size_t)pl->elem_bytes;
         SmallCtx& c = small_ctx(pl->device);
         c.ensure(bytes);
         std::memcpy(c.h, host, bytes);
-        NTT_CUDA_CHECK(cudaMemcpyAsync(c.d, c.h, bytes, cudaMemcpyHostToDevice, c.st));
+        const bool mapped = zero_copy_enabled() && bytes <= kZeroCopyBytes && pl->logn <= 12;
+        char* data = mapped ? c.h : c.d;
+        if (!mapped) NTT_CUDA_CHECK(cudaMemcpyAsync(c.d, c.h, bytes, cudaMemcpyHostToDevice, c.st));
         if (inverse)
-            pl->inv(c.d, batch, c.st);
+            pl->inv(data, batch, c.st);
         else
-            pl->fwd(c.d, batch, c.st);
-        NTT_CUDA_CHECK(cudaMemcpyAsync(c.h, c.d, bytes, cudaMemcpyDeviceToHost, c.st));
-        NTT_CUDA_CHECK(cudaStreamSynchronize(c.st));
+            pl->fwd(data, batch, c.st);
+        if (!mapped) NTT_CUDA_CHECK(cudaMemcpyAsync(c.h, c.d, bytes, cudaMemcpyDeviceToHost, c.st));
+        c.wait_done();
         std::memcpy(host, c.h, bytes);
         return NTT_B200_OK;
     });
 }
 
 int host_transform(const PrimePlan* pl, void* host, size_t batch, bool inverse) {
-    if (batch && pl->device < 16 && batch * pl->n * (size_t)pl->elem_bytes <= kSmallBytes)
+    if (batch && batch * pl->n * (size_t)pl->elem_bytes <= kSmallBytes)
         return host_transform_small(pl, host, batch, inverse);
+    NTT_NVTX("ntt_b200::host_transform (chunked H2D / kernel / D2H pipeline)");
     return guarded([&] {
         if (!batch) return NTT_B200_OK;
         DeviceGuard g(pl->device);
@@ -136,28 +151,27 @@ int host_transform(const PrimePlan* pl, void* host, size_t batch, bool inverse) 
         chunk_polys = std::min(chunk_polys, batch);
         size_t nchunks = (batch + chunk_polys - 1) / chunk_polys;
         int ns = (int)std::min<size_t>(kStreams, nchunks);
-        Stage sg[kMaxStreams];
+        ScopedStream sg[kMaxStreams];  // synchronised and destroyed on every exit path
+        void* dbuf[kMaxStreams] = {};
         for (int i = 0; i < ns; ++i) {
-            NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&sg[i].st, cudaStreamNonBlocking));
-            NTT_CUDA_CHECK(cudaMallocAsync(&sg[i].d, chunk_polys * poly_bytes, sg[i].st));
+            sg[i].open();
+            dbuf[i] = sg[i].alloc(chunk_polys * poly_bytes);
         }
         for (size_t c = 0; c < nchunks; ++c) {
-            Stage& s = sg[c % ns];
+            int i = (int)(c % ns);
             size_t b0 = c * chunk_polys, nb = std::min(chunk_polys, batch - b0);
             char* h = static_cast<char*>(host) + b0 * poly_bytes;
-            NTT_CUDA_CHECK(cudaMemcpyAsync(s.d, h, nb * poly_bytes, cudaMemcpyHostToDevice, s.st));
+            NTT_CUDA_CHECK(cudaMemcpyAsync(dbuf[i], h, nb * poly_bytes, cudaMemcpyHostToDevice, sg[i].st));
             if (inverse)
-                pl->inv(s.d, nb, s.st);
+                pl->inv(dbuf[i], nb, sg[i].st);
             else
-                pl->fwd(s.d, nb, s.st);
-            NTT_CUDA_CHECK(cudaMemcpyAsync(h, s.d, nb * poly_bytes, cudaMemcpyDeviceToHost, s.st));
+                pl->fwd(dbuf[i], nb, sg[i].st);
+            NTT_CUDA_CHECK(cudaMemcpyAsync(h, dbuf[i], nb * poly_bytes, cudaMemcpyDeviceToHost, sg[i].st));
         }
         cudaError_t first = cudaSuccess;
         for (int i = 0; i < ns; ++i) {
-            cudaFreeAsync(sg[i].d, sg[i].st);
-            cudaError_t e = cudaStreamSynchronize(sg[i].st);
+            cudaError_t e = sg[i].finish();
             if (first == cudaSuccess) first = e;
-            cudaStreamDestroy(sg[i].st);
         }
         NTT_CUDA_CHECK(first);
         return NTT_B200_OK;
@@ -208,12 +222,14 @@ int host_pointwise_small(const PrimePlan* pl, int op, void* dst, size_t len, con
         std::memcpy(c.h, dst, len * eb);
         if (a) std::memcpy(c.h + o_a, a, a_len * eb);
         if (b) std::memcpy(c.h + o_b, b, b_len * eb);
-        NTT_CUDA_CHECK(cudaMemcpyAsync(c.d, c.h, total, cudaMemcpyHostToDevice, c.st));
-        if (op == 0) pl->normalize(c.d, len, c.st);
-        if (op == 1) pl->mul_assign_normalize(c.d, c.d + o_a, len, a_len, c.st);
-        if (op == 2) pl->mul_accumulate(c.d, c.d + o_a, c.d + o_b, len, a_len, b_len, c.st);
-        NTT_CUDA_CHECK(cudaMemcpyAsync(c.h, c.d, len * eb, cudaMemcpyDeviceToHost, c.st));
-        NTT_CUDA_CHECK(cudaStreamSynchronize(c.st));
+        const bool mapped = zero_copy_enabled() && total <= kZeroCopyBytes;
+        char* w = mapped ? c.h : c.d;  // the kernels read and write the mapped pinned buffer directly
+        if (!mapped) NTT_CUDA_CHECK(cudaMemcpyAsync(c.d, c.h, total, cudaMemcpyHostToDevice, c.st));
+        if (op == 0) pl->normalize(w, len, c.st);
+        if (op == 1) pl->mul_assign_normalize(w, w + o_a, len, a_len, c.st);
+        if (op == 2) pl->mul_accumulate(w, w + o_a, w + o_b, len, a_len, b_len, c.st);
+        if (!mapped) NTT_CUDA_CHECK(cudaMemcpyAsync(c.h, c.d, len * eb, cudaMemcpyDeviceToHost, c.st));
+        c.wait_done();
         std::memcpy(dst, c.h, len * eb);
         return NTT_B200_OK;
     });
@@ -221,40 +237,36 @@ int host_pointwise_small(const PrimePlan* pl, int op, void* dst, size_t len, con
 
 int host_pointwise(const PrimePlan* pl, int op, void* dst, size_t len, const void* a, size_t a_len,
                    const void* b, size_t b_len) {
-    if (len && pl->device < 16 && (len + a_len + b_len) * (size_t)pl->elem_bytes + 64 <= kSmallBytes)
+    if (len && (len + a_len + b_len) * (size_t)pl->elem_bytes + 64 <= kSmallBytes)
         return host_pointwise_small(pl, op, dst, len, a, a ? a_len : 0, b, b ? b_len : 0);
     return guarded([&] {
         if (!len) return NTT_B200_OK;
         DeviceGuard g(pl->device);
         keep_pool_cached(pl->device);
         size_t eb = (size_t)pl->elem_bytes;
-        cudaStream_t st;
-        NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        void *dd = nullptr, *da = nullptr, *db = nullptr;
-        auto up = [&](void** d, const void* h, size_t n) {
-            NTT_CUDA_CHECK(cudaMallocAsync(d, n * eb, st));
-            NTT_CUDA_CHECK(cudaMemcpyAsync(*d, h, n * eb, cudaMemcpyHostToDevice, st));
+        ScopedStream s;
+        s.open();
+        auto up = [&](const void* h, size_t n) {
+            void* d = s.alloc(n * eb);
+            NTT_CUDA_CHECK(cudaMemcpyAsync(d, h, n * eb, cudaMemcpyHostToDevice, s.st));
+            return d;
         };
-        up(&dd, dst, len);
-        if (a) up(&da, a, a_len);
-        if (b) up(&db, b, b_len);
-        if (op == 0) pl->normalize(dd, len, st);
-        if (op == 1) pl->mul_assign_normalize(dd, da, len, a_len, st);
-        if (op == 2) pl->mul_accumulate(dd, da, db, len, a_len, b_len, st);
-        NTT_CUDA_CHECK(cudaMemcpyAsync(dst, dd, len * eb, cudaMemcpyDeviceToHost, st));
-        cudaFreeAsync(dd, st);
-        if (da) cudaFreeAsync(da, st);
-        if (db) cudaFreeAsync(db, st);
-        cudaError_t e = cudaStreamSynchronize(st);
-        cudaStreamDestroy(st);
-        NTT_CUDA_CHECK(e);
+        void* dd = up(dst, len);
+        void* da = a ? up(a, a_len) : nullptr;
+        void* db = b ? up(b, b_len) : nullptr;
+        if (op == 0) pl->normalize(dd, len, s.st);
+        if (op == 1) pl->mul_assign_normalize(dd, da, len, a_len, s.st);
+        if (op == 2) pl->mul_accumulate(dd, da, db, len, a_len, b_len, s.st);
+        NTT_CUDA_CHECK(cudaMemcpyAsync(dst, dd, len * eb, cudaMemcpyDeviceToHost, s.st));
+        NTT_CUDA_CHECK(s.finish());
         return NTT_B200_OK;
     });
 }
 
-// out = inv(acc + fwd(lhs) * rhs) for host operands, chunked and pipelined on three streams
+// out = inv(acc + fwd(lhs) * rhs) for host operands, chunked and pipelined on several streams
 int host_fwd_mac_inv(const PrimePlan* pl, void* out, const void* lhs, const void* rhs, size_t rhs_polys,
                      const void* acc, size_t acc_polys, size_t batch) {
+    NTT_NVTX("ntt_b200::host_fwd_mac_inv (chunked pipeline)");
     return guarded([&] {
         if (!batch) return NTT_B200_OK;
         DeviceGuard g(pl->device);
@@ -278,40 +290,41 @@ int host_fwd_mac_inv(const PrimePlan* pl, void* out, const void* lhs, const void
         chunk = std::min(chunk, batch);
         size_t nchunks = (batch + chunk - 1) / chunk;
         int ns = (int)std::min<size_t>(kStreams, nchunks);
-        cudaStream_t st[kMaxStreams] = {};
+        ScopedEvent shared_ready;      // declared before the streams: destroyed after they are drained
+        ScopedStream sg[kMaxStreams];  // synchronised and destroyed on every exit path
         void *d_io[kMaxStreams] = {}, *d_rhs[kMaxStreams] = {}, *d_acc[kMaxStreams] = {};
         void *d_rhs_shared = nullptr, *d_acc_shared = nullptr;
-        cudaEvent_t shared_ready = nullptr;
         for (int i = 0; i < ns; ++i) {
-            NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-            NTT_CUDA_CHECK(cudaMallocAsync(&d_io[i], chunk * pb, st[i]));
-            if (!rhs_shared) NTT_CUDA_CHECK(cudaMallocAsync(&d_rhs[i], chunk * pb, st[i]));
-            if (acc && !acc_shared) NTT_CUDA_CHECK(cudaMallocAsync(&d_acc[i], chunk * pb, st[i]));
+            sg[i].open();
+            d_io[i] = sg[i].alloc(chunk * pb);
+            if (!rhs_shared) d_rhs[i] = sg[i].alloc(chunk * pb);
+            if (acc && !acc_shared) d_acc[i] = sg[i].alloc(chunk * pb);
         }
         if (rhs_shared || acc_shared) {
-            NTT_CUDA_CHECK(cudaEventCreateWithFlags(&shared_ready, cudaEventDisableTiming));
+            shared_ready.create();
             if (rhs_shared) {
-                NTT_CUDA_CHECK(cudaMallocAsync(&d_rhs_shared, rhs_polys * pb, st[0]));
-                NTT_CUDA_CHECK(cudaMemcpyAsync(d_rhs_shared, rhs, rhs_polys * pb, cudaMemcpyHostToDevice, st[0]));
+                d_rhs_shared = sg[0].alloc(rhs_polys * pb);
+                NTT_CUDA_CHECK(cudaMemcpyAsync(d_rhs_shared, rhs, rhs_polys * pb, cudaMemcpyHostToDevice, sg[0].st));
             }
             if (acc_shared) {
-                NTT_CUDA_CHECK(cudaMallocAsync(&d_acc_shared, acc_polys * pb, st[0]));
-                NTT_CUDA_CHECK(cudaMemcpyAsync(d_acc_shared, acc, acc_polys * pb, cudaMemcpyHostToDevice, st[0]));
+                d_acc_shared = sg[0].alloc(acc_polys * pb);
+                NTT_CUDA_CHECK(cudaMemcpyAsync(d_acc_shared, acc, acc_polys * pb, cudaMemcpyHostToDevice, sg[0].st));
             }
-            NTT_CUDA_CHECK(cudaEventRecord(shared_ready, st[0]));
-            for (int i = 1; i < ns; ++i) NTT_CUDA_CHECK(cudaStreamWaitEvent(st[i], shared_ready, 0));
+            NTT_CUDA_CHECK(cudaEventRecord(shared_ready.ev, sg[0].st));
+            for (int i = 1; i < ns; ++i) NTT_CUDA_CHECK(cudaStreamWaitEvent(sg[i].st, shared_ready.ev, 0));
         }
         for (size_t c = 0; c < nchunks; ++c) {
             int i = (int)(c % ns);
+            cudaStream_t st = sg[i].st;
             size_t b0 = c * chunk, nb = std::min(chunk, batch - b0);
             const char* hl = static_cast<const char*>(lhs) + b0 * pb;
             char* ho = static_cast<char*>(out) + b0 * pb;
-            NTT_CUDA_CHECK(cudaMemcpyAsync(d_io[i], hl, nb * pb, cudaMemcpyHostToDevice, st[i]));
+            NTT_CUDA_CHECK(cudaMemcpyAsync(d_io[i], hl, nb * pb, cudaMemcpyHostToDevice, st));
             const void* r = d_rhs_shared;
             size_t rp = rhs_polys;
             if (!rhs_shared) {
                 NTT_CUDA_CHECK(cudaMemcpyAsync(d_rhs[i], static_cast<const char*>(rhs) + b0 * pb, nb * pb,
-                                               cudaMemcpyHostToDevice, st[i]));
+                                               cudaMemcpyHostToDevice, st));
                 r = d_rhs[i];
                 rp = nb;
             }
@@ -322,31 +335,20 @@ int host_fwd_mac_inv(const PrimePlan* pl, void* out, const void* lhs, const void
                 ap = acc_polys;
                 if (!acc_shared) {
                     NTT_CUDA_CHECK(cudaMemcpyAsync(d_acc[i], static_cast<const char*>(acc) + b0 * pb, nb * pb,
-                                                   cudaMemcpyHostToDevice, st[i]));
+                                                   cudaMemcpyHostToDevice, st));
                     a = d_acc[i];
                     ap = nb;
                 }
             }
-            pl->fwd_mac_inv(d_io[i], d_io[i], r, rp, a, ap, nb, st[i]);
-            NTT_CUDA_CHECK(cudaMemcpyAsync(ho, d_io[i], nb * pb, cudaMemcpyDeviceToHost, st[i]));
+            pl->fwd_mac_inv(d_io[i], d_io[i], r, rp, a, ap, nb, st);
+            NTT_CUDA_CHECK(cudaMemcpyAsync(ho, d_io[i], nb * pb, cudaMemcpyDeviceToHost, st));
         }
+        // the shared operands live in stream 0's pool: every other stream finishes first
         cudaError_t first = cudaSuccess;
-        for (int i = 0; i < ns; ++i) {
-            cudaError_t e = cudaStreamSynchronize(st[i]);
+        for (int i = ns - 1; i >= 0; --i) {
+            cudaError_t e = sg[i].finish();
             if (first == cudaSuccess) first = e;
         }
-        for (int i = 0; i < ns; ++i) {
-            cudaFreeAsync(d_io[i], st[i]);
-            if (d_rhs[i]) cudaFreeAsync(d_rhs[i], st[i]);
-            if (d_acc[i]) cudaFreeAsync(d_acc[i], st[i]);
-        }
-        if (d_rhs_shared) cudaFreeAsync(d_rhs_shared, st[0]);
-        if (d_acc_shared) cudaFreeAsync(d_acc_shared, st[0]);
-        for (int i = 0; i < ns; ++i) {
-            cudaStreamSynchronize(st[i]);
-            cudaStreamDestroy(st[i]);
-        }
-        if (shared_ready) cudaEventDestroy(shared_ready);
         NTT_CUDA_CHECK(first);
         return NTT_B200_OK;
     });
@@ -461,18 +463,25 @@ int ntt64_add_backward_dev(const PrimePlan* pl, uint64_t* standard, uint64_t* nt
     }                                                                                              \
     int ntt_b200_plan##SFX##_clone(const ntt_b200_plan##SFX* plan, ntt_b200_plan##SFX** out) {     \
         if (!plan || !out) return NTT_B200_ERR_ARG;                                                \
-        *out = new ntt_b200_plan##SFX{plan->impl->clone()};                                        \
-        return NTT_B200_OK;                                                                        \
+        *out = nullptr;                                                                            \
+        return guarded([&] {                                                                       \
+            *out = new ntt_b200_plan##SFX{plan->impl->clone()};                                    \
+            return NTT_B200_OK;                                                                    \
+        });                                                                                        \
     }                                                                                              \
     void ntt_b200_plan##SFX##_free(ntt_b200_plan##SFX* plan) { delete plan; }                      \
-    size_t ntt_b200_plan##SFX##_ntt_size(const ntt_b200_plan##SFX* plan) { return plan->impl->n; } \
+    size_t ntt_b200_plan##SFX##_ntt_size(const ntt_b200_plan##SFX* plan) {                         \
+        return plan ? plan->impl->n : 0; /* a null handle reads as the empty plan */               \
+    }                                                                                              \
     ELEM ntt_b200_plan##SFX##_modulus(const ntt_b200_plan##SFX* plan) {                            \
-        return (ELEM)plan->impl->p;                                                                \
+        return plan ? (ELEM)plan->impl->p : (ELEM)0;                                               \
     }                                                                                              \
     int ntt_b200_plan##SFX##_can_use_fast_reduction_code(const ntt_b200_plan##SFX* plan) {         \
-        return plan->impl->can_use_fast_reduction_code ? 1 : 0;                                    \
+        return plan && plan->impl->can_use_fast_reduction_code ? 1 : 0;                            \
     }                                                                                              \
-    int ntt_b200_plan##SFX##_device(const ntt_b200_plan##SFX* plan) { return plan->impl->device; } \
+    int ntt_b200_plan##SFX##_device(const ntt_b200_plan##SFX* plan) {                              \
+        return plan ? plan->impl->device : -1;                                                     \
+    }                                                                                              \
     int ntt_b200_plan##SFX##_fwd(const ntt_b200_plan##SFX* plan, ELEM* buf, size_t len) {          \
         if (!plan || !buf) return NTT_B200_ERR_ARG;                                                \
         if (len != plan->impl->n) return NTT_B200_ERR_LEN;                                         \
@@ -635,19 +644,15 @@ int ntt_b200_ntt64_forward(const ntt_b200_plan64* plan, uint64_t* ntt, const uin
     int g = guarded([&] {
         DeviceGuard dg(plan->impl->device);
         keep_pool_cached(plan->impl->device);
-        cudaStream_t st;
-        NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        uint64_t *ds = nullptr, *dn = nullptr;
-        NTT_CUDA_CHECK(cudaMallocAsync(&ds, len * 8, st));
-        NTT_CUDA_CHECK(cudaMallocAsync(&dn, len * 8, st));
+        ScopedStream s;  // drained and destroyed on every exit path
+        s.open();
+        cudaStream_t st = s.st;
+        uint64_t* ds = static_cast<uint64_t*>(s.alloc(len * 8));
+        uint64_t* dn = static_cast<uint64_t*>(s.alloc(len * 8));
         NTT_CUDA_CHECK(cudaMemcpyAsync(ds, standard, len * 8, cudaMemcpyHostToDevice, st));
         rc = ntt64_forward_dev(plan->impl.get(), dn, ds, len / n, mode, width, st);
         NTT_CUDA_CHECK(cudaMemcpyAsync(ntt, dn, len * 8, cudaMemcpyDeviceToHost, st));
-        cudaFreeAsync(ds, st);
-        cudaFreeAsync(dn, st);
-        cudaError_t e = cudaStreamSynchronize(st);
-        cudaStreamDestroy(st);
-        NTT_CUDA_CHECK(e);
+        NTT_CUDA_CHECK(s.finish());
         return NTT_B200_OK;
     });
     return g != NTT_B200_OK ? g : rc;
@@ -661,21 +666,17 @@ int ntt_b200_ntt64_add_backward(const ntt_b200_plan64* plan, uint64_t* standard,
     int g = guarded([&] {
         DeviceGuard dg(plan->impl->device);
         keep_pool_cached(plan->impl->device);
-        cudaStream_t st;
-        NTT_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        uint64_t *ds = nullptr, *dn = nullptr;
-        NTT_CUDA_CHECK(cudaMallocAsync(&ds, len * 8, st));
-        NTT_CUDA_CHECK(cudaMallocAsync(&dn, len * 8, st));
+        ScopedStream s;  // drained and destroyed on every exit path
+        s.open();
+        cudaStream_t st = s.st;
+        uint64_t* ds = static_cast<uint64_t*>(s.alloc(len * 8));
+        uint64_t* dn = static_cast<uint64_t*>(s.alloc(len * 8));
         NTT_CUDA_CHECK(cudaMemcpyAsync(ds, standard, len * 8, cudaMemcpyHostToDevice, st));
         NTT_CUDA_CHECK(cudaMemcpyAsync(dn, ntt, len * 8, cudaMemcpyHostToDevice, st));
         rc = ntt64_add_backward_dev(plan->impl.get(), ds, dn, len / n, mode, width, st);
         NTT_CUDA_CHECK(cudaMemcpyAsync(standard, ds, len * 8, cudaMemcpyDeviceToHost, st));
         NTT_CUDA_CHECK(cudaMemcpyAsync(ntt, dn, len * 8, cudaMemcpyDeviceToHost, st));
-        cudaFreeAsync(ds, st);
-        cudaFreeAsync(dn, st);
-        cudaError_t e = cudaStreamSynchronize(st);
-        cudaStreamDestroy(st);
-        NTT_CUDA_CHECK(e);
+        NTT_CUDA_CHECK(s.finish());
         return NTT_B200_OK;
     });
     return g != NTT_B200_OK ? g : rc;

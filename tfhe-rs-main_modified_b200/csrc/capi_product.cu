@@ -256,8 +256,8 @@ int ntt_b200_product_try_new(size_t n, uint64_t modulus, const uint64_t* factors
     });
 }
 void ntt_b200_product_free(ntt_b200_product_plan* plan) { delete plan; }
-size_t ntt_b200_product_ntt_size(const ntt_b200_product_plan* plan) { return plan->n; }
-uint64_t ntt_b200_product_modulus(const ntt_b200_product_plan* plan) { return plan->modulus; }
+size_t ntt_b200_product_ntt_size(const ntt_b200_product_plan* plan) { return plan ? plan->n : 0; }
+uint64_t ntt_b200_product_modulus(const ntt_b200_product_plan* plan) { return plan ? plan->modulus : 0; }
 size_t ntt_b200_product_ntt_domain_len(const ntt_b200_product_plan* plan) { return plan->domain_len(); }
 
 int ntt_b200_product_fwd_device(const ntt_b200_product_plan* plan, uint64_t* ntt, const uint64_t* standard,

@@ -255,11 +255,7 @@ struct PlanImpl final : PrimePlan {
         if (!aligned16(data) || logn - stage - R < 8 || !tma_pass_enabled()) return false;
         auto kern = ntt_global_pass_tma_kernel<A, R, INV>;
         constexpr size_t smem = global_pass_tma_smem<A, R>();
-        static bool allowed[64] = {};
-        if (device >= 0 && device < 64 && !allowed[device]) {
-            NTT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            allowed[device] = true;
-        }
+        allow_dynamic_smem<ntt_global_pass_tma_kernel<A, R, INV>>(smem);
         const unsigned log_tiles_per_poly = (unsigned)(logn - R - 8);
         const size_t tiles = batch << log_tiles_per_poly;
         const size_t per_sm = std::min<size_t>(3, (size_t(200) << 10) / smem);
@@ -286,6 +282,7 @@ struct PlanImpl final : PrimePlan {
     // (profiles/r01_large_n_cluster.txt): against a radix-2/4 pass + 4096-point kernel they gain 21 % at 2^13
     // and 4..15 % at 2^14 (u64), but the TMA-staged radix-16 pass + 512/1024-point kernels is faster still
     // (profiles/r01_large_n_depth.txt); with 512- and 1024-thread CTAs (2^15, 2^16) too few clusters are resident.
+    static bool fast_sized(int log_sub) { return log_sub >= kFastMinLog && log_sub <= kFastMaxLog; }
     static bool cluster_sized(int logn) { return sizeof(T) == 8 && (logn == 13 || logn == 14); }
     // Number of top stages run as strided passes before the single-CTA kernel takes the 2^(logn - depth)
     // point sub-blocks.  NTT_B200_DEPTH=k overrides it (A/B measurements).
@@ -316,6 +313,7 @@ struct PlanImpl final : PrimePlan {
 
     void fwd(void* data, size_t batch, cudaStream_t st) const override {
         if (!batch) return;
+        NTT_NVTX("ntt_b200::Plan::fwd");
         DeviceGuard g(device);
         T* d = static_cast<T*>(data);
         const bool fast_ok = aligned16(d) && logn >= kFastMinLog;
@@ -323,10 +321,14 @@ struct PlanImpl final : PrimePlan {
         if (fast_ok && cluster_sized(logn) && cluster_path_enabled() &&
             fast_cluster_fwd<A>(d, batch, logn, d_fwd.get(), ctx, st))
             return;
-        if (fast_ok) {
+        if (fast_ok && fast_sized(logn - fast_depth())) {
+            // decided before any pass is launched: once the strided passes have run, only the fast kernel
+            // for the remaining sub-blocks can finish the transform
             int depth = fast_depth();
             for (auto [s, r] : global_groups(depth)) launch_global_r<false>(r, d, batch, s, 0, st);
-            if (fast_fwd<A>(d, batch << depth, logn - depth, (unsigned)depth, d_fwd.get(), ctx, st)) return;
+            if (!fast_fwd<A>(d, batch << depth, logn - depth, (unsigned)depth, d_fwd.get(), ctx, st))
+                throw CudaError("no fast forward kernel for this size");
+            return;
         }
         // small or unaligned: generic rows kernel (n <= 2^14 / 2^15 in one CTA)
         int depth = std::max(0, logn - kMaxLogRow);
@@ -335,14 +337,16 @@ struct PlanImpl final : PrimePlan {
     }
     void inv(void* data, size_t batch, cudaStream_t st) const override {
         if (!batch) return;
+        NTT_NVTX("ntt_b200::Plan::inv");
         DeviceGuard g(device);
         T* d = static_cast<T*>(data);
         const bool fast_ok = aligned16(d) && logn >= kFastMinLog;
         if (fast_ok && cluster_sized(logn) && cluster_path_enabled() &&
             fast_cluster_inv<A>(d, batch, logn, d_inv.get(), ctx, st))
             return;
-        int depth = fast_ok ? fast_depth() : std::max(0, logn - kMaxLogRow);
-        if (fast_ok) {
+        const bool use_fast = fast_ok && fast_sized(logn - fast_depth());
+        int depth = use_fast ? fast_depth() : std::max(0, logn - kMaxLogRow);
+        if (use_fast) {
             bool ok = fast_inv<A>(d, batch << depth, logn - depth, (unsigned)depth, d_inv.get(), ctx, st);
             if (!ok) throw CudaError("no fast inverse kernel for this size");
         } else {
@@ -400,6 +404,7 @@ struct PlanImpl final : PrimePlan {
     void ext_product(void* out, const void* in, const void* ggsw, unsigned rows, unsigned cols,
                      size_t batch, cudaStream_t st) const override {
         if (!batch || !rows || !cols) return;
+        NTT_NVTX("ntt_b200::Plan::ext_product");
         DeviceGuard g(device);
         if (aligned16(out) && aligned16(in) && aligned16(ggsw) &&
             fast_ext_product<A>(static_cast<T*>(out), static_cast<const T*>(in),
@@ -434,6 +439,7 @@ struct PlanImpl final : PrimePlan {
                      const void* acc, size_t acc_polys, size_t batch,
                      cudaStream_t st) const override {
         if (!batch) return;
+        NTT_NVTX("ntt_b200::Plan::fwd_mac_inv");
         DeviceGuard g(device);
         size_t total = batch * n;
         if (aligned16(out) && aligned16(lhs) && aligned16(rhs) && aligned16(acc) &&

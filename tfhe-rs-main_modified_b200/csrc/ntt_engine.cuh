@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
@@ -90,6 +91,42 @@ struct PrimePlan {
 // nullptr <=> the reference's try_new returns None.  Throws CudaError on CUDA failures.
 std::shared_ptr<PrimePlan> make_plan64(size_t n, uint64_t p);
 std::shared_ptr<PrimePlan> make_plan32(size_t n, uint32_t p);
+
+// Profiling ranges (the reference's CUDA backend convention: PUSH_RANGE / POP_RANGE around every host
+// entry, backends/tfhe-cuda-backend/cuda/src/utils/helper_profile.cu:15-41).  Compiled in with
+// -DNTT_B200_NVTX (python build.py --nvtx); header-only NVTX v3, no extra library.  Off by default.
+#ifdef NTT_B200_NVTX
+}  // namespace nttb200
+#include <nvtx3/nvToolsExt.h>
+namespace nttb200 {
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define NTT_NVTX_CAT2(a, b) a##b
+#define NTT_NVTX_CAT(a, b) NTT_NVTX_CAT2(a, b)
+#define NTT_NVTX(name) ::nttb200::NvtxRange NTT_NVTX_CAT(nvtx_range_, __LINE__)(name)
+#else
+#define NTT_NVTX(name) ((void)0)
+#endif
+
+// Kernels that need more than the default 48 KiB of dynamic shared memory opt in once per device
+// (the kernel is a template argument so that the flags are per kernel, not per signature).  The flags
+// are shared by concurrent host threads: atomics, and a device index beyond the table simply sets the
+// attribute on every call (it is idempotent and cheap).
+template <auto Kernel>
+void allow_dynamic_smem(size_t bytes) {
+    if (bytes <= 48 * 1024) return;
+    static std::atomic<bool> done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && done[dev].load(std::memory_order_acquire)) return;
+    NTT_CUDA_CHECK(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (tracked) done[dev].store(true, std::memory_order_release);
+}
 
 // RAII device scope
 struct DeviceGuard {

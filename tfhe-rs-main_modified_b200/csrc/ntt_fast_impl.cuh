@@ -32,17 +32,9 @@ template <class A, int LOGN, int PPT>
 constexpr size_t fast_smem_bytes() {
     return (size_t)FastPolys<LOGN>::value * PPT * FastShape<LOGN>::kPaddedElems * sizeof(typename A::T);
 }
-// Kernels that need more than the default 48 KiB of dynamic shared memory opt in once per device.
-// (the kernel is a template argument so that the "done" flags are per kernel, not per signature)
 template <auto Kernel>
 void fast_allow_smem(size_t bytes) {
-    if (bytes <= 48 * 1024) return;
-    static bool done[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && done[dev]) return;
-    NTT_CUDA_CHECK(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    if (dev >= 0 && dev < 64) done[dev] = true;
+    allow_dynamic_smem<Kernel>(bytes);
 }
 
 template <class A, int LOGN, int PPT>
