@@ -54,9 +54,12 @@ struct FastShape {
 // per SM hide the load phase of one CTA behind the butterflies of the others.  32-bit families need
 // 40-48 registers, so they are given 1536 threads per SM (six 256-thread CTAs; measured +8 % at
 // n = 2048); the exact path for p >= 2^31 spills there and keeps 1024.
-template <class A, int THREADS>
+template <class A, int THREADS, int PPT = 2>
 struct FastMinBlocks {
-    static constexpr int kThreadsPerSM = (sizeof(typename A::T) == 4 && !std::is_same<A, Wide32>::value) ? NTT_FAST_U32_THREADS_PER_SM : 1024;
+    // (u32, four polynomials per thread: 72 registers, three 256-thread CTAs per SM measured best,
+    // profiles/r02_u32_kernel_variants.txt)
+    static constexpr bool kU32 = sizeof(typename A::T) == 4 && !std::is_same<A, Wide32>::value;
+    static constexpr int kThreadsPerSM = kU32 ? (PPT <= 2 ? NTT_FAST_U32_THREADS_PER_SM : 768) : 1024;
     static constexpr int value = kThreadsPerSM / THREADS > 0 ? kThreadsPerSM / THREADS : 1;
 };
 
@@ -77,10 +80,10 @@ struct FastPairLoads {
     static constexpr bool value = INV || LOGN <= 11;
 };
 
-// 16 bytes of padding after every 128 bytes: u64 -> a + 2*(a>>4), u32 -> a + 4*(a>>5)
+// 16 bytes of padding after every 128 bytes: u64 -> a + 2*(a>>4), u32 -> a + 4*(a>>5), 16-byte slots -> a + (a>>3)
 template <class T>
 NTT_DEVINL constexpr unsigned pad_index(unsigned a) {
-    return sizeof(T) == 8 ? a + 2u * (a >> 4) : a + 4u * (a >> 5);
+    return sizeof(T) == 16 ? a + (a >> 3) : sizeof(T) == 8 ? a + 2u * (a >> 4) : a + 4u * (a >> 5);
 }
 
 // Tuple addressing.  A radix-8 tuple's base is i*(8*t2) + j with j < t2; when 8*t2 is a multiple of
@@ -230,8 +233,88 @@ NTT_DEVINL void store8_consecutive(T* __restrict__ g, const T (&x)[8]) {
 }
 
 // Core transform of PPT polynomials by N/8 cooperating threads.  `t` = thread index within the
-// polynomial, `s` = padded shared-memory tiles (PPT consecutive tiles of kPaddedElems).  Within a
-// pass every thread loads and stores the same 8 positions, so one CTA barrier per pass is enough.
+// polynomial, `s` = the exchange tile (PPT * kPaddedElems elements; its inner layout is private to
+// these two functions).  Within a pass every thread loads and stores the same 8 positions, so one CTA
+// barrier per pass is enough.
+//
+// Tile layout.  64-bit elements, or one polynomial per thread: PPT consecutive padded tiles.  Two
+// 32-bit polynomials per thread: ONE tile of 64-bit slots, slot e = (poly0[e], poly1[e]), padded like a
+// u64 polynomial -- every pass moves both polynomials with one LDS.64 / STS.64 per position instead of
+// two 32-bit accesses (half the shared-memory instructions of the u32 kernels, same bank behaviour as
+// the u64 kernels), and the last pass reads 8 consecutive slots with four LDS.128.
+// Four 32-bit polynomials per thread: one tile of 16-byte slots (poly0[e] .. poly3[e]), one LDS.128 /
+// STS.128 per position; with one slot of padding per eight slots the radix-8 passes (slot strides n/8,
+// n/64, 4) and the last pass (eight consecutive slots per thread, one 128-bit access each) are free of
+// bank conflicts per quarter warp.
+template <class T, int PPT>
+struct TileLayout {
+    static constexpr bool kPaired = sizeof(T) == 4 && PPT == 2;
+    static constexpr bool kQuad = sizeof(T) == 4 && PPT == 4;
+    using Slot = typename std::conditional<kQuad, uint4, typename std::conditional<kPaired, uint64_t, T>::type>::type;
+};
+template <class T, int PPT, int PADDED>
+NTT_DEVINL void tile_load(const T* s, unsigned off, T (&x)[PPT][8], int k) {
+    if constexpr (TileLayout<T, PPT>::kQuad) {
+        uint4 v = reinterpret_cast<const uint4*>(s)[off];
+        x[0][k] = v.x, x[1][k] = v.y, x[2][k] = v.z, x[3][k] = v.w;
+    } else if constexpr (TileLayout<T, PPT>::kPaired) {
+        uint2 v = reinterpret_cast<const uint2*>(s)[off];
+        x[0][k] = v.x;
+        x[1][k] = v.y;
+    } else {
+#pragma unroll
+        for (int pp = 0; pp < PPT; ++pp) x[pp][k] = s[pp * PADDED + off];
+    }
+}
+template <class T, int PPT, int PADDED>
+NTT_DEVINL void tile_store(T* s, unsigned off, const T (&x)[PPT][8], int k) {
+    if constexpr (TileLayout<T, PPT>::kQuad) {
+        reinterpret_cast<uint4*>(s)[off] = make_uint4(x[0][k], x[1][k], x[2][k], x[3][k]);
+    } else if constexpr (TileLayout<T, PPT>::kPaired) {
+        reinterpret_cast<uint2*>(s)[off] = make_uint2(x[0][k], x[1][k]);
+    } else {
+#pragma unroll
+        for (int pp = 0; pp < PPT; ++pp) s[pp * PADDED + off] = x[pp][k];
+    }
+}
+// the 8 consecutive elements 8t .. 8t+7 of every polynomial <-> the tile
+template <class T, int PPT, int PADDED>
+NTT_DEVINL void tile_load8(const T* s, unsigned t, T (&x)[PPT][8]) {
+    if constexpr (TileLayout<T, PPT>::kQuad) {
+        const uint4* v = reinterpret_cast<const uint4*>(s) + pad_index<uint4>(8 * t);  // 8 slots, no padding inside
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint4 q = v[k];
+            x[0][k] = q.x, x[1][k] = q.y, x[2][k] = q.z, x[3][k] = q.w;
+        }
+    } else if constexpr (TileLayout<T, PPT>::kPaired) {
+        const uint4* v = reinterpret_cast<const uint4*>(reinterpret_cast<const uint2*>(s) + pad_index<uint64_t>(8 * t));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint4 q = v[k];
+            x[0][2 * k] = q.x, x[1][2 * k] = q.y, x[0][2 * k + 1] = q.z, x[1][2 * k + 1] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int pp = 0; pp < PPT; ++pp) load8_consecutive(s + pp * PADDED + pad_index<T>(8 * t), x[pp]);
+    }
+}
+template <class T, int PPT, int PADDED>
+NTT_DEVINL void tile_store8(T* s, unsigned t, const T (&x)[PPT][8]) {
+    if constexpr (TileLayout<T, PPT>::kQuad) {
+        uint4* v = reinterpret_cast<uint4*>(s) + pad_index<uint4>(8 * t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = make_uint4(x[0][k], x[1][k], x[2][k], x[3][k]);
+    } else if constexpr (TileLayout<T, PPT>::kPaired) {
+        uint4* v = reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(s) + pad_index<uint64_t>(8 * t));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = make_uint4(x[0][2 * k], x[1][2 * k], x[0][2 * k + 1], x[1][2 * k + 1]);
+    } else {
+#pragma unroll
+        for (int pp = 0; pp < PPT; ++pp) store8_consecutive(s + pp * PADDED + pad_index<T>(8 * t), x[pp]);
+    }
+}
+
 template <class A, int LOGN, int PPT>
 NTT_DEVINL void fwd_from_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsigned t,
                               const typename A::TW* __restrict__ tw, const typename A::Ctx& c,
@@ -239,6 +322,7 @@ NTT_DEVINL void fwd_from_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsi
     // on entry x holds elements t + k*(N/8): exactly the first radix-8 tuple (stages 0..2)
     using S = FastShape<LOGN>;
     using T = typename A::T;
+    using Slot = typename TileLayout<T, PPT>::Slot;
 #pragma unroll
     for (int pass = 0; pass < S::kRadix8Passes; ++pass) {
         const int stage = 3 * pass;
@@ -246,29 +330,26 @@ NTT_DEVINL void fwd_from_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsi
         unsigned i = t >> log_t2, j = t & ((1u << log_t2) - 1u);
         unsigned base = (i << (log_t2 + 3)) + j;
         // (pass and k are unrolled, so these fold to constants)
-        const bool const_off = ((8u << log_t2) % (128u / sizeof(T))) == 0;
-        const unsigned pbase = pad_index<T>(base);
+        const bool const_off = ((8u << log_t2) % (128u / sizeof(Slot))) == 0;
+        const unsigned pbase = pad_index<Slot>(base);
         if (pass > 0) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                unsigned off = const_off ? pbase + pad_index<T>((unsigned)k << log_t2)
-                                         : pad_index<T>(base + ((unsigned)k << log_t2));
-#pragma unroll
-                for (int pp = 0; pp < PPT; ++pp) x[pp][k] = s[pp * S::kPaddedElems + off];
+                unsigned off = const_off ? pbase + pad_index<Slot>((unsigned)k << log_t2)
+                                         : pad_index<Slot>(base + ((unsigned)k << log_t2));
+                tile_load<T, PPT, S::kPaddedElems>(s, off, x, k);
             }
         }
         tuple_ro<A, 3, 0, false, false, PPT, FastPairLoads<LOGN, false>::value>(x, tw, sub.base(stage) + i, c);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            unsigned off = const_off ? pbase + pad_index<T>((unsigned)k << log_t2)
-                                         : pad_index<T>(base + ((unsigned)k << log_t2));
-#pragma unroll
-            for (int pp = 0; pp < PPT; ++pp) s[pp * S::kPaddedElems + off] = x[pp][k];
+            unsigned off = const_off ? pbase + pad_index<Slot>((unsigned)k << log_t2)
+                                     : pad_index<Slot>(base + ((unsigned)k << log_t2));
+            tile_store<T, PPT, S::kPaddedElems>(s, off, x, k);
         }
         __syncthreads();
     }
-#pragma unroll
-    for (int pp = 0; pp < PPT; ++pp) load8_consecutive(s + pp * S::kPaddedElems + pad_index<T>(8 * t), x[pp]);
+    tile_load8<T, PPT, S::kPaddedElems>(s, t, x);
     last_pass<A, LOGN, false, false, PPT>(x, tw, t, c, sub);
 }
 
@@ -280,9 +361,9 @@ NTT_DEVINL void inv_to_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsign
                             const SubPoly& sub) {
     using S = FastShape<LOGN>;
     using T = typename A::T;
+    using Slot = typename TileLayout<T, PPT>::Slot;
     last_pass<A, LOGN, true, true, PPT>(x, tw, t, c, sub);
-#pragma unroll
-    for (int pp = 0; pp < PPT; ++pp) store8_consecutive(s + pp * S::kPaddedElems + pad_index<T>(8 * t), x[pp]);
+    tile_store8<T, PPT, S::kPaddedElems>(s, t, x);
 #pragma unroll
     for (int pass = S::kRadix8Passes - 1; pass >= 0; --pass) {
         const int stage = 3 * pass;
@@ -290,24 +371,22 @@ NTT_DEVINL void inv_to_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsign
         unsigned i = t >> log_t2, j = t & ((1u << log_t2) - 1u);
         unsigned base = (i << (log_t2 + 3)) + j;
         // (pass and k are unrolled, so these fold to constants)
-        const bool const_off = ((8u << log_t2) % (128u / sizeof(T))) == 0;
-        const unsigned pbase = pad_index<T>(base);
+        const bool const_off = ((8u << log_t2) % (128u / sizeof(Slot))) == 0;
+        const unsigned pbase = pad_index<Slot>(base);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            unsigned off = const_off ? pbase + pad_index<T>((unsigned)k << log_t2)
-                                         : pad_index<T>(base + ((unsigned)k << log_t2));
-#pragma unroll
-            for (int pp = 0; pp < PPT; ++pp) x[pp][k] = s[pp * S::kPaddedElems + off];
+            unsigned off = const_off ? pbase + pad_index<Slot>((unsigned)k << log_t2)
+                                     : pad_index<Slot>(base + ((unsigned)k << log_t2));
+            tile_load<T, PPT, S::kPaddedElems>(s, off, x, k);
         }
         tuple_ro<A, 3, 0, true, false, PPT, FastPairLoads<LOGN, true>::value>(x, tw, sub.base(stage) + i, c);
         if (pass > 0) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                unsigned off = const_off ? pbase + pad_index<T>((unsigned)k << log_t2)
-                                         : pad_index<T>(base + ((unsigned)k << log_t2));
-#pragma unroll
-                for (int pp = 0; pp < PPT; ++pp) s[pp * S::kPaddedElems + off] = x[pp][k];
+                unsigned off = const_off ? pbase + pad_index<Slot>((unsigned)k << log_t2)
+                                         : pad_index<Slot>(base + ((unsigned)k << log_t2));
+                tile_store<T, PPT, S::kPaddedElems>(s, off, x, k);
             }
         }
     }
@@ -319,15 +398,18 @@ NTT_DEVINL void inv_to_regs(typename A::T (&x)[PPT][8], typename A::T* s, unsign
 // (r mod 2^depth) of polynomial r >> depth; a thread group then pairs the same sub-block of PPT
 // consecutive polynomials, which share their twiddles.  Out-of-range rows are clamped and not
 // stored (whole-CTA barriers inside).
-template <class A, int LOGN, int POLYS, int PPT>
+// SUB = false: the rows are whole polynomials (depth == 0, the common case): the twiddle bases and the
+// row mapping fold to constants (7-11 % fewer instructions in the u32 kernels, 2-3 % in the u64 ones).
+template <class A, int LOGN, int POLYS, int PPT, bool SUB = true>
 __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
-                                  FastMinBlocks<A, FastShape<LOGN>::kThreadsPerPoly * POLYS>::value)
-    ntt_fast_fwd_kernel(typename A::T* __restrict__ data, size_t rows, unsigned depth,
+                                  FastMinBlocks<A, FastShape<LOGN>::kThreadsPerPoly * POLYS, PPT>::value)
+    ntt_fast_fwd_kernel(typename A::T* __restrict__ data, size_t rows, unsigned depth_arg,
                         const typename A::TW* __restrict__ tw, typename A::Ctx c) {
     using T = typename A::T;
     using S = FastShape<LOGN>;
     extern __shared__ __align__(16) unsigned char fast_smem_raw[];  // POLYS * PPT padded tiles
     T* smem = reinterpret_cast<T*>(fast_smem_raw);
+    const unsigned depth = SUB ? depth_arg : 0u;
     const unsigned t = threadIdx.x;
     // thread group `grp` works on sub-block `half` of PPT consecutive polynomials (same twiddles)
     const size_t grp = (size_t)blockIdx.x * POLYS + threadIdx.y;
@@ -354,15 +436,16 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
     }
 }
 
-template <class A, int LOGN, int POLYS, int PPT>
+template <class A, int LOGN, int POLYS, int PPT, bool SUB = true>
 __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
-                                  FastMinBlocks<A, FastShape<LOGN>::kThreadsPerPoly * POLYS>::value)
-    ntt_fast_inv_kernel(typename A::T* __restrict__ data, size_t rows, unsigned depth,
+                                  FastMinBlocks<A, FastShape<LOGN>::kThreadsPerPoly * POLYS, PPT>::value)
+    ntt_fast_inv_kernel(typename A::T* __restrict__ data, size_t rows, unsigned depth_arg,
                         const typename A::TW* __restrict__ tw, typename A::Ctx c) {
     using T = typename A::T;
     using S = FastShape<LOGN>;
     extern __shared__ __align__(16) unsigned char fast_smem_raw[];  // POLYS * PPT padded tiles
     T* smem = reinterpret_cast<T*>(fast_smem_raw);
+    const unsigned depth = SUB ? depth_arg : 0u;
     const unsigned t = threadIdx.x;
     // thread group `grp` works on sub-block `half` of PPT consecutive polynomials (same twiddles)
     const size_t grp = (size_t)blockIdx.x * POLYS + threadIdx.y;

@@ -14,9 +14,16 @@ struct FastPolys {  // polynomials per CTA: keep CTAs at >= 256 threads
 // Polynomials per thread: two when the polynomial is big enough for the shared index arithmetic
 // and twiddle loads to matter (the tiles are dynamic shared memory: 72 KiB for two 4096-point
 // u64 polynomials, still two CTAs per SM).
-template <class A, int LOGN>
+#ifndef NTT_FAST_U32_PPT
+#define NTT_FAST_U32_PPT 4
+#endif
+template <class A, int LOGN, bool INV = false>
 struct FastPPT {
-    static constexpr int value = LOGN >= 10 ? 2 : 1;
+    // 32-bit Shoup families, forward: four polynomials per thread (16-byte tile slots, TileLayout::kQuad)
+    // halve the per-polynomial index arithmetic and twiddle loads once more; the inverse is faster with two
+    // (profiles/r02_u32_kernel_variants.txt: fwd 242 against 235 M NTT/s, inv 232 against 253)
+    static constexpr bool kU32 = sizeof(typename A::T) == 4 && !std::is_same<A, Wide32>::value;
+    static constexpr int value = LOGN >= 10 ? ((kU32 && LOGN <= 11 && !INV) ? NTT_FAST_U32_PPT : 2) : 1;
 };
 
 // The fused fwd -> pointwise -> inv kernel needs more registers; with two 4096-point u64
@@ -45,14 +52,22 @@ void launch_fast_fwd_p(typename A::T* data, size_t rows, unsigned depth, const t
     size_t polys = rows >> depth, groups = ((polys + PPT - 1) / PPT) << depth;
     unsigned grid = (unsigned)((groups + P - 1) / P);
     constexpr size_t smem = fast_smem_bytes<A, LOGN, PPT>();
-    fast_allow_smem<ntt_fast_fwd_kernel<A, LOGN, P, PPT>>(smem);
-    ntt_fast_fwd_kernel<A, LOGN, P, PPT><<<grid, block, smem, st>>>(data, rows, depth, tw, c);
+    if (depth == 0) {
+        fast_allow_smem<ntt_fast_fwd_kernel<A, LOGN, P, PPT, false>>(smem);
+        ntt_fast_fwd_kernel<A, LOGN, P, PPT, false><<<grid, block, smem, st>>>(data, rows, 0u, tw, c);
+    } else {
+        fast_allow_smem<ntt_fast_fwd_kernel<A, LOGN, P, PPT, true>>(smem);
+        ntt_fast_fwd_kernel<A, LOGN, P, PPT, true><<<grid, block, smem, st>>>(data, rows, depth, tw, c);
+    }
 }
 template <class A, int LOGN>
 void launch_fast_fwd(typename A::T* data, size_t rows, unsigned depth, const typename A::TW* tw,
                      const typename A::Ctx& c, cudaStream_t st) {
-    if (FastPPT<A, LOGN>::value == 2 && (rows >> depth) > 1)
-        launch_fast_fwd_p<A, LOGN, FastPPT<A, LOGN>::value>(data, rows, depth, tw, c, st);
+    constexpr int kP = FastPPT<A, LOGN>::value;
+    if (kP == 4 && (rows >> depth) >= 4)
+        launch_fast_fwd_p<A, LOGN, kP>(data, rows, depth, tw, c, st);
+    else if (kP >= 2 && (rows >> depth) > 1)
+        launch_fast_fwd_p<A, LOGN, 2>(data, rows, depth, tw, c, st);
     else
         launch_fast_fwd_p<A, LOGN, 1>(data, rows, depth, tw, c, st);
 }
@@ -64,14 +79,22 @@ void launch_fast_inv_p(typename A::T* data, size_t rows, unsigned depth, const t
     size_t polys = rows >> depth, groups = ((polys + PPT - 1) / PPT) << depth;
     unsigned grid = (unsigned)((groups + P - 1) / P);
     constexpr size_t smem = fast_smem_bytes<A, LOGN, PPT>();
-    fast_allow_smem<ntt_fast_inv_kernel<A, LOGN, P, PPT>>(smem);
-    ntt_fast_inv_kernel<A, LOGN, P, PPT><<<grid, block, smem, st>>>(data, rows, depth, tw, c);
+    if (depth == 0) {
+        fast_allow_smem<ntt_fast_inv_kernel<A, LOGN, P, PPT, false>>(smem);
+        ntt_fast_inv_kernel<A, LOGN, P, PPT, false><<<grid, block, smem, st>>>(data, rows, 0u, tw, c);
+    } else {
+        fast_allow_smem<ntt_fast_inv_kernel<A, LOGN, P, PPT, true>>(smem);
+        ntt_fast_inv_kernel<A, LOGN, P, PPT, true><<<grid, block, smem, st>>>(data, rows, depth, tw, c);
+    }
 }
 template <class A, int LOGN>
 void launch_fast_inv(typename A::T* data, size_t rows, unsigned depth, const typename A::TW* tw,
                      const typename A::Ctx& c, cudaStream_t st) {
-    if (FastPPT<A, LOGN>::value == 2 && (rows >> depth) > 1)
-        launch_fast_inv_p<A, LOGN, FastPPT<A, LOGN>::value>(data, rows, depth, tw, c, st);
+    constexpr int kP = FastPPT<A, LOGN, true>::value;
+    if (kP == 4 && (rows >> depth) >= 4)
+        launch_fast_inv_p<A, LOGN, kP>(data, rows, depth, tw, c, st);
+    else if (kP >= 2 && (rows >> depth) > 1)
+        launch_fast_inv_p<A, LOGN, 2>(data, rows, depth, tw, c, st);
     else
         launch_fast_inv_p<A, LOGN, 1>(data, rows, depth, tw, c, st);
 }
