@@ -174,6 +174,13 @@ NTT_DEVINL uint32_t rem64_p30(uint64_t v, uint32_t p, uint32_t mu32, uint32_t c3
     h = umin_<uint32_t>(h, h - p);
     return barrett32_narrow((uint64_t)h * c32 + lo, p, 2 * p, bar_mu, 29);
 }
+// exact (hi * 2^64 + lo) % p: both halves reduced, then one more narrow Barrett step on
+// h * (2^64 mod p) + l <= (p - 1)^2 + p - 1 < p^2
+NTT_DEVINL uint32_t rem128_p30(uint64_t lo, uint64_t hi, uint32_t p, uint32_t mu32, uint32_t c32, uint32_t c64,
+                               uint32_t bar_mu) {
+    uint32_t h = rem64_p30(hi, p, mu32, c32, bar_mu), l = rem64_p30(lo, p, mu32, c32, bar_mu);
+    return barrett32_narrow((uint64_t)h * c64 + l, p, 2 * p, bar_mu, 29);
+}
 NTT_DEVINL uint32_t rem32_p30(uint32_t v, uint32_t p, uint32_t mu32) {
     uint32_t h = v - __umulhi(v, mu32) * p;  // [0, 2p)
     return umin_<uint32_t>(h, h - p);
@@ -402,7 +409,11 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly, CrtFusedMinB
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const VT lv = lhs[base + t + q * TPP], rv = rhs[base + t + q * TPP];
-            if constexpr (sizeof(VT) == 4) {
+            if constexpr (sizeof(VT) == 16) {
+                const uint32_t c64 = k.P_c64[j];
+                x[0][q] = rem128_p30(lv.lo, lv.hi, pj, mu32, c32, c64, ctx.bar_mu);
+                y[0][q] = BINARY ? (uint32_t)rv.lo : rem128_p30(rv.lo, rv.hi, pj, mu32, c32, c64, ctx.bar_mu);
+            } else if constexpr (sizeof(VT) == 4) {
                 x[0][q] = rem32_p30((uint32_t)lv, pj, mu32);
                 y[0][q] = BINARY ? (uint32_t)rv : rem32_p30((uint32_t)rv, pj, mu32);
             } else {
@@ -464,12 +475,15 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly, CrtFusedMinB
         uint32_t x[1][8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            if (!reduce)
+            if constexpr (sizeof(VT) == 16) {
+                x[0][q] = reduce ? rem128_p30(lv[q].lo, lv[q].hi, pj, mu32, c32, k.P_c64[j], ctx.bar_mu) : (uint32_t)lv[q].lo;
+            } else if (!reduce) {
                 x[0][q] = (uint32_t)lv[q];
-            else if constexpr (sizeof(VT) == 4)
+            } else if constexpr (sizeof(VT) == 4) {
                 x[0][q] = rem32_p30((uint32_t)lv[q], pj, mu32);
-            else
+            } else {
                 x[0][q] = rem64_p30((uint64_t)lv[q], pj, mu32, c32, ctx.bar_mu);
+            }
         }
         fwd_from_regs<S32H, LOGN, 1>(x, smem, t, P.fwd[j], ctx, sub);
 #pragma unroll
@@ -577,6 +591,8 @@ struct ntt_b200_native_plan {
             case NTT_B200_NATIVE64_PLAN32: return launch_fwd_fused<uint64_t, 5>(value, res, batch, reduce, st);
             case NTT_B200_NATIVE_BINARY32_PLAN32: return launch_fwd_fused<uint32_t, 2>(value, res, batch, reduce, st);
             case NTT_B200_NATIVE_BINARY64_PLAN32: return launch_fwd_fused<uint64_t, 3>(value, res, batch, reduce, st);
+            case NTT_B200_NATIVE128_PLAN32: return launch_fwd_fused<U128, 10>(value, res, batch, reduce, st);
+            case NTT_B200_NATIVE_BINARY128_PLAN32: return launch_fwd_fused<U128, 5>(value, res, batch, reduce, st);
             default: return false;
         }
     }
@@ -631,6 +647,12 @@ struct ntt_b200_native_plan {
                 return launch_fused<NTT_B200_NATIVE_BINARY32_PLAN32, uint32_t, 2, true>(prod, lhs, rhs, batch, st);
             case NTT_B200_NATIVE_BINARY64_PLAN32:
                 return launch_fused<NTT_B200_NATIVE_BINARY64_PLAN32, uint64_t, 3, true>(prod, lhs, rhs, batch, st);
+            // ten (five) primes: nine (four) finished residue polynomials wait in shared memory, 162 KiB at
+            // n = 4096 (one 512-thread CTA per SM) -- still 3-4x the unfused sequence (profiles/r02_native_bench.txt)
+            case NTT_B200_NATIVE128_PLAN32:
+                return launch_fused<NTT_B200_NATIVE128_PLAN32, U128, 10, false>(prod, lhs, rhs, batch, st);
+            case NTT_B200_NATIVE_BINARY128_PLAN32:
+                return launch_fused<NTT_B200_NATIVE_BINARY128_PLAN32, U128, 5, true>(prod, lhs, rhs, batch, st);
             default: return false;
         }
     }

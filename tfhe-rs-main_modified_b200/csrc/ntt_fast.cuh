@@ -250,11 +250,19 @@ template <class T, int PPT>
 struct TileLayout {
     static constexpr bool kPaired = sizeof(T) == 4 && PPT == 2;
     static constexpr bool kQuad = sizeof(T) == 4 && PPT == 4;
-    using Slot = typename std::conditional<kQuad, uint4, typename std::conditional<kPaired, uint64_t, T>::type>::type;
+    // Two 64-bit polynomials per thread as 16-byte slots (poly0[e], poly1[e]): implemented, measured at the
+    // SASS level and NOT used -- a 128-bit access needs four consecutive registers, and the moves that line
+    // them up (IMAD.MOV 116 -> 198 in the Solinas n = 2048 forward kernel) outweigh the 40 shared-memory
+    // instructions saved (2548 against 2507 instructions).
+    static constexpr bool kPair64 = false && sizeof(T) == 8 && PPT == 2;
+    using Slot = typename std::conditional<kQuad || kPair64, uint4, typename std::conditional<kPaired, uint64_t, T>::type>::type;
 };
 template <class T, int PPT, int PADDED>
 NTT_DEVINL void tile_load(const T* s, unsigned off, T (&x)[PPT][8], int k) {
-    if constexpr (TileLayout<T, PPT>::kQuad) {
+    if constexpr (TileLayout<T, PPT>::kPair64) {
+        ulonglong2 v = reinterpret_cast<const ulonglong2*>(s)[off];
+        x[0][k] = v.x, x[1][k] = v.y;
+    } else if constexpr (TileLayout<T, PPT>::kQuad) {
         uint4 v = reinterpret_cast<const uint4*>(s)[off];
         x[0][k] = v.x, x[1][k] = v.y, x[2][k] = v.z, x[3][k] = v.w;
     } else if constexpr (TileLayout<T, PPT>::kPaired) {
@@ -268,7 +276,9 @@ NTT_DEVINL void tile_load(const T* s, unsigned off, T (&x)[PPT][8], int k) {
 }
 template <class T, int PPT, int PADDED>
 NTT_DEVINL void tile_store(T* s, unsigned off, const T (&x)[PPT][8], int k) {
-    if constexpr (TileLayout<T, PPT>::kQuad) {
+    if constexpr (TileLayout<T, PPT>::kPair64) {
+        reinterpret_cast<ulonglong2*>(s)[off] = make_ulonglong2(x[0][k], x[1][k]);
+    } else if constexpr (TileLayout<T, PPT>::kQuad) {
         reinterpret_cast<uint4*>(s)[off] = make_uint4(x[0][k], x[1][k], x[2][k], x[3][k]);
     } else if constexpr (TileLayout<T, PPT>::kPaired) {
         reinterpret_cast<uint2*>(s)[off] = make_uint2(x[0][k], x[1][k]);
@@ -280,7 +290,14 @@ NTT_DEVINL void tile_store(T* s, unsigned off, const T (&x)[PPT][8], int k) {
 // the 8 consecutive elements 8t .. 8t+7 of every polynomial <-> the tile
 template <class T, int PPT, int PADDED>
 NTT_DEVINL void tile_load8(const T* s, unsigned t, T (&x)[PPT][8]) {
-    if constexpr (TileLayout<T, PPT>::kQuad) {
+    if constexpr (TileLayout<T, PPT>::kPair64) {
+        const ulonglong2* v = reinterpret_cast<const ulonglong2*>(s) + pad_index<uint4>(8 * t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            ulonglong2 q = v[k];
+            x[0][k] = q.x, x[1][k] = q.y;
+        }
+    } else if constexpr (TileLayout<T, PPT>::kQuad) {
         const uint4* v = reinterpret_cast<const uint4*>(s) + pad_index<uint4>(8 * t);  // 8 slots, no padding inside
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -301,7 +318,11 @@ NTT_DEVINL void tile_load8(const T* s, unsigned t, T (&x)[PPT][8]) {
 }
 template <class T, int PPT, int PADDED>
 NTT_DEVINL void tile_store8(T* s, unsigned t, const T (&x)[PPT][8]) {
-    if constexpr (TileLayout<T, PPT>::kQuad) {
+    if constexpr (TileLayout<T, PPT>::kPair64) {
+        ulonglong2* v = reinterpret_cast<ulonglong2*>(s) + pad_index<uint4>(8 * t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = make_ulonglong2(x[0][k], x[1][k]);
+    } else if constexpr (TileLayout<T, PPT>::kQuad) {
         uint4* v = reinterpret_cast<uint4*>(s) + pad_index<uint4>(8 * t);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = make_uint4(x[0][k], x[1][k], x[2][k], x[3][k]);
