@@ -450,6 +450,75 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly, CrtFusedMinB
     }
 }
 
+// ---- the same for the Plan52 kinds (one to three 50-bit primes, 64-bit residues) ------------------
+// native32::Plan52 (u32 values, no reduction: native32.rs:452-464), native64::Plan52 (u64 values, `% Q_j`),
+// native_binary32::Plan52 / native_binary64::Plan52 (rhs copied unreduced).  Same structure: operands read
+// per prime, three transforms per prime in registers + one tile, finished residues parked in shared memory.
+using S64H = Shoup<uint64_t, true>;  // primes52 are 50-bit (lib.rs:605-610)
+template <int NP>
+struct FusedPrimes64 {
+    const S64H::TW* fwd[NP];
+    const S64H::TW* inv[NP];
+    S64H::Ctx ctx[NP];
+    S64H::TW n_inv[NP];
+};
+template <int NP, int LOGN>
+constexpr size_t fused52_smem_bytes() {
+    return (size_t)(FastShape<LOGN>::kPaddedElems + (NP - 1) * (1 << LOGN)) * sizeof(uint64_t);
+}
+template <int KIND, class VT, int NP, int LOGN, bool BINARY, bool REDUCE>
+__global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly,
+                                  (512 / FastShape<LOGN>::kThreadsPerPoly > 0 ? 512 / FastShape<LOGN>::kThreadsPerPoly : 1))
+    native_polymul_fused52_kernel(VT* __restrict__ prod, const VT* __restrict__ lhs, const VT* __restrict__ rhs,
+                                  const __grid_constant__ FusedPrimes64<NP> P, const __grid_constant__ CrtConsts k) {
+    using S = FastShape<LOGN>;
+    constexpr int TPP = S::kThreadsPerPoly;
+    extern __shared__ __align__(16) unsigned char fused_smem_raw[];
+    uint64_t* smem = reinterpret_cast<uint64_t*>(fused_smem_raw);  // transform tile
+    uint64_t* res_s = smem + S::kPaddedElems;                       // residues of primes 0 .. NP-2
+    const unsigned t = threadIdx.x;
+    const size_t base = (size_t)blockIdx.x << LOGN;
+    const SubPoly sub{0u, 0u};
+    uint64_t last[8];
+#pragma unroll 1
+    for (int j = 0; j < NP; ++j) {
+        const uint64_t qj = k.Q[j], qb = k.Q_b64[j];
+        const S64H::Ctx ctx = P.ctx[j];
+        uint64_t x[1][8], y[1][8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint64_t lv = (uint64_t)lhs[base + t + q * TPP], rv = (uint64_t)rhs[base + t + q * TPP];
+            x[0][q] = REDUCE ? rem64(lv, qj, qb) : lv;
+            y[0][q] = (BINARY || !REDUCE) ? rv : rem64(rv, qj, qb);
+        }
+        fwd_from_regs<S64H, LOGN, 1>(x, smem, t, P.fwd[j], ctx, sub);
+        __syncthreads();  // everyone has read its last-pass inputs before the tile is reused
+        fwd_from_regs<S64H, LOGN, 1>(y, smem, t, P.fwd[j], ctx, sub);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            uint64_t a = S64H::fwd_fin(ctx, x[0][q]), b = S64H::fwd_fin(ctx, y[0][q]);
+            x[0][q] = S64H::mul_const(ctx, S64H::mul_full(ctx, a, b), P.n_inv[j]);
+        }
+        __syncthreads();
+        inv_to_regs<S64H, LOGN, 1>(x, smem, t, P.inv[j], ctx, sub);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint64_t r = S64H::inv_fin(ctx, x[0][q]);
+            if (j < NP - 1)
+                res_s[(j * 8 + q) * TPP + t] = r;
+            else
+                last[q] = r;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        auto r32 = [&](int) { return (uint32_t)0; };
+        auto r64 = [&](int j) { return j < NP - 1 ? res_s[(j * 8 + q) * TPP + t] : last[q]; };
+        crt_with<KIND>(k, r32, r64, base + t + q * TPP, prod);
+    }
+}
+
 // ---- fused fwd of the same plans: one CTA per polynomial, a loop over the primes -----------------
 // The value is read once, reduced modulo prime j in registers and transformed; only the residues are
 // written (the unfused sequence writes the split residues and reads them back for the in-place
@@ -637,8 +706,52 @@ struct ntt_b200_native_plan {
         NTT_CUDA_CHECK(cudaGetLastError());
         return true;
     }
+    template <int NP>
+    bool fused_primes64(FusedPrimes64<NP>& P) const {
+        for (int j = 0; j < NP; ++j) {
+            RawShoup64H raw;
+            if (!p64[j].impl->raw_shoup64h(&raw)) return false;
+            P.fwd[j] = raw.fwd;
+            P.inv[j] = raw.inv;
+            P.ctx[j] = raw.ctx;
+            P.n_inv[j] = raw.n_inv;
+        }
+        return true;
+    }
+    template <int KIND, class VT, int NP, bool BINARY, bool REDUCE>
+    bool launch_fused52(void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st) const {
+        FusedPrimes64<NP> P{};
+        if (!fused_primes64(P)) return false;
+        auto aligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+        if (!aligned(prod) || !aligned(lhs) || !aligned(rhs)) return false;
+        unsigned grid = (unsigned)batch;
+#define NTT_FUSED_CASE(L)                                                                         \
+    case L: {                                                                                     \
+        constexpr size_t smem = fused52_smem_bytes<NP, L>();                                      \
+        allow_dynamic_smem<native_polymul_fused52_kernel<KIND, VT, NP, L, BINARY, REDUCE>>(smem); \
+        native_polymul_fused52_kernel<KIND, VT, NP, L, BINARY, REDUCE>                            \
+            <<<grid, FastShape<L>::kThreadsPerPoly, smem, st>>>((VT*)prod, (const VT*)lhs, (const VT*)rhs, P, consts); \
+    } break;
+        switch (__builtin_ctzll((unsigned long long)n)) {
+            NTT_FUSED_CASE(10)
+            NTT_FUSED_CASE(11)
+            NTT_FUSED_CASE(12)
+            default: return false;
+        }
+#undef NTT_FUSED_CASE
+        NTT_CUDA_CHECK(cudaGetLastError());
+        return true;
+    }
     bool polymul_fused(void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st) const {
         switch (kind) {
+            case NTT_B200_NATIVE32_PLAN52:
+                return launch_fused52<NTT_B200_NATIVE32_PLAN52, uint32_t, 2, false, false>(prod, lhs, rhs, batch, st);
+            case NTT_B200_NATIVE64_PLAN52:
+                return launch_fused52<NTT_B200_NATIVE64_PLAN52, uint64_t, 3, false, true>(prod, lhs, rhs, batch, st);
+            case NTT_B200_NATIVE_BINARY32_PLAN52:
+                return launch_fused52<NTT_B200_NATIVE_BINARY32_PLAN52, uint32_t, 1, true, false>(prod, lhs, rhs, batch, st);
+            case NTT_B200_NATIVE_BINARY64_PLAN52:
+                return launch_fused52<NTT_B200_NATIVE_BINARY64_PLAN52, uint64_t, 2, true, true>(prod, lhs, rhs, batch, st);
             case NTT_B200_NATIVE32_PLAN32:
                 return launch_fused<NTT_B200_NATIVE32_PLAN32, uint32_t, 3, false>(prod, lhs, rhs, batch, st);
             case NTT_B200_NATIVE64_PLAN32:

@@ -217,6 +217,15 @@ struct PlanImpl final : PrimePlan {
         }
     }
 
+    bool raw_shoup64h(RawShoup64H* out) const override {
+        if constexpr (std::is_same<A, Shoup<uint64_t, true>>::value) {
+            *out = RawShoup64H{d_fwd.get(), d_inv.get(), ctx, n_inv};
+            return true;
+        } else {
+            return false;
+        }
+    }
+
     template <bool INV>
     void launch_rows(T* data, size_t num_rows, int log_row, int depth, int finalize,
                      cudaStream_t st) const {

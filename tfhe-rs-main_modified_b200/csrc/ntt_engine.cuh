@@ -33,6 +33,14 @@ struct RawShoup32H {
     ShoupTw<uint32_t> n_inv;
 };
 
+// The same for a plan of a prime below 2^62 (the 50-bit CRT primes of the Plan52 kinds).
+struct RawShoup64H {
+    const ShoupTw<uint64_t>* fwd;
+    const ShoupTw<uint64_t>* inv;
+    Shoup<uint64_t, true>::Ctx ctx;
+    ShoupTw<uint64_t> n_inv;
+};
+
 // Abstract prime plan (prime32::Plan / prime64::Plan); one concrete class per modulus family.
 struct PrimePlan {
     size_t n = 0;
@@ -86,6 +94,7 @@ struct PrimePlan {
     }
     virtual std::shared_ptr<PrimePlan> clone() const = 0;
     virtual bool raw_shoup32h(RawShoup32H*) const { return false; }
+    virtual bool raw_shoup64h(RawShoup64H*) const { return false; }
 };
 
 // nullptr <=> the reference's try_new returns None.  Throws CudaError on CUDA failures.
