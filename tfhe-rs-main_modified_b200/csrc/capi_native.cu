@@ -382,6 +382,7 @@ template <int LOGN>
 struct CrtFusedMinBlocks {
     static constexpr int value = 1024 / FastShape<LOGN>::kThreadsPerPoly > 0 ? 1024 / FastShape<LOGN>::kThreadsPerPoly : 1;
 };
+constexpr size_t kMaxFusedSmem = 227 * 1024;  // opt-in dynamic shared memory of one CTA on sm_100
 template <int NP, int LOGN>
 constexpr size_t fused_smem_bytes() {
     return (size_t)(FastShape<LOGN>::kPaddedElems + (NP - 1) * (1 << LOGN)) * sizeof(uint32_t);
@@ -648,6 +649,7 @@ struct ntt_b200_native_plan {
             NTT_FUSED_CASE(10)
             NTT_FUSED_CASE(11)
             NTT_FUSED_CASE(12)
+            NTT_FUSED_CASE(13)
             default: return false;
         }
 #undef NTT_FUSED_CASE
@@ -689,17 +691,21 @@ struct ntt_b200_native_plan {
         unsigned grid = (unsigned)batch;
 #define NTT_FUSED_CASE(L)                                                                         \
     case L: {                                                                                     \
-        auto kern = native_polymul_fused_kernel<KIND, VT, NP, L, BINARY>;                         \
         constexpr size_t smem = fused_smem_bytes<NP, L>();                                        \
-        if (smem > 48 * 1024)                                                                     \
-            NTT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<grid, FastShape<L>::kThreadsPerPoly, smem, st>>>((VT*)prod, (const VT*)lhs,        \
-                                                                (const VT*)rhs, P, consts);       \
+        if constexpr (smem <= kMaxFusedSmem) {                                                    \
+            allow_dynamic_smem<native_polymul_fused_kernel<KIND, VT, NP, L, BINARY>>(smem);       \
+            native_polymul_fused_kernel<KIND, VT, NP, L, BINARY>                                  \
+                <<<grid, FastShape<L>::kThreadsPerPoly, smem, st>>>((VT*)prod, (const VT*)lhs,    \
+                                                                    (const VT*)rhs, P, consts);   \
+        } else {                                                                                  \
+            return false; /* the parked residues do not fit one SM's shared memory */             \
+        }                                                                                         \
     } break;
         switch (__builtin_ctzll((unsigned long long)n)) {
             NTT_FUSED_CASE(10)
             NTT_FUSED_CASE(11)
             NTT_FUSED_CASE(12)
+            NTT_FUSED_CASE(13)  // 1024-thread CTAs, one per SM
             default: return false;
         }
 #undef NTT_FUSED_CASE

@@ -113,6 +113,9 @@ void launch_fast_fmi(typename A::T* out, const typename A::T* lhs, const typenam
         out, lhs, rhs, rhs_polys, acc, acc_polys ? acc_polys : 1, batch, tw_fwd, tw_inv, c);
 }
 
+// (A 2^13-point single-CTA kernel -- 1024 threads, 36 KiB tile -- was measured for the 32-bit families and
+// is slower stand-alone than the TMA-staged radix-16 pass + 512-point kernels: 31.9 / 36.3 against 36.9 /
+// 38.9 M NTT/s, profiles/r02_large_n_u32.txt.  The fused CRT kernels do use fwd_from_regs<.., 13, ..>.)
 #define NTT_FAST_SWITCH(CALL)          \
     switch (logn) {                    \
         case 8: CALL(8); break;        \
