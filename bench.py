@@ -29,7 +29,7 @@ SOLINAS_P = (1 << 64) - (1 << 32) + 1
 BATCH_PER_GPU = 65536          # 65536 * 16 KiB = 1 GiB per GPU: far beyond the 126 MB L2
 ALG_BYTES_PER_NTT = 2 * N * 8  # one in-place NTT reads and writes each coefficient once
 E2E_BATCH = 65536              # host-buffer leg: 1 GiB in + 1 GiB out per step
-NCU_TRAFFIC_PER_LAUNCH = {"fwd": 2.1099e9, "inv": 2.0913e9}  # dram read+write bytes of one launch, ncu --set full (profiles/ v4)
+NCU_TRAFFIC_PER_LAUNCH = {"fwd": 2.1018e9, "inv": 2.0891e9}  # dram read+write bytes of one launch, ncu --set full (profiles/r02_ncu_full_solinas2048_summary.md)
 # Issue cost of one thread of the shipped kernels (two polynomials, 88 butterflies), from the SASS of
 # ntt_fast_{fwd,inv}_kernel<Solinas64,11,1,2> weighted by the measured issue costs of
 # profiles/r01_int_pipe_microbench.txt (IMAD.WIDE 4 clk, other IMAD 2 clk on the FMA-heavy pipe; IADD3 / LOP3 /
@@ -389,13 +389,13 @@ def run_gpu(args):
             "config": workload_config(world),
             "roofline": {"bound": "hbm", "kernel": "ntt %s (N=2048 Solinas)" % dom, "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm, "traffic": NCU_TRAFFIC_PER_LAUNCH[dom], "peak_source": which,
-                         "traffic_source": "profiles/r01_ncu_full_solinas2048_v4_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
-                         "limiter": "integer instruction throughput (ncu: ALU pipe 69-70 %, FMA-heavy pipe 70-74 %, DRAM 26-29 %): "
+                         "traffic_source": "profiles/r02_ncu_full_solinas2048_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                         "limiter": "integer instruction throughput (ncu r02: ALU pipe 70-72 %, FMA-heavy pipe 71-74 %, issue 66 %, DRAM 28-30 %): "
                                     "the Solinas butterfly is carry-chain adds, see DESIGN.md section 5",
                          "int_pipe_busy_frac": int_pipes,
                          "int_pipe_note": "pipe clocks needed by the SASS instruction mix / pipe clocks available; ncu measures "
-                                          "70-74 % (fmaheavy) and 69-70 % (alu), profiles/r01_ncu_full_solinas2048_v4_summary.md; "
-                                          "a two-pipe mix tops out at 0.76 in profiles/r01_int_pipe_microbench.txt",
+                                          "71-74 % (fmaheavy) and 70-72 % (alu), profiles/r02_ncu_full_solinas2048_summary.md; "
+                                          "the register-resident butterfly loop reaches 83-85 % (profiles/r02_solinas_bf_variants.md)",
                          "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                          "algorithmic_bytes_per_launch": batch * ALG_BYTES_PER_NTT},
             # the binding roofline: the busier integer pipe of the dominant kernel against what the same butterfly

@@ -263,8 +263,43 @@ struct PbsClusterShape {
     // with a second, split-phase barrier fits 4 CTAs at 64 registers: same peak throughput, +10 %
     // latency -- measured, not kept.)
     static constexpr int kMinBlocks = 768 / kThreads > 0 ? 768 / kThreads : 1;
-    static size_t bytes(size_t n_lwe) { return (kTile + kAcc + kXbuf) * 8 + (n_lwe + 1) * 4; }
+    static size_t bytes(size_t n_lwe) { return (kTile + kAcc + kXbuf + 2) * 8 + (n_lwe + 1) * 4; }  // + two mbarriers
 };
+
+// ---- distributed-shared-memory exchange without a cluster barrier per round -----------------------
+// barrier.cluster.arrive.release / wait.acquire (cg::cluster_group::sync) costs a GPU-scope MEMBAR and an
+// L1 invalidation (CCTL.IVALL) each time, which also throws the twiddle tables out of L1 once per CMUX.
+// The per-round exchange instead uses asynchronous remote stores that complete a transaction count on
+// an mbarrier in the RECEIVER's shared memory (st.async ... mbarrier::complete_tx::bytes, SASS STAS +
+// SYNCS): the receiver arms the barrier with the byte count it expects and waits on it locally.
+NTT_DEVINL uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+NTT_DEVINL uint32_t map_to_cta(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+NTT_DEVINL void mbar_init(uint32_t mbar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(arrivals) : "memory");
+}
+NTT_DEVINL void mbar_fence_init_cluster() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+NTT_DEVINL void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+NTT_DEVINL void mbar_wait_parity(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{ .reg .pred p;\n"
+        "MBAR_WAIT_LOOP: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_WAIT_DONE;\n"
+        "bra MBAR_WAIT_LOOP;\n"
+        "MBAR_WAIT_DONE: }" ::"r"(mbar), "r"(parity)
+        : "memory");
+}
+// 16 bytes into the peer CTA's shared memory, counted on the peer's mbarrier
+NTT_DEVINL void st_async_remote_v2(uint32_t remote_addr, uint64_t a, uint64_t b, uint32_t remote_mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
+                 "l"(a), "l"(b), "r"(remote_mbar)
+                 : "memory");
+}
 
 template <class A, int LOGN, bool BNF>
 __global__ void __cluster_dims__(2, 1, 1)
@@ -284,11 +319,19 @@ __global__ void __cluster_dims__(2, 1, 1)
     uint64_t* tile = pbs_smem;
     uint64_t* accS = pbs_smem + CS::kTile;                                  // polynomial r of the accumulator
     ulonglong2* xbuf = reinterpret_cast<ulonglong2*>(accS + CS::kAcc);      // [2][4][TPP] vectors
-    unsigned* sw = reinterpret_cast<unsigned*>(accS + CS::kAcc + CS::kXbuf);
+    uint64_t* mbar = accS + CS::kAcc + CS::kXbuf;                           // one mbarrier per exchange buffer
+    unsigned* sw = reinterpret_cast<unsigned*>(mbar + 2);
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned r = cluster.block_rank();
-    ulonglong2* peer_xbuf = cluster.map_shared_rank(xbuf, r ^ 1u);
     const unsigned t = threadIdx.x;
+    // (addresses of the second barrier = first + 8: a CTA's window of the cluster address space keeps offsets)
+    const uint32_t my_mbar0 = smem_addr_u32(mbar), peer_mbar0 = map_to_cta(my_mbar0, r ^ 1u);
+    const uint32_t peer_xbuf = map_to_cta(smem_addr_u32(xbuf), r ^ 1u);
+    if (t == 0) {
+        mbar_init(my_mbar0, 1);
+        mbar_init(my_mbar0 + 8u, 1);
+        mbar_fence_init_cluster();
+    }
     const size_t b = blockIdx.x >> 1;
     const uint64_t p = FixedModulus<A>::value ? FixedModulus<A>::value : c.p;
     const SubPoly sub{0u, 0u};
@@ -300,17 +343,22 @@ __global__ void __cluster_dims__(2, 1, 1)
         const uint64_t* l = lut + (b % lut_count) * (size_t)(GS * N) + (size_t)r * N;
         for (unsigned j = t; j < N; j += TPP) accS[j] = BNF ? l[j] : pbs::monomial_div_coeff(l, j, body, LOGN, p);
     }
-    cluster.sync();  // both CTAs are resident before any remote shared-memory write
+    cluster.sync();  // both CTAs are resident and their mbarriers initialised before any remote store
 
-    // Ping-pong exchange buffers indexed by the number of executed CMUXes: the peer's write of round
-    // e + 2 into the buffer of round e comes after barrier e + 1, which this CTA reaches only after
-    // it has read round e.
+    // Ping-pong exchange buffers indexed by the number of executed CMUXes, one mbarrier each.  The peer's
+    // stores of round e + 2 into the buffer of round e are issued after it has received this CTA's round
+    // e + 1 products, which this CTA sends only after it has read round e: two buffers suffice without any
+    // cluster-wide barrier inside the loop.  A buffer's mbarrier is armed (one arrival + the byte count of
+    // one polynomial of products) by thread 0 at the start of the round that uses it; remote bytes that
+    // land before the arming only drive the transaction count negative while that arrival is pending.
     unsigned executed = 0;
     for (unsigned i = 0; i < n_lwe; ++i) {
         const unsigned a = sw[i];
         if (a & kPbsSkip) continue;  // uniform over the cluster
         const ulonglong2* gq = reinterpret_cast<const ulonglong2*>(bsk_tw + (size_t)i * GS * GS * N) +
                                pbs_key_index<LOGN, GS>(0, 0, t, r, 0, 0) / 2;
+        const unsigned slot = executed & 1u, parity = (executed >> 1) & 1u;
+        if (t == 0) mbar_arrive_expect_tx(my_mbar0 + 8u * slot, 8u << LOGN);
         uint64_t x[1][8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -327,18 +375,18 @@ __global__ void __cluster_dims__(2, 1, 1)
             x[0][k] = d;
         }
         fwd_from_regs<A, LOGN, 1>(x, tile, t, tw_fwd, c, sub);
-        ulonglong2* send = peer_xbuf + (size_t)(executed & 1u) * 4 * TPP;
-        const ulonglong2* recv = xbuf + (size_t)(executed & 1u) * 4 * TPP;
+        const uint32_t send = peer_xbuf + (slot * 4 * TPP + t) * 16u;
+        const ulonglong2* recv = xbuf + (size_t)slot * 4 * TPP;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             ulonglong2 g_own = __ldcg(gq + (size_t)q * TPP * 4 + r);         // column r
             ulonglong2 g_peer = __ldcg(gq + (size_t)q * TPP * 4 + (r ^ 1u));  // column 1 - r
-            send[q * TPP + t] = make_ulonglong2(A::mul_const(c, x[0][2 * q], g_peer.x),
-                                                A::mul_const(c, x[0][2 * q + 1], g_peer.y));
+            st_async_remote_v2(send + q * TPP * 16u, A::mul_const(c, x[0][2 * q], g_peer.x),
+                               A::mul_const(c, x[0][2 * q + 1], g_peer.y), peer_mbar0 + 8u * slot);
             x[0][2 * q] = A::mul_const(c, x[0][2 * q], g_own.x);
             x[0][2 * q + 1] = A::mul_const(c, x[0][2 * q + 1], g_own.y);
         }
-        cluster.sync();  // the peer's products for my column have landed
+        mbar_wait_parity(my_mbar0 + 8u * slot, parity);  // the peer's products for my column have landed
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             ulonglong2 v = recv[q * TPP + t];
