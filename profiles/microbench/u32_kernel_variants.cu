@@ -80,16 +80,19 @@ void run(uint32_t* d, size_t batch, const A::TW* tw, A::Ctx c) {
 
 template <int LOGN, int PPT, bool INV>
 void run_shipped(uint32_t* d, size_t batch, const A::TW* tw, A::Ctx c) {
-    constexpr size_t smem = (size_t)PPT * FastShape<LOGN>::kPaddedElems * 4;
-    auto kern = INV ? ntt_fast_inv_kernel<A, LOGN, 1, PPT, false> : ntt_fast_fwd_kernel<A, LOGN, 1, PPT, false>;
+    constexpr int POLYS = (1 << LOGN) >= 2048 ? 1 : 2048 / (1 << LOGN);  // FastPolys
+    constexpr size_t smem = (size_t)POLYS * PPT * FastShape<LOGN>::kPaddedElems * 4;
+    auto kern = INV ? ntt_fast_inv_kernel<A, LOGN, POLYS, PPT, false> : ntt_fast_fwd_kernel<A, LOGN, POLYS, PPT, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    unsigned grid = (unsigned)(batch / PPT);
-    for (int w = 0; w < 3; ++w) kern<<<grid, 256, smem>>>(d, batch, 0u, tw, c);
+    batch = (size_t)131072 * 2048 >> LOGN;  // 1 GiB of u32 whatever the length
+    unsigned grid = (unsigned)(batch / (PPT * POLYS));
+    dim3 block(FastShape<LOGN>::kThreadsPerPoly, POLYS);
+    for (int w = 0; w < 3; ++w) kern<<<grid, block, smem>>>(d, batch, 0u, tw, c);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    for (int r = 0; r < 10; ++r) kern<<<grid, 256, smem>>>(d, batch, 0u, tw, c);
+    for (int r = 0; r < 10; ++r) kern<<<grid, block, smem>>>(d, batch, 0u, tw, c);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
@@ -144,5 +147,25 @@ int main() {
     run_shipped<LOGN, 4, false>(d, batch, dtw, c);
     run_shipped<LOGN, 2, true>(d, batch, dtw, c);
     run_shipped<LOGN, 4, true>(d, batch, dtw, c);
+    // other lengths (the twiddle table above covers 2048 entries; 4096 reuses it cyclically through the same
+    // pointer range only for timing, so give it its own)
+    std::vector<A::TW> tw2(4096);
+    for (size_t i = 0; i < 4096; ++i) tw2[i] = tw[i & 2047];
+    A::TW* dtw2;
+    cudaMalloc(&dtw2, 4096 * sizeof(A::TW));
+    cudaMemcpy(dtw2, tw2.data(), 4096 * sizeof(A::TW), cudaMemcpyHostToDevice);
+    run_shipped<10, 2, false>(d, batch, dtw2, c);
+    run_shipped<10, 4, false>(d, batch, dtw2, c);
+    run_shipped<10, 2, true>(d, batch, dtw2, c);
+    run_shipped<10, 4, true>(d, batch, dtw2, c);
+    run_shipped<12, 2, false>(d, batch, dtw2, c);
+    run_shipped<12, 4, false>(d, batch, dtw2, c);
+    run_shipped<12, 2, true>(d, batch, dtw2, c);
+    run_shipped<12, 4, true>(d, batch, dtw2, c);
+    run_shipped<9, 1, false>(d, batch, dtw2, c);
+    run_shipped<9, 2, false>(d, batch, dtw2, c);
+    run_shipped<9, 4, false>(d, batch, dtw2, c);
+    run_shipped<8, 1, false>(d, batch, dtw2, c);
+    run_shipped<8, 2, false>(d, batch, dtw2, c);
     return 0;
 }

@@ -553,3 +553,35 @@ def test_device_pointers_without_16_byte_alignment(T, bits, n, p):
     assert (view.cpu().numpy().view(dt).reshape(batch, n) == want_i).all()
     gp.normalize_device(view, stream=st)
     assert (view.cpu().numpy().view(dt).reshape(batch, n) == x).all()
+
+
+@pytest.mark.gpu
+def test_small_host_calls_staged_path_matches_the_mapped_one(T):
+    """The per-polynomial host calls run on the mapped pinned staging buffer by default; NTT_B200_ZERO_COPY=0
+    stages through device memory instead.  Both must give the oracle's bits (the switch is read once per
+    process, so the staged path runs in a child process)."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np
+import tfhe_ntt_b200 as T
+import oracle_lib as O
+for bits, n, p in [(64, 1024, O.SOLINAS_P), (64, 4096, O.SOLINAS_P), (32, 2048, 1073479681), (64, 64, O.SOLINAS_P)]:
+    mod = T.prime64 if bits == 64 else T.prime32
+    dt = np.uint64 if bits == 64 else np.uint32
+    plan, ref = mod.Plan.try_new(n, p), O.OraclePlan(bits, n, p)
+    rng = np.random.default_rng(n)
+    x = (rng.integers(0, 1 << 62, size=n, dtype=np.uint64) %% np.uint64(p)).astype(dt)
+    y = x.copy(); plan.fwd(y); assert (y == ref.fwd(x)).all()
+    plan.inv(y); assert (y == ref.inv(ref.fwd(x))).all()
+    a, l, r = x.copy(), ref.fwd(x), x[::-1].copy()
+    plan.mul_accumulate(a, l, r); assert (a == ref.mul_accumulate(x, l, r)).all()
+    plan.normalize(a); plan.mul_assign_normalize(a, r)
+print("ok")
+''' % (ROOT, ROOT)
+    for zero_copy in ("1", "0"):
+        env = dict(os.environ, NTT_B200_ZERO_COPY=zero_copy)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0 and "ok" in r.stdout, (zero_copy, r.stdout, r.stderr)

@@ -258,3 +258,26 @@ def test_cluster_latency_path_bit_exact(N, bnf):
     G2, key2, _ = _setup(rng, 3, 1, 512, 10, 2)
     with pytest.raises(T.NttB200Error):
         G2.blind_rotate_ntt64_assign(_rand_mod(rng, 4, P), _rand_mod(rng, 1024, P), key2, path=G2.PATH_CLUSTER)
+
+
+@pytest.mark.gpu
+def test_classic_pbs_rejects_more_decomposition_bits_than_the_modulus_has():
+    """base_log * level > ceil(log2 p): the reference's SignedDecomposerNonNative::new asserts
+    (decomposer.rs:487-520); the classic entry points answer ERR_ARG instead of shifting by a negative amount.
+    The bnf variant (native decomposer over 64 bits) accepts the same key."""
+    import tfhe_ntt_b200 as T
+    from tfhe_ntt_b200 import ntt64_pbs as G
+    from tfhe_ntt_b200._binding import NttB200Error
+    p = T.prime.largest_prime_in_arithmetic_progression64(1 << 16, 1, 0, 1 << 62)  # 62-bit prime
+    n, n_lwe, gs, base_log, level = 256, 3, 2, 21, 3                               # 63 bits > 62
+    plan = T.prime64.Plan.try_new(n, p)
+    rng = np.random.default_rng(10)
+    bsk = _rand_mod(rng, n_lwe * level * gs * gs * n, p)
+    key = G.NttLweBootstrapKey.from_container(plan, bsk, n_lwe, gs, base_log, level)
+    lwe = _rand_mod(rng, (1, n_lwe + 1), p)
+    lut = _rand_mod(rng, (1, gs * n), p)
+    with pytest.raises(NttB200Error):
+        G.blind_rotate_ntt64_assign(lwe.reshape(-1), lut.copy().reshape(-1), key)
+    out = np.zeros((gs - 1) * n + 1, dtype=np.uint64)
+    with pytest.raises(NttB200Error):
+        G.programmable_bootstrap_ntt64_lwe_ciphertext(lwe.reshape(-1), out, lut.reshape(-1), key)

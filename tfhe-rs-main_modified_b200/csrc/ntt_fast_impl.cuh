@@ -19,11 +19,13 @@ struct FastPolys {  // polynomials per CTA: keep CTAs at >= 256 threads
 #endif
 template <class A, int LOGN, bool INV = false>
 struct FastPPT {
-    // 32-bit Shoup families, forward: four polynomials per thread (16-byte tile slots, TileLayout::kQuad)
-    // halve the per-polynomial index arithmetic and twiddle loads once more; the inverse is faster with two
-    // (profiles/r02_u32_kernel_variants.txt: fwd 242 against 235 M NTT/s, inv 232 against 253)
+    // 32-bit Shoup families: four polynomials per thread (16-byte tile slots, TileLayout::kQuad) halve the
+    // per-polynomial index arithmetic and twiddle loads once more -- forward at n = 1024 / 2048, inverse at
+    // n = 1024 (at 2048 the inverse is as fast with two, at 4096 four lose 20-30 %); short polynomials
+    // (n = 256, 512) take two per thread as well: +10..20 % (profiles/r02_u32_kernel_variants.txt)
     static constexpr bool kU32 = sizeof(typename A::T) == 4 && !std::is_same<A, Wide32>::value;
-    static constexpr int value = LOGN >= 10 ? ((kU32 && LOGN <= 11 && !INV) ? NTT_FAST_U32_PPT : 2) : 1;
+    static constexpr bool kFour = kU32 && (LOGN == 10 || (LOGN == 11 && !INV));
+    static constexpr int value = kFour ? NTT_FAST_U32_PPT : 2;
 };
 
 // The fused fwd -> pointwise -> inv kernel needs more registers; with two 4096-point u64

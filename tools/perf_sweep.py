@@ -27,7 +27,9 @@ def main():
     cases = [(64, 1024, T.prime64.SOLINAS_PRIME), (64, 2048, T.prime64.SOLINAS_PRIME), (64, 4096, T.prime64.SOLINAS_PRIME),
              (64, 2048, 4611686018427322369), (64, 2048, 9223372036853661697), (64, 2048, 18446744073707716609),
              (32, 2048, 1073479681), (32, 4096, 1068236801), (32, 2048, 2147352577), (32, 2048, 4293918721),
-             (64, 16384, T.prime64.SOLINAS_PRIME), (64, 65536, T.prime64.SOLINAS_PRIME), (64, 256, T.prime64.SOLINAS_PRIME)]
+             (64, 16384, T.prime64.SOLINAS_PRIME), (64, 65536, T.prime64.SOLINAS_PRIME), (64, 256, T.prime64.SOLINAS_PRIME),
+             (64, 512, T.prime64.SOLINAS_PRIME), (64, 512, 4611686018427322369), (32, 256, 1073479681), (32, 512, 1073479681),
+             (32, 1024, 1073479681)]
     for bits, n, p in cases:
         mod = T.prime64 if bits == 64 else T.prime32
         plan = mod.Plan.try_new(n, p)
