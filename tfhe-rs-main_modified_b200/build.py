@@ -16,7 +16,7 @@ OBJ_DIR = os.path.join(HERE, "build")
 SOURCES = ["ntt_engine.cu", "ntt_fast_solinas.cu", "ntt_fast_shoup64.cu", "ntt_fast_shoup32.cu",
            "ntt_fast_exact.cu", "ntt_pbs_solinas.cu", "capi_prime.cu", "capi_native.cu", "capi_product.cu", "capi_pbs.cu",
            "capi_custum_radix.cu"]
-NVCC_FLAGS = [
+NVCC_FLAGS = [*(os.environ.get("NTT_B200_EXTRA_NVCC", "").split()),
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]

@@ -66,10 +66,10 @@ struct FastMinBlocks {
 // The fused fwd -> pointwise -> inv kernel: 32-bit Shoup families are held to
 // NTT_FUSED_U32_THREADS_PER_SM threads per SM, everything else to 1024 (64 registers: the 64-bit
 // families then spill a few words but run four 256-thread CTAs per SM instead of two).
-template <class A, int THREADS>
+template <class A, int THREADS, int PPT = 2>
 struct FusedMinBlocks {
     static constexpr int kThreadsPerSM =
-        (sizeof(typename A::T) == 4 && !std::is_same<A, Wide32>::value) ? NTT_FUSED_U32_THREADS_PER_SM : 1024;
+        (sizeof(typename A::T) == 4 && !std::is_same<A, Wide32>::value) ? (PPT <= 2 ? NTT_FUSED_U32_THREADS_PER_SM : 768) : 1024;
     static constexpr int value = kThreadsPerSM / THREADS > 0 ? kThreadsPerSM / THREADS : 1;
 };
 
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
 // PBS external product shape):  out = inv(acc + fwd(lhs) * rhs).
 template <class A, int LOGN, int POLYS, int PPT>
 __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
-                                  FusedMinBlocks<A, FastShape<LOGN>::kThreadsPerPoly * POLYS>::value)
+                                  FusedMinBlocks<A, FastShape<LOGN>::kThreadsPerPoly * POLYS, PPT>::value)
     ntt_fast_fwd_mac_inv_kernel(typename A::T* __restrict__ out,
                                 const typename A::T* __restrict__ lhs,
                                 const typename A::T* __restrict__ rhs, size_t rhs_polys,

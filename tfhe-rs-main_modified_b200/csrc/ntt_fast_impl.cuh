@@ -34,7 +34,11 @@ template <class A, int LOGN>
 struct FastPPTFused {
     static constexpr bool fits =
         2 * FastPolys<LOGN>::value * FastShape<LOGN>::kPaddedElems * sizeof(typename A::T) <= 48 * 1024;
-    static constexpr int value = (LOGN >= 10 && fits) ? 2 : 1;
+#ifndef NTT_FUSED_U32_PPT
+#define NTT_FUSED_U32_PPT 2
+#endif
+    static constexpr bool kU32 = sizeof(typename A::T) == 4 && !std::is_same<A, Wide32>::value;
+    static constexpr int value = (kU32 && (LOGN == 10 || LOGN == 11)) ? NTT_FUSED_U32_PPT : (fits ? 2 : 1);
 };
 
 template <class A, int LOGN, int PPT>
