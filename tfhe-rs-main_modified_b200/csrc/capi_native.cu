@@ -385,7 +385,8 @@ struct CrtFusedMinBlocks {
 constexpr size_t kMaxFusedSmem = 227 * 1024;  // opt-in dynamic shared memory of one CTA on sm_100
 template <int NP, int LOGN>
 constexpr size_t fused_smem_bytes() {
-    return (size_t)(FastShape<LOGN>::kPaddedElems + (NP - 1) * (1 << LOGN)) * sizeof(uint32_t);
+    // two transform tiles (the two operands of a prime are transformed together) + the parked residues
+    return (size_t)(2 * FastShape<LOGN>::kPaddedElems + (NP - 1) * (1 << LOGN)) * sizeof(uint32_t);
 }
 
 template <int KIND, class VT, int NP, int LOGN, bool BINARY>
@@ -396,8 +397,8 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly, CrtFusedMinB
     using S = FastShape<LOGN>;
     constexpr int TPP = S::kThreadsPerPoly;
     extern __shared__ __align__(16) unsigned char fused_smem_raw[];
-    uint32_t* smem = reinterpret_cast<uint32_t*>(fused_smem_raw);  // transform tile
-    uint32_t* res_s = smem + S::kPaddedElems;                       // residues of primes 0 .. NP-2
+    uint32_t* smem = reinterpret_cast<uint32_t*>(fused_smem_raw);  // two transform tiles (paired layout)
+    uint32_t* res_s = smem + 2 * S::kPaddedElems;                   // residues of primes 0 .. NP-2
     const unsigned t = threadIdx.x;
     const size_t base = (size_t)blockIdx.x << LOGN;
     const SubPoly sub{0u, 0u};
@@ -406,32 +407,33 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly, CrtFusedMinB
     for (int j = 0; j < NP; ++j) {
         const uint32_t pj = k.P[j], mu32 = k.P_mu32[j], c32 = k.P_c32[j];
         const S32H::Ctx ctx = P.ctx[j];
-        uint32_t x[1][8], y[1][8];
+        // the two operands' residues modulo this prime are transformed together (one twiddle fetch, one
+        // index computation, one 64-bit shared-memory access per position for both: TileLayout::kPaired)
+        uint32_t xy[2][8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const VT lv = lhs[base + t + q * TPP], rv = rhs[base + t + q * TPP];
             if constexpr (sizeof(VT) == 16) {
                 const uint32_t c64 = k.P_c64[j];
-                x[0][q] = rem128_p30(lv.lo, lv.hi, pj, mu32, c32, c64, ctx.bar_mu);
-                y[0][q] = BINARY ? (uint32_t)rv.lo : rem128_p30(rv.lo, rv.hi, pj, mu32, c32, c64, ctx.bar_mu);
+                xy[0][q] = rem128_p30(lv.lo, lv.hi, pj, mu32, c32, c64, ctx.bar_mu);
+                xy[1][q] = BINARY ? (uint32_t)rv.lo : rem128_p30(rv.lo, rv.hi, pj, mu32, c32, c64, ctx.bar_mu);
             } else if constexpr (sizeof(VT) == 4) {
-                x[0][q] = rem32_p30((uint32_t)lv, pj, mu32);
-                y[0][q] = BINARY ? (uint32_t)rv : rem32_p30((uint32_t)rv, pj, mu32);
+                xy[0][q] = rem32_p30((uint32_t)lv, pj, mu32);
+                xy[1][q] = BINARY ? (uint32_t)rv : rem32_p30((uint32_t)rv, pj, mu32);
             } else {
-                x[0][q] = rem64_p30((uint64_t)lv, pj, mu32, c32, ctx.bar_mu);
-                y[0][q] = BINARY ? (uint32_t)rv : rem64_p30((uint64_t)rv, pj, mu32, c32, ctx.bar_mu);
+                xy[0][q] = rem64_p30((uint64_t)lv, pj, mu32, c32, ctx.bar_mu);
+                xy[1][q] = BINARY ? (uint32_t)rv : rem64_p30((uint64_t)rv, pj, mu32, c32, ctx.bar_mu);
             }
         }
-        fwd_from_regs<S32H, LOGN, 1>(x, smem, t, P.fwd[j], ctx, sub);
-        __syncthreads();  // everyone has read its last-pass inputs before the tile is reused
-        fwd_from_regs<S32H, LOGN, 1>(y, smem, t, P.fwd[j], ctx, sub);
+        fwd_from_regs<S32H, LOGN, 2>(xy, smem, t, P.fwd[j], ctx, sub);
         // mul_assign_normalize on the 8 consecutive NTT-domain coefficients of this thread
+        uint32_t x[1][8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            uint32_t a = S32H::fwd_fin(ctx, x[0][q]), b = S32H::fwd_fin(ctx, y[0][q]);
+            uint32_t a = S32H::fwd_fin(ctx, xy[0][q]), b = S32H::fwd_fin(ctx, xy[1][q]);
             x[0][q] = S32H::mul_const(ctx, S32H::mul_full(ctx, a, b), P.n_inv[j]);
         }
-        __syncthreads();
+        __syncthreads();  // everyone has read its last-pass inputs before the tile is reused
         inv_to_regs<S32H, LOGN, 1>(x, smem, t, P.inv[j], ctx, sub);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
