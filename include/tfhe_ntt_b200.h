@@ -400,6 +400,13 @@ int ntt_b200_largest_prime_in_arithmetic_progression64(uint64_t factor, uint64_t
  * their bases apply (see csrc/capi_custum_radix.cu).  n must be a power of two (1 allowed) and the
  * table at least n long (the reference indexes it modulo n): NTT_B200_ERR_LEN otherwise, where the
  * reference overflows its stack or panics on an index.
+ * PRECONDITION (not checked): the table is the power table the module's make_twiddles builds
+ * (fwd.rs:72-103) -- twiddles[0] = 1, twiddles[k] = twiddles[k-1] * twiddles[1] mod p, every entry
+ * below p -- and the inputs are below p.  For any other table the reference's radix-4 and split-radix
+ * recursions (which read tw[(i + q n/4) % n], tw[2k], tw[3k] and J = tw[n/4] directly) and the GPU's
+ * single schedule are different functions of the table and the results diverge.
+ * The _mut entry points keep every level of one vector in shared memory: n <= 4096, NTT_B200_ERR_LEN
+ * above that is a capacity limit of this implementation, not a length mismatch of the caller.
  * ------------------------------------------------------------------------------------------ */
 #define NTT_B200_CR_RADIX2 0      /* fft_radix2_recursive fwd.rs:170-205 (= fwd_1.rs:190-230), ifft inv.rs:178-230 */
 #define NTT_B200_CR_RADIX4 1      /* fft_radix4_recursive fwd.rs:105-168 (= fwd_1.rs:102-188), ifft inv.rs:106-176 */
