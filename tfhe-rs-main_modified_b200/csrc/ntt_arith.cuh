@@ -186,26 +186,36 @@ template <>
 NTT_DEVINL uint32_t Shoup<uint32_t, false>::mul_pw(const Ctx& c, uint32_t x, uint32_t gf) { return mul_full(c, x, gf); }
 
 // ------------------------------------------------------------------------------------
-// Wide32: p >= 2^31, exact arithmetic through 64-bit intermediates
+// Wide32: p >= 2^31, exact canonical arithmetic (the reference's prime32/generic.rs path).
+// Round 2: twiddles in Montgomery form (w * 2^32 mod p), one 32-bit REDC per product -- IMAD.WIDE,
+// IMAD, IMAD.HI and a conditional add instead of a Shoup quotient with a 64-bit remainder -- and
+// add / sub through the complement (p - b) so that nothing needs a 33rd bit: 13 instead of 19
+// instructions per butterfly.
 // ------------------------------------------------------------------------------------
 struct Wide32 {
     using T = uint32_t;
-    using TW = ShoupTw<uint32_t>;
+    using TW = uint32_t;  // w * 2^32 mod p
     struct Ctx {
-        uint32_t p, two_p, pinv, r2;
+        uint32_t p, two_p, pinv, r2;  // pinv = p^-1 mod 2^32, r2 = 2^64 mod p
         uint64_t barrett64;
     };
     static constexpr bool kHarvey = false;
-    NTT_DEVINL static T mul_exact(const Ctx& c, T b, TW w) {
-        uint32_t q = __umulhi(b, w.ws);
-        uint64_t r = (uint64_t)b * w.w - (uint64_t)q * c.p;  // [0, 2p)
-        return (uint32_t)(r >= c.p ? r - c.p : r);
+    // a * wm * 2^-32 mod p, canonical, for any 32-bit a and wm < p
+    NTT_DEVINL static T mul_exact(const Ctx& c, T a, TW wm) {
+        uint64_t t = (uint64_t)a * wm;
+        uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);  // hi <= wm - 1 < p
+        uint32_t u = __umulhi(lo * c.pinv, c.p);              // < p
+        uint32_t r = hi - u;
+        return hi < u ? r + c.p : r;
     }
-    NTT_DEVINL static T add_full(const Ctx& c, T a, T b) {
-        uint64_t s = (uint64_t)a + b;
-        return (uint32_t)(s >= c.p ? s - c.p : s);
+    NTT_DEVINL static T add_full(const Ctx& c, T a, T b) {  // a, b < p
+        uint32_t nb = c.p - b;                               // in (0, p]
+        return a >= nb ? a - nb : a + b;                     // a + b < p when a < p - b: no 33rd bit
     }
-    NTT_DEVINL static T sub_full(const Ctx& c, T a, T b) { return a >= b ? a - b : a + (c.p - b); }
+    NTT_DEVINL static T sub_full(const Ctx& c, T a, T b) {
+        uint32_t d = a - b;
+        return a >= b ? d : d + c.p;
+    }
     NTT_DEVINL static void fwd_bf(const Ctx& c, T& a, T& b, TW w) {
         T t = mul_exact(c, b, w), z0 = a;
         a = add_full(c, z0, t);
@@ -219,7 +229,7 @@ struct Wide32 {
     NTT_DEVINL static T fwd_fin(const Ctx&, T a) { return a; }
     NTT_DEVINL static T inv_fin(const Ctx&, T a) { return a; }
     NTT_DEVINL static T inv_fin_prod(const Ctx&, T a) { return a; }
-    NTT_DEVINL static T mul_const(const Ctx& c, T a, TW w) { return mul_exact(c, a, w); }
+    NTT_DEVINL static T mul_const(const Ctx& c, T a, TW wm) { return mul_exact(c, a, wm); }
     NTT_DEVINL static T mul_full(const Ctx& c, T a, T b) {
         return barrett32((uint64_t)a * b, c.p, c.barrett64);
     }

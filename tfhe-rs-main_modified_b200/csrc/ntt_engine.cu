@@ -70,10 +70,13 @@ struct Build<Shoup<T, H>> {
 template <>
 struct Build<Wide32> {
     using A = Wide32;
-    static A::TW tw(uint64_t w, uint64_t p) { return {(uint32_t)w, (uint32_t)((w << 32) / p)}; }
+    static A::TW tw(uint64_t w, uint64_t p) { return (uint32_t)((w << 32) % p); }  // Montgomery form
     static A::Ctx ctx(uint64_t p) {
         A::Ctx c{};
         c.p = (uint32_t)p;
+        c.two_p = (uint32_t)(2 * p);
+        c.pinv = (uint32_t)inv_mod_2_64(p);  // the low word of p^-1 mod 2^64 is p^-1 mod 2^32
+        c.r2 = (uint32_t)((((u128)1) << 64) % p);
         c.barrett64 = ~uint64_t(0) / p;
         return c;
     }
