@@ -29,8 +29,8 @@ print(json.dumps({"eb": eb, "ms": dt * 1e3, "ntt_per_s": 2 * eb / dt, "GBps_each
 ''' % ROOT
 
 for eb in (32768, 65536):
-    for mib in (4, 8, 16, 32):
-        for ns in (3, 4, 6):
+    for mib in [int(x) for x in os.environ.get("SWEEP_MIB", "4,8,16,32").split(",")]:
+        for ns in [int(x) for x in os.environ.get("SWEEP_STREAMS", "3,4,6").split(",")]:
             env = dict(os.environ, NTT_B200_CHUNK_MIB=str(mib), NTT_B200_STREAMS=str(ns))
             r = subprocess.run([sys.executable, "-c", CODE, str(eb)], env=env, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
