@@ -136,13 +136,10 @@ NTT_DEVINL void ldg_tw_run(const TW* __restrict__ p, TW (&w)[CNT]) {
 // Gentleman-Sande stage of distance d leaves sums at positions with bit d clear and canonical
 // products at positions with bit d set, so which inputs of the next stage are canonical is
 // static.
-// one radix-2 stage (Q-th of R, 2^Q twiddles) of a tuple
-template <class A, int R, int OFF, bool INV, bool ENTRY_CANON, int PPT, int Q, bool PAIR>
-NTT_DEVINL void tuple_stage(typename A::T (&x)[PPT][8], const typename A::TW* __restrict__ tw,
-                            unsigned w0, const typename A::Ctx& c) {
+// one radix-2 stage (Q-th of R, 2^Q twiddles) of a tuple, twiddles already in registers
+template <class A, int R, int OFF, bool INV, bool ENTRY_CANON, int PPT, int Q>
+NTT_DEVINL void tuple_stage_regs(typename A::T (&x)[PPT][8], const typename A::TW* wq, const typename A::Ctx& c) {
     constexpr int d = 1 << (R - 1 - Q);
-    typename A::TW wq[1 << Q];
-    ldg_tw_run<typename A::TW, (1 << Q), PAIR>(tw + (w0 << Q), wq);
 #pragma unroll
     for (int h = 0; h < (1 << Q); ++h) {
         const typename A::TW w = wq[h];
@@ -159,6 +156,14 @@ NTT_DEVINL void tuple_stage(typename A::T (&x)[PPT][8], const typename A::TW* __
             }
         }
     }
+}
+// ... fetched through the read-only path
+template <class A, int R, int OFF, bool INV, bool ENTRY_CANON, int PPT, int Q, bool PAIR>
+NTT_DEVINL void tuple_stage(typename A::T (&x)[PPT][8], const typename A::TW* __restrict__ tw,
+                            unsigned w0, const typename A::Ctx& c) {
+    typename A::TW wq[1 << Q];
+    ldg_tw_run<typename A::TW, (1 << Q), PAIR>(tw + (w0 << Q), wq);
+    tuple_stage_regs<A, R, OFF, INV, ENTRY_CANON, PPT, Q>(x, wq, c);
 }
 template <class A, int R, int OFF, bool INV, bool ENTRY_CANON, int PPT, bool PAIR = true>
 NTT_DEVINL void tuple_ro(typename A::T (&x)[PPT][8], const typename A::TW* __restrict__ tw,
@@ -183,16 +188,35 @@ NTT_DEVINL void last_pass(typename A::T (&x)[PPT][8], const typename A::TW* __re
     constexpr int S = FastShape<LOGN>::kLastStages;
     constexpr bool PAIR = FastPairLoads<LOGN, INV>::value;
     const unsigned m = sub.base(LOGN - S);  // table index of group 0 of the first fused stage
-    if (S == 3) {
+    using TW = typename A::TW;
+    if constexpr (S == 3) {
         tuple_ro<A, 3, 0, INV, ENTRY_CANON, PPT, PAIR>(x, tw, m + u, c);
-    } else if (S == 2) {
-        tuple_ro<A, 2, 0, INV, ENTRY_CANON, PPT, PAIR>(x, tw, m + 2 * u, c);
-        tuple_ro<A, 2, 4, INV, ENTRY_CANON, PPT, PAIR>(x, tw, m + 2 * u + 1, c);
+    } else if constexpr (S == 2) {
+        // Two radix-4 tuples whose twiddles are neighbours in the table (records m+2u, m+2u+1 of the first
+        // stage, 2(m+2u) .. +3 of the second): fetched as one 16-byte and one 32-byte run per thread instead of
+        // per tuple, which halves the sectors / wavefronts a warp touches for them.
+        TW wa[2], wb[4];
+        ldg_tw_run<TW, 2, true>(tw + (m + 2 * u), wa);
+        ldg_tw_run<TW, 4, true>(tw + 2 * (m + 2 * u), wb);
+        if (!INV) {
+            tuple_stage_regs<A, 2, 0, INV, ENTRY_CANON, PPT, 0>(x, wa, c);
+            tuple_stage_regs<A, 2, 4, INV, ENTRY_CANON, PPT, 0>(x, wa + 1, c);
+            tuple_stage_regs<A, 2, 0, INV, ENTRY_CANON, PPT, 1>(x, wb, c);
+            tuple_stage_regs<A, 2, 4, INV, ENTRY_CANON, PPT, 1>(x, wb + 2, c);
+        } else {
+            tuple_stage_regs<A, 2, 0, INV, ENTRY_CANON, PPT, 1>(x, wb, c);
+            tuple_stage_regs<A, 2, 4, INV, ENTRY_CANON, PPT, 1>(x, wb + 2, c);
+            tuple_stage_regs<A, 2, 0, INV, ENTRY_CANON, PPT, 0>(x, wa, c);
+            tuple_stage_regs<A, 2, 4, INV, ENTRY_CANON, PPT, 0>(x, wa + 1, c);
+        }
     } else {
-        tuple_ro<A, 1, 0, INV, ENTRY_CANON, PPT, PAIR>(x, tw, m + 4 * u, c);
-        tuple_ro<A, 1, 2, INV, ENTRY_CANON, PPT, PAIR>(x, tw, m + 4 * u + 1, c);
-        tuple_ro<A, 1, 4, INV, ENTRY_CANON, PPT, PAIR>(x, tw, m + 4 * u + 2, c);
-        tuple_ro<A, 1, 6, INV, ENTRY_CANON, PPT, PAIR>(x, tw, m + 4 * u + 3, c);
+        // four radix-2 butterflies on consecutive pairs: records m+4u .. m+4u+3 in one 32-byte run
+        TW w[4];
+        ldg_tw_run<TW, 4, true>(tw + (m + 4 * u), w);
+        tuple_stage_regs<A, 1, 0, INV, ENTRY_CANON, PPT, 0>(x, w, c);
+        tuple_stage_regs<A, 1, 2, INV, ENTRY_CANON, PPT, 0>(x, w + 1, c);
+        tuple_stage_regs<A, 1, 4, INV, ENTRY_CANON, PPT, 0>(x, w + 2, c);
+        tuple_stage_regs<A, 1, 6, INV, ENTRY_CANON, PPT, 0>(x, w + 3, c);
     }
 }
 
