@@ -585,3 +585,37 @@ print("ok")
         env = dict(os.environ, NTT_B200_ZERO_COPY=zero_copy)
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
         assert r.returncode == 0 and "ok" in r.stdout, (zero_copy, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,p", [(64, SOLINAS_P), (64, 4611686018427322369), (64, 9223372036853661697),
+                                    (64, 18446744073707716609), (32, 1073479681), (32, 2147352577), (32, 4293918721)])
+def test_ragged_batches_every_family_and_polys_per_thread(T, bits, p):
+    """Batch sizes around the polynomials-per-thread / polynomials-per-CTA groupings of the single-CTA kernels
+    (1, 2 or 4 polynomials per thread, up to 8 per CTA for short polynomials): the clamped tail rows must not
+    be stored and every live row must match the oracle, device calls on an offset (still 16-byte aligned) view."""
+    import torch
+    dt = np.uint64 if bits == 64 else np.uint32
+    sdt = np.int64 if bits == 64 else np.int32
+    for n in (256, 512, 1024, 2048, 4096):
+        gp, op = plan_pair(T, bits, n, p)
+        rng = np.random.default_rng(n ^ bits)
+        for batch in (1, 2, 3, 4, 5, 7, 8, 9, 15, 17, 33):
+            hi = rng.integers(0, 1 << 32, size=(batch, n), dtype=np.uint64)
+            lo = rng.integers(0, 1 << 32, size=(batch, n), dtype=np.uint64)
+            x = (((hi << np.uint64(32)) | lo) % np.uint64(p)).astype(dt)  # numpy's uint64 % is exact
+            x[0, :4] = [0, 1, p - 1, p - 1]
+            guard = np.full((2, n), 0xA5A5A5A5, dtype=dt)  # rows before / after the batch must stay untouched
+            buf = np.concatenate([guard[:1], x, guard[1:]])
+            d = torch.from_numpy(buf.view(sdt)).cuda()
+            view = d[1:1 + batch]
+            st = torch.cuda.current_stream()
+            gp.fwd_device(view, batch, stream=st)
+            got = d.cpu().numpy().view(dt)
+            assert (got[0] == guard[0]).all() and (got[-1] == guard[1]).all(), (n, batch)
+            want = op.fwd(x)
+            assert (got[1:1 + batch] == want).all(), (n, batch)
+            gp.inv_device(view, batch, stream=st)
+            got = d.cpu().numpy().view(dt)
+            assert (got[0] == guard[0]).all() and (got[-1] == guard[1]).all(), (n, batch)
+            assert (got[1:1 + batch] == op.inv(want)).all(), (n, batch)
