@@ -522,6 +522,17 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
     }
 }
 
+// Index of polynomial `poly` into an operand that holds `count` polynomials reused cyclically by a batch of
+// `batch`.  The common cases cost nothing: an operand per polynomial (count == batch: the index itself) and
+// one operand for all (count == 1); only a truly periodic operand pays a modulo, 32-bit when it can be --
+// a 64-bit `%` is a ~100-instruction subroutine call, and the fused kernel used to run four of them per thread.
+NTT_DEVINL size_t shared_index(size_t poly, size_t count, size_t batch) {
+    if (count >= batch) return poly;
+    if (count == 1) return 0;
+    if (batch <= 0xFFFFFFFFull) return (size_t)((unsigned)poly % (unsigned)count);
+    return poly % count;
+}
+
 // Fused fwd -> pointwise multiply(-accumulate) -> inv, one pass over HBM (BASELINE C2 / the
 // PBS external product shape):  out = inv(acc + fwd(lhs) * rhs).
 template <class A, int LOGN, int POLYS, int PPT>
@@ -557,11 +568,11 @@ __global__ void __launch_bounds__(FastShape<LOGN>::kThreadsPerPoly* POLYS,
 #pragma unroll
     for (int pp = 0; pp < PPT; ++pp) {
         T r[8];
-        load8_consecutive(rhs + ((poly[pp] % rhs_polys) << LOGN) + 8 * t, r);
+        load8_consecutive(rhs + (shared_index(poly[pp], rhs_polys, batch) << LOGN) + 8 * t, r);
 #pragma unroll
         for (int k = 0; k < 8; ++k) x[pp][k] = A::mul_full(c, A::fwd_fin(c, x[pp][k]), r[k]);
         if (acc) {
-            load8_consecutive(acc + ((poly[pp] % acc_polys) << LOGN) + 8 * t, r);
+            load8_consecutive(acc + (shared_index(poly[pp], acc_polys, batch) << LOGN) + 8 * t, r);
 #pragma unroll
             for (int k = 0; k < 8; ++k) x[pp][k] = A::add_full(c, x[pp][k], r[k]);
         }
