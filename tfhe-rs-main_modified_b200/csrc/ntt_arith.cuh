@@ -357,6 +357,11 @@ struct Solinas64 {
 // ------------------------------------------------------------------------------------
 // Mont64: any odd prime p >= 2^63 other than Solinas.  Twiddles are stored in Montgomery
 // form (w * 2^64 mod p) so that one REDC gives the exact canonical product.
+// Round 2: values travel as arbitrary 64-bit representatives, like Solinas64, with the wrap of a
+// sum folded as + (2^64 - p) and the wrap of a difference as + p (both modulo 2^64): for b < p a
+// single fold can never wrap again (a + b - 2^64 <= p - 2, and a - b + 2^64 >= 2^64 - p + 1), so a
+// butterfly needs no comparison at all -- 5 + 5 carry-chain instructions instead of 10 + 6 with
+// compare / select.  The REDC accepts any 64-bit multiplicand (its high product word stays below p).
 // ------------------------------------------------------------------------------------
 struct Mont64 {
     using T = uint64_t;
@@ -368,32 +373,55 @@ struct Mont64 {
     NTT_DEVINL static T mul_exact(const Ctx& c, T a, TW wm) {
         return redc64(a * wm, __umul64hi(a, wm), c.p, c.pinv);
     }
-    NTT_DEVINL static T add_full(const Ctx& c, T a, T b) {
-        uint64_t s = a + b;
-        return (s < a || s >= c.p) ? s - c.p : s;
+    // a arbitrary, b < p
+    NTT_DEVINL static T add_lazy(const Ctx& c, T a, T b) {
+        const uint64_t cc = 0 - c.p;  // 2^64 - p
+        uint64_t r;
+        asm("{ .reg .u32 a0,a1,b0,b1,c0,c1,k;\n\t"
+            "mov.b64 {a0,a1}, %1; mov.b64 {b0,b1}, %2; mov.b64 {c0,c1}, %3;\n\t"
+            "add.cc.u32 a0,a0,b0; addc.cc.u32 a1,a1,b1; addc.u32 k,0,0;\n\t"
+            "mad.lo.cc.u32 a0,k,c0,a0; madc.lo.u32 a1,k,c1,a1;\n\t"
+            "mov.b64 %0, {a0,a1}; }"
+            : "=l"(r)
+            : "l"(a), "l"(b), "l"(cc));
+        return r;
     }
-    NTT_DEVINL static T sub_full(const Ctx& c, T a, T b) { return a >= b ? a - b : a - b + c.p; }
+    NTT_DEVINL static T sub_lazy(const Ctx& c, T a, T b) {
+        uint64_t r;
+        asm("{ .reg .u32 a0,a1,b0,b1,p0,p1,k;\n\t"
+            "mov.b64 {a0,a1}, %1; mov.b64 {b0,b1}, %2; mov.b64 {p0,p1}, %3;\n\t"
+            "sub.cc.u32 a0,a0,b0; subc.cc.u32 a1,a1,b1; subc.u32 k,0,0;\n\t"  // k = 0 or 0xFFFFFFFF
+            "and.b32 p0,p0,k; and.b32 p1,p1,k;\n\t"
+            "add.cc.u32 a0,a0,p0; addc.u32 a1,a1,p1;\n\t"
+            "mov.b64 %0, {a0,a1}; }"
+            : "=l"(r)
+            : "l"(a), "l"(b), "l"(c.p));
+        return r;
+    }
+    NTT_DEVINL static T canon(const Ctx& c, T a) { return a >= c.p ? a - c.p : a; }  // a < 2^64 < 2p
+    NTT_DEVINL static T add_full(const Ctx& c, T a, T b) { return canon(c, add_lazy(c, a, b)); }
     NTT_DEVINL static void fwd_bf(const Ctx& c, T& a, T& b, TW w) {
         T t = mul_exact(c, b, w), z0 = a;
-        a = add_full(c, z0, t);
-        b = sub_full(c, z0, t);
+        a = add_lazy(c, z0, t);
+        b = sub_lazy(c, z0, t);
     }
-    NTT_DEVINL static void inv_bf(const Ctx& c, T& a, T& b, TW w, bool /*b_canonical*/ = false) {
-        T s = add_full(c, a, b), d = sub_full(c, a, b);
-        a = s;
-        b = mul_exact(c, d, w);
+    // Gentleman-Sande: b is brought into [0, p) unless the caller knows it is (a product of the previous stage)
+    NTT_DEVINL static void inv_bf(const Ctx& c, T& a, T& b, TW w, bool b_canonical = false) {
+        T bc = b_canonical ? b : canon(c, b), z0 = a;
+        a = add_lazy(c, z0, bc);
+        b = mul_exact(c, sub_lazy(c, z0, bc), w);
     }
-    NTT_DEVINL static T fwd_fin(const Ctx&, T a) { return a; }
-    NTT_DEVINL static T inv_fin(const Ctx&, T a) { return a; }
-    NTT_DEVINL static T inv_fin_prod(const Ctx&, T a) { return a; }
+    NTT_DEVINL static T fwd_fin(const Ctx& c, T a) { return canon(c, a); }
+    NTT_DEVINL static T inv_fin(const Ctx& c, T a) { return canon(c, a); }
+    NTT_DEVINL static T inv_fin_prod(const Ctx&, T a) { return a; }  // REDC output is canonical
     NTT_DEVINL static T mul_const(const Ctx& c, T a, TW wm) { return mul_exact(c, a, wm); }
     NTT_DEVINL static T mul_full(const Ctx& c, T a, T b) {
         uint64_t x = redc64(a * b, __umul64hi(a, b), c.p, c.pinv);
         return redc64(x * c.r2, __umul64hi(x, c.r2), c.p, c.pinv);
     }
-    NTT_DEVINL static T acc_add(const Ctx& c, T acc, T prod) { return add_full(c, acc, prod); }
-    NTT_DEVINL static T acc_fin(const Ctx&, T acc) { return acc; }
-    static constexpr bool kPwLazyIn = false;  // values are canonical throughout
+    NTT_DEVINL static T acc_add(const Ctx& c, T acc, T prod) { return add_lazy(c, acc, prod); }
+    NTT_DEVINL static T acc_fin(const Ctx& c, T acc) { return canon(c, acc); }
+    static constexpr bool kPwLazyIn = false;  // the pointwise step canonicalises the transform output first
     NTT_DEVINL static T pw_form(const Ctx& c, T g) { return redc64(g * c.r2, __umul64hi(g, c.r2), c.p, c.pinv); }
     NTT_DEVINL static T mul_pw(const Ctx& c, T x, T gf) { return mul_exact(c, x, gf); }
 };
