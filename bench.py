@@ -31,10 +31,10 @@ ALG_BYTES_PER_NTT = 2 * N * 8  # one in-place NTT reads and writes each coeffici
 E2E_BATCH = 65536              # host-buffer leg: 1 GiB in + 1 GiB out per step
 NCU_TRAFFIC_PER_LAUNCH = {"fwd": 2.1018e9, "inv": 2.0891e9}  # dram read+write bytes of one launch, ncu --set full (profiles/r02_ncu_full_solinas2048_summary.md)
 # Issue cost of one thread of the shipped kernels (two polynomials, 88 butterflies), from the SASS of
-# ntt_fast_{fwd,inv}_kernel<Solinas64,11,1,2> weighted by the measured issue costs of
+# ntt_fast_{fwd,inv}_kernel<Solinas64,11,1,2,false> weighted by the measured issue costs of
 # profiles/r01_int_pipe_microbench.txt (IMAD.WIDE 4 clk, other IMAD 2 clk on the FMA-heavy pipe; IADD3 / LOP3 /
 # SEL / ISETP 2 clk on the ALU pipe); a polynomial pair is 8 warps.
-PIPE_CLK_PER_THREAD = {"fwd": {"fmaheavy": 2800, "alu": 2692}, "inv": {"fmaheavy": 2828, "alu": 3082}}  # profiles/r02_sass_hist_shipped_solinas2048.txt
+PIPE_CLK_PER_THREAD = {"fwd": {"fmaheavy": 2768, "alu": 2670}, "inv": {"fmaheavy": 2768, "alu": 3062}}  # profiles/r02_sass_hist_shipped_solinas2048.txt
 # Busy fraction of the busier integer pipe that the shipped butterfly sustains when nothing else runs (register-resident
 # loop, profiles/r02_solinas_bf_variants.md: 33.75 pipe clocks needed per warp-butterfly, 39.9 measured): the ceiling of
 # roofline_int.
