@@ -333,6 +333,49 @@ def test_native_try_new_none(T):
     assert T.native64.Plan32.try_new(32768) is not None
 
 
+@pytest.mark.parametrize("kind", range(10))
+@pytest.mark.parametrize("n", [1024, 4096, 8192])
+def test_native_plans_at_the_fused_kernel_sizes(T, kind, n):
+    """n = 1024 ... 8192 run the one-CTA-per-product kernels (native_polymul_fused_kernel, ..._fused52_kernel,
+    native_fwd_fused_kernel; 1024-thread CTAs at 8192, the scratch-arena path where the residues do not fit):
+    every kind, a ragged batch, against the oracle and the wrapping schoolbook convolution."""
+    gp = native_cls(T, kind).try_new(n)
+    op = OracleNativePlan(kind, n)
+    assert gp is not None
+    vb = op.value_bytes
+    is_binary = kind >= O.NATIVE_BINARY32_PLAN32
+    rng = np.random.default_rng(kind * 131 + n)
+    batch = 3
+    shape = (batch, n, 2) if vb == 16 else (batch, n)
+    lhs = np.stack([rand_values(rng, vb, n) for _ in range(batch)]).reshape(shape)
+    rhs = np.stack([rand_values(rng, vb, n, binary=is_binary) for _ in range(batch)]).reshape(shape)
+    # edge rows: all ones of the word (the largest value), and a zero polynomial
+    lhs[1] = np.iinfo(lhs.dtype).max
+    if not is_binary:
+        rhs[1] = np.iinfo(rhs.dtype).max
+    lhs[2, : n // 2] = 0
+    prod = np.zeros_like(lhs)
+    gp.negacyclic_polymul_batch(prod, lhs, rhs)
+    for b in range(batch):
+        want = op.negacyclic_polymul(np.ascontiguousarray(lhs[b]), np.ascontiguousarray(rhs[b]))
+        assert (prod[b] == want).all(), (kind, n, b)
+    assert (prod[0] == O.negacyclic_convolution_wrapping(vb, np.ascontiguousarray(lhs[0]), np.ascontiguousarray(rhs[0]))).all()
+    # the fused forward (value read once, residues of every prime written) and the inverse on its output
+    res = [np.zeros(n, dtype=op.rdtype) for _ in range(op.num_primes)]
+    gp.fwd(np.ascontiguousarray(lhs[0]), *res)
+    for a, w in zip(res, op.fwd(np.ascontiguousarray(lhs[0]))):
+        assert (a == w).all()
+    if is_binary:
+        bres = [np.zeros(n, dtype=op.rdtype) for _ in range(op.num_primes)]
+        gp.fwd_binary(np.ascontiguousarray(rhs[0]), *bres)
+        for a, w in zip(bres, op.fwd(np.ascontiguousarray(rhs[0]), binary=True)):
+            assert (a == w).all()
+    want_val, _ = op.inv([r.copy() for r in res])
+    got_val = op.value_array()
+    gp.inv(got_val, *[r.copy() for r in res])
+    assert (got_val == want_val).all()
+
+
 def test_native_batch(T):
     n, batch = 1024, 20
     gp = T.native64.Plan32.try_new(n)
