@@ -662,3 +662,51 @@ def test_ragged_batches_every_family_and_polys_per_thread(T, bits, p):
             got = d.cpu().numpy().view(dt)
             assert (got[0] == guard[0]).all() and (got[-1] == guard[1]).all(), (n, batch)
             assert (got[1:1 + batch] == op.inv(want)).all(), (n, batch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,p", [(64, SOLINAS_P), (64, 4611686018427322369), (64, 9223372036853661697),
+                                    (64, 18446744073707716609), (32, 1073479681), (32, 2147352577), (32, 4293918721)])
+def test_fused_fwd_mac_inv_every_family_ragged_and_shared_operands(T, bits, p):
+    """ntt_fast_fwd_mac_inv_kernel for every modulus family and every single-CTA size: ragged batches, the
+    pointwise operand per polynomial / one row for the whole batch / a cycle of three rows (the kernel's
+    shared_index), with and without an accumulator (per polynomial or one shared row), in place and out of place."""
+    import torch
+    dt = np.uint64 if bits == 64 else np.uint32
+    sdt = np.int64 if bits == 64 else np.int32
+    st = torch.cuda.current_stream()
+
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(sdt)).cuda()
+
+    def below(rng, shape):  # numpy's uint64 % is exact
+        hi = rng.integers(0, 1 << 32, size=shape, dtype=np.uint64)
+        lo = rng.integers(0, 1 << 32, size=shape, dtype=np.uint64)
+        return (((hi << np.uint64(32)) | lo) % np.uint64(p)).astype(dt)
+
+    for n in (256, 512, 1024, 2048, 4096):
+        gp, op = plan_pair(T, bits, n, p)
+        rng = np.random.default_rng(n * 3 + bits)
+        for batch in (1, 3, 6, 9, 33):
+            lhs = below(rng, (batch, n))
+            lhs[0, :3] = [0, 1, p - 1]
+            rhs_full = below(rng, (batch, n))
+            rhs_full[-1, :] = p - 1
+            acc_full = below(rng, (batch, n))
+            f = op.fwd(lhs)
+            for rhs_polys in sorted(c for c in {batch, 1, 3} if batch % c == 0):
+                rhs = rhs_full[:rhs_polys]
+                rhs_rows = np.concatenate([rhs] * (batch // rhs_polys))
+                for acc_polys in (0, batch, 1):
+                    acc_rows = (np.zeros_like(lhs) if acc_polys == 0 else
+                                acc_full if acc_polys == batch else np.tile(acc_full[:1], (batch, 1)))
+                    want = op.inv(op.mul_accumulate(acc_rows.copy(), f, rhs_rows))
+                    d_l = dev(lhs)
+                    d_o = torch.full_like(d_l, 0x5A)
+                    gp.fwd_mac_inv_device(d_o, d_l, dev(rhs), None if acc_polys == 0 else dev(acc_full[:acc_polys]),
+                                          stream=st)
+                    assert (d_o.cpu().numpy().view(dt) == want).all(), (n, batch, rhs_polys, acc_polys)
+                    assert (d_l.cpu().numpy().view(dt) == lhs).all()  # the operand is left alone
+            gp.fwd_mac_inv_device(d_l, d_l, dev(rhs_full), None, stream=st)  # in place
+            assert (d_l.cpu().numpy().view(dt) ==
+                    op.inv(op.mul_accumulate(np.zeros_like(lhs), f, rhs_full))).all(), (n, batch)
