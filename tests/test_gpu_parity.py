@@ -710,3 +710,44 @@ def test_fused_fwd_mac_inv_every_family_ragged_and_shared_operands(T, bits, p):
             gp.fwd_mac_inv_device(d_l, d_l, dev(rhs_full), None, stream=st)  # in place
             assert (d_l.cpu().numpy().view(dt) ==
                     op.inv(op.mul_accumulate(np.zeros_like(lhs), f, rhs_full))).all(), (n, batch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,p", [(64, SOLINAS_P), (64, 4611686018427322369), (64, 9223372036853661697),
+                                    (64, 18446744073707716609), (32, 1073479681), (32, 2147352577), (32, 4293918721)])
+def test_ext_product_every_family_size_and_matrix_shape(T, bits, p):
+    """ntt_fast_ext_product_kernel<A, LOGN, COLS> (and the composition it falls back to) for every modulus family,
+    n = 512 ... 4096 and GGSW shapes rows x cols up to 4 x 4, three batch items with edge rows."""
+    import torch
+    dt = np.uint64 if bits == 64 else np.uint32
+    sdt = np.int64 if bits == 64 else np.int32
+    tdt = torch.int64 if bits == 64 else torch.int32
+
+    def below(rng, shape):
+        hi = rng.integers(0, 1 << 32, size=shape, dtype=np.uint64)
+        lo = rng.integers(0, 1 << 32, size=shape, dtype=np.uint64)
+        return (((hi << np.uint64(32)) | lo) % np.uint64(p)).astype(dt)
+
+    for n in (512, 1024, 2048, 4096):
+        gp, op = plan_pair(T, bits, n, p)
+        rng = np.random.default_rng(n + bits)
+        for rows, cols in ((1, 1), (2, 2), (4, 2), (3, 3), (2, 4), (4, 4), (6, 2)):
+            batch = 3
+            x = below(rng, (batch, rows, n))
+            x[0, 0, :3] = [0, 1, p - 1]
+            x[1] = p - 1
+            g = below(rng, (rows, cols, n))
+            g[0, 0, :] = p - 1
+            d_x = torch.from_numpy(x.view(sdt)).cuda()
+            d_g = torch.from_numpy(g.view(sdt)).cuda()
+            d_o = torch.zeros((batch, cols, n), dtype=tdt, device="cuda")
+            gp.ext_product_device(d_o, d_x, d_g, rows, cols, stream=torch.cuda.current_stream())
+            got = d_o.cpu().numpy().view(dt)
+            assert (d_x.cpu().numpy().view(dt) == x).all() and (d_g.cpu().numpy().view(dt) == g).all()
+            for b in range(batch):
+                f = op.fwd(x[b])
+                for c in range(cols):
+                    acc = np.zeros(n, dtype=dt)
+                    for r in range(rows):
+                        acc = op.mul_accumulate(acc, f[r], g[r, c])
+                    assert (got[b, c] == op.inv(acc)).all(), (n, rows, cols, b, c)
