@@ -751,3 +751,57 @@ def test_ext_product_every_family_size_and_matrix_shape(T, bits, p):
                     for r in range(rows):
                         acc = op.mul_accumulate(acc, f[r], g[r, c])
                     assert (got[b, c] == op.inv(acc)).all(), (n, rows, cols, b, c)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", range(10))
+def test_native_device_batch_calls(T, kind):
+    """fwd_device / inv_device / negacyclic_polymul_device of the CRT plans on device-resident batches
+    (residues of prime j = one [batch][n] array): every row against the oracle, n below, inside and above the
+    sizes of the one-CTA-per-product kernels."""
+    import torch
+    st = torch.cuda.current_stream()
+    for n in (256, 2048, 16384):
+        gp = native_cls(T, kind).try_new(n)
+        op = OracleNativePlan.try_new(kind, n)
+        assert (gp is None) == (op is None)
+        if gp is None:
+            continue
+        vb = op.value_bytes
+        is_binary = kind >= O.NATIVE_BINARY32_PLAN32
+        rng = np.random.default_rng(kind * 7 + n)
+        batch = 5 if n <= 2048 else 2
+        shape = (batch, n, 2) if vb == 16 else (batch, n)
+        lhs = np.stack([rand_values(rng, vb, n) for _ in range(batch)]).reshape(shape)
+        rhs = np.stack([rand_values(rng, vb, n, binary=is_binary) for _ in range(batch)]).reshape(shape)
+        sdt = {4: np.int32, 8: np.int64, 16: np.int64}[vb]
+        rsdt = np.int32 if op.residue_bytes == 4 else np.int64
+        d_l = torch.from_numpy(lhs.view(sdt)).cuda()
+        d_r = torch.from_numpy(rhs.view(sdt)).cuda()
+        d_res = [torch.zeros((batch, n), dtype=torch.int32 if op.residue_bytes == 4 else torch.int64, device="cuda")
+                 for _ in range(op.num_primes)]
+        gp.fwd_device(d_l, d_res, batch, stream=st)
+        res = [r.cpu().numpy().view(op.rdtype) for r in d_res]
+        for b in range(batch):
+            for j, w in enumerate(op.fwd(np.ascontiguousarray(lhs[b]))):
+                assert (res[j][b] == w).all(), (n, b, j)
+        if is_binary:
+            gp.fwd_device(d_r, d_res, batch, binary=True, stream=st)
+            bres = [r.cpu().numpy().view(op.rdtype) for r in d_res]
+            for b in range(batch):
+                for j, w in enumerate(op.fwd(np.ascontiguousarray(rhs[b]), binary=True)):
+                    assert (bres[j][b] == w).all(), (n, b, j)
+            gp.fwd_device(d_l, d_res, batch, stream=st)
+        d_v = torch.zeros_like(d_l)
+        gp.inv_device(d_v, d_res, batch, stream=st)
+        val = d_v.cpu().numpy().view(lhs.dtype).reshape(shape)
+        for b in range(batch):
+            want, _ = op.inv([r[b] for r in res])
+            assert (val[b] == want).all(), (n, b)
+        d_p = torch.zeros_like(d_l)
+        gp.negacyclic_polymul_device(d_p, d_l, d_r, batch=batch, stream=st)
+        prod = d_p.cpu().numpy().view(lhs.dtype).reshape(shape)
+        for b in range(batch):
+            want = op.negacyclic_polymul(np.ascontiguousarray(lhs[b]), np.ascontiguousarray(rhs[b]))
+            assert (prod[b] == want).all(), (n, b)
+        assert (d_l.cpu().numpy().view(lhs.dtype).reshape(shape) == lhs).all()
