@@ -805,3 +805,55 @@ def test_native_device_batch_calls(T, kind):
             want = op.negacyclic_polymul(np.ascontiguousarray(lhs[b]), np.ascontiguousarray(rhs[b]))
             assert (prod[b] == want).all(), (n, b)
         assert (d_l.cpu().numpy().view(lhs.dtype).reshape(shape) == lhs).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,p", [(64, SOLINAS_P), (64, 4611686018427322369), (64, 9223372036853661697),
+                                    (64, 18446744073707716609), (64, 1125899904679937), (32, 1073479681),
+                                    (32, 2147352577), (32, 4293918721)])
+def test_adversarial_canonical_patterns(T, bits, p):
+    """Inputs that push the lazy representatives of every family to the ends of their ranges: constant and
+    alternating vectors of p - 1, values around the 2^32 limb boundaries of the Solinas prime, one-hot vectors,
+    through fwd, inv and the fused fwd+mac+inv, n = 256 ... 16384 (single-CTA and two-pass sizes)."""
+    import torch
+    dt = np.uint64 if bits == 64 else np.uint32
+    sdt = np.int64 if bits == 64 else np.int32
+    specials = [0, 1, 2, p - 1, p - 2, p // 2, p // 2 + 1]
+    if bits == 64:
+        specials += [v for v in ((1 << 32) - 1, 1 << 32, (1 << 32) + 1, p - (1 << 32), p - (1 << 32) + 1,
+                                 (1 << 63) - 1, 1 << 63, 0xFFFFFFFF00000000, 0xFFFFFFFE00000001) if v < p]
+    for n in (256, 2048, 4096, 16384):
+        gp, op = plan_pair(T, bits, n, p)
+        if gp is None:
+            assert op is None
+            continue
+        rows = []
+        for v in specials:
+            rows.append(np.full(n, v, dtype=dt))
+            alt = np.zeros(n, dtype=dt)
+            alt[::2] = v
+            alt[1::2] = p - 1
+            rows.append(alt)
+        for pos in (0, 1, n // 2, n - 1):
+            one_hot = np.zeros(n, dtype=dt)
+            one_hot[pos] = p - 1
+            rows.append(one_hot)
+        ramp = (np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) % np.uint64(p)).astype(dt)
+        rows.append(np.sort(ramp)[::-1].copy())
+        x = np.stack(rows)
+        d = torch.from_numpy(x.view(sdt)).cuda()
+        st = torch.cuda.current_stream()
+        gp.fwd_device(d, x.shape[0], stream=st)
+        f = op.fwd(x)
+        assert (d.cpu().numpy().view(dt) == f).all(), n
+        # the inverse on the special rows themselves (as NTT-domain data) and on the spectra
+        for src in (x, f):
+            d = torch.from_numpy(np.ascontiguousarray(src).view(sdt)).cuda()
+            gp.inv_device(d, src.shape[0], stream=st)
+            assert (d.cpu().numpy().view(dt) == op.inv(src)).all(), n
+        if n <= 4096:
+            d_l = torch.from_numpy(x.view(sdt)).cuda()
+            d_o = torch.empty_like(d_l)
+            gp.fwd_mac_inv_device(d_o, d_l, d_l, d_l, stream=st)  # rhs = acc = the special rows
+            want = op.inv(op.mul_accumulate(x.copy(), f, x))
+            assert (d_o.cpu().numpy().view(dt) == want).all(), n
