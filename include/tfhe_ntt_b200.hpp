@@ -195,6 +195,7 @@ class NativePlan {
     using value_type = V;
     using residue_type = R;
     static constexpr int num_primes = NP;
+    static constexpr bool is_binary = BINARY;
     static std::optional<NativePlan> try_new(size_t n) {
         ntt_b200_native_plan* h = nullptr;
         int st = ntt_b200_native_try_new(KIND, n, &h);

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol(T):
 def test_headers_compile_as_c_and_cpp():
     inc = os.path.join(ROOT, "include")
     subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", HEADER], check=True)
-    for src in ("example_prime.cpp", "example_pbs.cpp"):
+    for src in ("example_prime.cpp", "example_pbs.cpp", "example_native.cpp"):
         subprocess.run(["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-I", inc,
                         os.path.join(ROOT, "tests", "cpp", src)], check=True)
 

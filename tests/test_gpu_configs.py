@@ -252,6 +252,19 @@ def test_cpp_host_mirror_example(T, tmp_path):
     assert "cpp example ok" in r.stdout
 
 
+def test_cpp_host_mirror_native_plans(T, tmp_path):
+    """tests/cpp/example_native.cpp: the reference's product-equals-schoolbook tests of all ten CRT plan types
+    (native64.rs:1180-1244 and siblings) through the C++ mirror of the API."""
+    exe = tmp_path / "example_native"
+    libdir = os.path.dirname(T.library_path())
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "example_native.cpp"), "-o", str(exe),
+                    "-L", libdir, "-ltfhe_ntt_b200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "cpp native ok" in r.stdout
+
+
 def test_batch_edge_sizes(T):
     # ragged batches: sizes that do not fill a CTA, and the chunked host pipeline boundary
     n, p = 256, SOLINAS_P
