@@ -857,3 +857,45 @@ def test_adversarial_canonical_patterns(T, bits, p):
             gp.fwd_mac_inv_device(d_o, d_l, d_l, d_l, stream=st)  # rhs = acc = the special rows
             want = op.inv(op.mul_accumulate(x.copy(), f, x))
             assert (d_o.cpu().numpy().view(dt) == want).all(), n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,p", [(64, q) for q in PRIMES64] + [(32, q) for q in PRIMES32])
+def test_reference_property_product_equals_schoolbook(T, bits, p):
+    """The reference's own unit tests of the prime plans, run on the GPU path (prime64.rs:1305-1361,
+    prime32.rs: `test_product`): for random lhs, rhs < p
+        inv(fwd(lhs) . fwd(rhs)) == n * negacyclic_convolution(lhs, rhs)    (pointwise product via mul_accumulate)
+        inv(mul_assign_normalize(fwd(lhs), fwd(rhs))) == negacyclic_convolution(lhs, rhs)
+    and every fwd output is below p -- against the O(n^2) schoolbook definition, not against the oracle's transform."""
+    dt = np.uint64 if bits == 64 else np.uint32
+    rng = np.random.default_rng(bits + (p & 0xFFFF))
+    for n in (16, 32, 64, 128, 256, 512, 1024, 2048):
+        mod = T.prime64 if bits == 64 else T.prime32
+        gp = mod.Plan.try_new(n, p)
+        if gp is None:  # prime32 plans start at n = 32; (p - 1) may not be divisible by 2n
+            continue
+        hi = rng.integers(0, 1 << 32, size=(2, n), dtype=np.uint64)
+        lo = rng.integers(0, 1 << 32, size=(2, n), dtype=np.uint64)
+        v = (((hi << np.uint64(32)) | lo) % np.uint64(p)).astype(dt)
+        lhs, rhs = v[0].copy(), v[1].copy()
+        conv = O.negacyclic_convolution_mod(bits, p, lhs, rhs)
+        fl, fr = lhs.copy(), rhs.copy()
+        gp.fwd(fl)
+        gp.fwd(fr)
+        assert int(fl.max()) < p and int(fr.max()) < p
+        # product through mul_accumulate on a zero accumulator, then the unnormalised inverse: n * conv
+        acc = np.zeros(n, dtype=dt)
+        gp.mul_accumulate(acc, fl, fr)
+        gp.inv(acc)
+        want_n = np.array([int(c) * n % p for c in conv], dtype=dt)
+        assert (acc == want_n).all(), n
+        # mul_assign_normalize folds the 1/n in
+        prod = fl.copy()
+        gp.mul_assign_normalize(prod, fr)
+        gp.inv(prod)
+        assert (prod == conv).all(), n
+        # normalize(inv(fwd(x))) == x
+        back = fl.copy()
+        gp.inv(back)
+        gp.normalize(back)
+        assert (back == lhs).all(), n
