@@ -297,6 +297,15 @@ def test_native_plans(T, kind, n):
     want_res = op.fwd(value)
     for a, b in zip(res, want_res):
         assert (a == b).all()
+    # the reference's reconstruct_* property (native64.rs:1175-1242): inv(fwd(v)) == v * n, wrapping in the value word
+    back = op.value_array()
+    gp.inv(back, *[r.copy() for r in res])
+    if vb == 16:
+        ints = [((int(h) << 64) | int(l)) * n % (1 << 128) for l, h in value]
+        want_back = np.array([[i & ((1 << 64) - 1), i >> 64] for i in ints], dtype=np.uint64)
+    else:
+        want_back = (value.astype(np.uint64) * np.uint64(n)).astype(value.dtype)
+    assert (back == want_back).all()
     if is_binary:
         bval = rand_values(rng, vb, n, binary=True)
         bres = [np.zeros(n, dtype=op.rdtype) for _ in range(op.num_primes)]
