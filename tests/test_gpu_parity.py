@@ -908,3 +908,36 @@ def test_reference_property_product_equals_schoolbook(T, bits, p):
         gp.inv(back)
         gp.normalize(back)
         assert (back == lhs).all(), n
+
+
+@pytest.mark.gpu
+def test_plans_release_their_device_memory(T):
+    """Creating and dropping plans (prime, CRT, bootstrap key) in a loop must not grow device memory:
+    tables are freed with the handle (Drop in the Rust crate)."""
+    import gc
+    import torch
+    from tfhe_ntt_b200 import ntt64_pbs as G
+
+    def churn(rounds):
+        for i in range(rounds):
+            p64 = T.prime64.Plan.try_new(4096, SOLINAS_P)
+            x = np.arange(4096, dtype=np.uint64)
+            p64.fwd(x)
+            p32 = T.prime32.Plan.try_new(2048, 1073479681)
+            nat = T.native128.Plan32.try_new(1024)
+            lhs = np.ones((1024, 2), dtype=np.uint64)
+            prod = np.zeros_like(lhs)
+            nat.negacyclic_polymul(prod, lhs, lhs)
+            big = T.prime64.Plan.try_new(65536, SOLINAS_P)
+            plan = T.prime64.Plan.try_new(512, SOLINAS_P)
+            bsk = np.zeros(4 * 1 * 2 * 2 * 512, dtype=np.uint64)
+            key = G.NttLweBootstrapKey.from_container(plan, bsk, 4, 2, 10, 1)
+            del p64, p32, nat, big, key, plan
+        gc.collect()
+        torch.cuda.synchronize()
+
+    churn(3)  # warm the per-thread staging buffers and the stream-ordered pool
+    free0, _ = torch.cuda.mem_get_info()
+    churn(40)
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < (8 << 20), (free0, free1)
