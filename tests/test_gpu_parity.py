@@ -1,5 +1,6 @@
 """GPU parity: the CUDA engine (through the C ABI / the tfhe_ntt_b200 host mirror) against the
 CPU oracle on the same seeded inputs.  Bit-exact (integer path)."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -941,3 +942,43 @@ def test_plans_release_their_device_memory(T):
     churn(40)
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < (8 << 20), (free0, free1)
+
+
+@pytest.mark.gpu
+def test_try_new_acceptance_agrees_with_the_oracle_on_random_moduli(T):
+    """Plan::try_new returns None under exactly the reference's rules (prime64.rs:769-774, prime32.rs:667-672):
+    random sizes (powers of two or not) and moduli (primes with and without 2n | p - 1, composites, tiny values);
+    accepted plans must also transform like the oracle's."""
+    rng = np.random.default_rng(2024)
+    sizes = [1, 2, 8, 16, 24, 32, 48, 64, 128, 256, 1000, 1024, 4096]
+    accepted = 0
+    for bits in (64, 32):
+        top = 64 if bits == 64 else 32
+        for trial in range(120):
+            n = sizes[int(rng.integers(0, len(sizes)))]
+            kind = trial % 4
+            width = int(rng.integers(8, top + 1))
+            if kind == 0:    # an NTT-friendly prime for some size
+                m = 1 << int(rng.integers(5, 14))
+                out = C.c_uint64(0)
+                ok = O.lib().tfo_largest_prime_in_arithmetic_progression64(m, 1, 0, (1 << width) - 1, C.byref(out))
+                p = int(out.value) if ok else 1062862849
+            elif kind == 1:  # a random odd number, usually composite
+                p = (int(rng.integers(1, 1 << 62)) >> (62 - min(width, 62))) | 1
+            elif kind == 2:  # tiny and degenerate moduli
+                p = int(rng.integers(0, 40))
+            else:            # even numbers and powers of two
+                p = 1 << int(rng.integers(1, top))
+            p &= (1 << top) - 1
+            mod = T.prime64 if bits == 64 else T.prime32
+            gp = mod.Plan.try_new(n, p)
+            op = OraclePlan.try_new(bits, n, p)
+            assert (gp is None) == (op is None), (bits, n, p)
+            if gp is not None:
+                accepted += 1
+                dt = np.uint64 if bits == 64 else np.uint32
+                x = (rng.integers(0, 1 << 62, size=n, dtype=np.uint64) % np.uint64(p)).astype(dt)
+                y = x.copy()
+                gp.fwd(y)
+                assert (y == op.fwd(x)).all(), (bits, n, p)
+    assert accepted >= 10
