@@ -73,7 +73,9 @@ int ntt_b200_plan64_normalize(const ntt_b200_plan64 *plan, uint64_t *values, siz
  * (lib.rs:658-688) the shorter of the two slices bounds the work */
 int ntt_b200_plan64_mul_assign_normalize(const ntt_b200_plan64 *plan, uint64_t *lhs,
                                          size_t lhs_len, const uint64_t *rhs, size_t rhs_len);
-/* Plan::mul_accumulate(acc, lhs, rhs) prime64.rs:1182-1222 */
+/* Plan::mul_accumulate(acc, lhs, rhs) prime64.rs:1182-1222.  Always the canonical (acc + lhs*rhs) mod p; the
+ * reference's one-step Barrett code (prime64.rs:586-609) returns that value + p for about one product in 10^5 on
+ * moduli below 2^64/3 that need two correction steps -- the only known divergence. */
 int ntt_b200_plan64_mul_accumulate(const ntt_b200_plan64 *plan, uint64_t *acc, size_t acc_len,
                                    const uint64_t *lhs, size_t lhs_len, const uint64_t *rhs,
                                    size_t rhs_len);

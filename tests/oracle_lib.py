@@ -281,6 +281,38 @@ class OraclePlan:
         return "scalar"
 
 
+def reference_barrett_quirk(bits, p):
+    """True for the moduli on which the reference's `mul_accumulate` can return r + p instead of r.
+
+    prime64.rs:733-756 / prime32.rs:606-627 (`BarrettInit*::new`) compute whether the Barrett quotient of a product
+    needs one correction step or two; `can_use_fast_reduction_code` (prime64.rs:814-816, prime32.rs:748-749) nevertheless
+    enables the one-step code (`mul_accumulate_scalar`, prime64.rs:586-609: one `min(prod, prod - p)`, then
+    `min(acc + prod, acc + prod - p)`) for every modulus below 2^W / 3 -- its comment only argues that nothing overflows.
+    For a two-step modulus a product can therefore leave as true_prod + p, and the accumulated value as r + p >= p.
+    (The 52-bit IFMA path, taken only on CPUs with AVX512-IFMA, is used for single-step moduli only.)"""
+    big_q = p.bit_length()
+    big_l = big_q + bits - 1
+    beta = (1 << big_l) % p
+    single_step = beta <= p - (1 << (big_q - 1))
+    below_third = p < ((1 << bits) // 3 + 1)
+    return below_third and not single_step
+
+
+def assert_mul_accumulate_matches_reference(bits, p, got, oracle, what=""):
+    """GPU `mul_accumulate` against the oracle's literal restatement: identical, except that on the moduli of
+    `reference_barrett_quirk` the reference (and so the oracle) may be r + p where the GPU returns the canonical r."""
+    got = np.asarray(got).astype(np.uint64)
+    oracle = np.asarray(oracle).astype(np.uint64)
+    assert int(got.max()) < p, ("non-canonical GPU value", what)
+    diff = oracle - got  # wrapping
+    bad = np.nonzero(diff)[0]
+    if bad.size == 0:
+        return 0
+    assert reference_barrett_quirk(bits, p), ("mismatch on a modulus without the reference's Barrett quirk", what, p)
+    assert (diff[bad] == np.uint64(p)).all(), ("oracle - gpu is neither 0 nor p", what, p)
+    return int(bad.size)
+
+
 def negacyclic_convolution_mod(bits, p, lhs, rhs):
     dt = np.uint64 if bits == 64 else np.uint32
     l = np.ascontiguousarray(lhs, dtype=dt)

@@ -982,3 +982,91 @@ def test_try_new_acceptance_agrees_with_the_oracle_on_random_moduli(T):
                 gp.fwd(y)
                 assert (y == op.fwd(x)).all(), (bits, n, p)
     assert accepted >= 10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,t", [(32, 29), (32, 30), (32, 31), (64, 32), (64, 50), (64, 51), (64, 61), (64, 62), (64, 63)])
+def test_primes_on_both_sides_of_every_dispatch_threshold(T, bits, t):
+    """The modulus families are chosen by the bit length of p (prime64.rs:897-968, prime32.rs:797-843: < 2^30 / 2^31,
+    < 2^50 / 2^51 / 2^62 / 2^63): the largest NTT-friendly prime below 2^t and one just above it, transforms,
+    pointwise operations and the fused kernel against the oracle."""
+    def friendly(lo, hi, m):
+        out = C.c_uint64(0)
+        ok = O.lib().tfo_largest_prime_in_arithmetic_progression64(m, 1, lo, hi, C.byref(out))
+        return int(out.value) if ok else None
+
+    dt = np.uint64 if bits == 64 else np.uint32
+    n = 2048
+    cands = [friendly(0, (1 << t) - 1, 2 * n)]
+    if t < bits:
+        cands.append(friendly(1 << t, (1 << t) + (1 << (t - 4)), 2 * n))
+    rng = np.random.default_rng(t)
+    for p in [c for c in cands if c]:
+        for size in (64, n):
+            gp, op = plan_pair(T, bits, size, p)
+            assert gp is not None and op is not None, (p, size)
+            hi = rng.integers(0, 1 << 32, size=(3, size), dtype=np.uint64)
+            lo = rng.integers(0, 1 << 32, size=(3, size), dtype=np.uint64)
+            x = (((hi << np.uint64(32)) | lo) % np.uint64(p)).astype(dt)
+            x[0, :4] = [0, 1, p - 1, p - 2]
+            x[2] = p - 1
+            y = x.copy()
+            gp.fwd_batch(y)
+            f = op.fwd(x)
+            assert (y == f).all(), (p, size)
+            gp.inv_batch(y)
+            assert (y == op.inv(f)).all(), (p, size)
+            a, b = f[0].copy(), f[1].copy()
+            acc = x[2].copy()
+            gp.mul_accumulate(acc, a, b)
+            # identical to the reference except for its documented one-step Barrett quirk (r + p on two-step moduli)
+            O.assert_mul_accumulate_matches_reference(bits, p, acc, op.mul_accumulate(x[2].copy(), f[0], f[1]), (p, size))
+            exact = np.array([(int(u) * int(v) + p - 1) % p for u, v in zip(f[0], f[1])], dtype=np.uint64)
+            assert (acc.astype(np.uint64) == exact).all(), (p, size)
+            gp.mul_assign_normalize(a, b)
+            assert (a == op.mul_assign_normalize(f[0].copy(), f[1])).all(), (p, size)
+            z = x[1].copy()
+            gp.normalize(z)
+            assert (z == op.normalize(x[1].copy())).all(), (p, size)
+            if size >= 256:
+                out = np.zeros_like(x)
+                gp.fwd_mac_inv_batch(out, x, x)
+                assert (out == op.inv(op.mul_accumulate(np.zeros_like(x), f, x))).all(), (p, size)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,p", [(64, 4899916394578788353), (64, 1125899881086977), (32, 1140830209), (32, 1068236801)])
+def test_reference_one_step_barrett_quirk_is_the_only_divergence(T, bits, p):
+    """The one place where the engine does NOT reproduce the reference bit for bit, pinned down.
+
+    On moduli below 2^W / 3 whose Barrett quotient needs two correction steps the reference's `mul_accumulate`
+    (one-step code, prime64.rs:586-609 / prime32.rs:575-598) can return r + p; the engine always returns the canonical
+    r = (acc + lhs * rhs) mod p.  Over 2^18 random products: the oracle (a literal restatement) and the engine differ
+    only by exactly p, only on such a modulus, and the engine's value is the exact one; `mul_assign_normalize` and
+    `normalize` agree everywhere (their Shoup step absorbs the extra p)."""
+    assert O.reference_barrett_quirk(bits, p)
+    dt = np.uint64 if bits == 64 else np.uint32
+    n, total = 2048, 1 << 18
+    gp, op = plan_pair(T, bits, n, p)
+    rng = np.random.default_rng(p & 0xFFFF)
+
+    def below(count):
+        hi = rng.integers(0, 1 << 32, size=count, dtype=np.uint64)
+        lo = rng.integers(0, 1 << 32, size=count, dtype=np.uint64)
+        return (((hi << np.uint64(32)) | lo) % np.uint64(p)).astype(dt)
+
+    lhs, rhs, acc0 = below(total), below(total), below(total)
+    acc = acc0.copy()
+    gp.mul_accumulate(acc, lhs, rhs)
+    ref = op.mul_accumulate(acc0.copy(), lhs, rhs)
+    hits = O.assert_mul_accumulate_matches_reference(bits, p, acc, ref)
+    idx = np.nonzero(acc != ref)[0]
+    for i in list(idx[:50]) + list(rng.integers(0, total, size=200)):
+        assert int(acc[i]) == (int(lhs[i]) * int(rhs[i]) + int(acc0[i])) % p
+    print("reference quirk hits for p = %d: %d of %d" % (p, hits, total))
+    m = lhs.copy()
+    gp.mul_assign_normalize(m, rhs)
+    assert (m == op.mul_assign_normalize(lhs.copy(), rhs)).all()
+    z = lhs.copy()
+    gp.normalize(z)
+    assert (z == op.normalize(lhs.copy())).all()
