@@ -1070,3 +1070,55 @@ def test_reference_one_step_barrett_quirk_is_the_only_divergence(T, bits, p):
     z = lhs.copy()
     gp.normalize(z)
     assert (z == op.normalize(lhs.copy())).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits", [64, 32])
+def test_every_modulus_width(T, bits):
+    """NTT-friendly primes of every bit length the plans accept (7 ... 64 for prime64, 7 ... 32 for prime32), two per
+    length (the largest one, and one from the lower half of the range, where the reference's Barrett constants behave
+    differently): transforms, pointwise operations and the fused kernel against the oracle."""
+    dt = np.uint64 if bits == 64 else np.uint32
+    rng = np.random.default_rng(bits)
+
+    def friendly(lo, hi, m):
+        out = C.c_uint64(0)
+        ok = O.lib().tfo_largest_prime_in_arithmetic_progression64(m, 1, lo, hi, C.byref(out))
+        return int(out.value) if ok and lo <= int(out.value) <= hi else None
+
+    seen = 0
+    for width in range(7, bits + 1):
+        for size in (32, 512):
+            top = friendly(1 << (width - 1), (1 << width) - 1, 2 * size)
+            low = friendly(1 << (width - 1), (1 << (width - 1)) + (1 << max(width - 3, 0)), 2 * size)
+            for p in sorted({c for c in (top, low) if c}):
+                gp, op = plan_pair(T, bits, size, p)
+                assert (gp is None) == (op is None), (p, size)
+                if gp is None:
+                    continue
+                seen += 1
+                hi = rng.integers(0, 1 << 32, size=(3, size), dtype=np.uint64)
+                lo = rng.integers(0, 1 << 32, size=(3, size), dtype=np.uint64)
+                x = (((hi << np.uint64(32)) | lo) % np.uint64(p)).astype(dt)
+                x[0, :3] = [0, 1, p - 1]
+                x[2] = p - 1
+                y = x.copy()
+                gp.fwd_batch(y)
+                f = op.fwd(x)
+                assert (y == f).all(), (p, size)
+                gp.inv_batch(y)
+                assert (y == op.inv(f)).all(), (p, size)
+                acc = x[2].copy()
+                gp.mul_accumulate(acc, f[0], f[1])
+                O.assert_mul_accumulate_matches_reference(bits, p, acc, op.mul_accumulate(x[2].copy(), f[0], f[1]), (p, size))
+                a = f[0].copy()
+                gp.mul_assign_normalize(a, f[1])
+                assert (a == op.mul_assign_normalize(f[0].copy(), f[1])).all(), (p, size)
+                z = x[1].copy()
+                gp.normalize(z)
+                assert (z == op.normalize(x[1].copy())).all(), (p, size)
+                if size >= 256:
+                    out = np.zeros_like(x)
+                    gp.fwd_mac_inv_batch(out, x, x)
+                    assert (out == op.inv(op.mul_accumulate(np.zeros_like(x), f, x))).all(), (p, size)
+    assert seen > (60 if bits == 64 else 30)
