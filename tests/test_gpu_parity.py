@@ -1122,3 +1122,32 @@ def test_every_modulus_width(T, bits):
                     gp.fwd_mac_inv_batch(out, x, x)
                     assert (out == op.inv(op.mul_accumulate(np.zeros_like(x), f, x))).all(), (p, size)
     assert seen > (60 if bits == 64 else 30)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", range(10))
+def test_native_plans_remaining_sizes(T, kind):
+    """The CRT plans at the sizes the other tests skip (64, 128, 512, 32768, and the first rejected ones): polymul,
+    fwd and inv against the oracle; try_new agrees on acceptance."""
+    for n in (16, 64, 128, 512, 32768, 65536):
+        gp = native_cls(T, kind).try_new(n)
+        op = OracleNativePlan.try_new(kind, n)
+        assert (gp is None) == (op is None), (kind, n)
+        if gp is None:
+            continue
+        vb = op.value_bytes
+        is_binary = kind >= O.NATIVE_BINARY32_PLAN32
+        rng = np.random.default_rng(kind * 17 + n)
+        lhs = rand_values(rng, vb, n)
+        rhs = rand_values(rng, vb, n, binary=is_binary)
+        prod = op.value_array()
+        gp.negacyclic_polymul(prod, lhs, rhs)
+        assert (prod == op.negacyclic_polymul(lhs, rhs)).all(), (kind, n)
+        res = [np.zeros(n, dtype=op.rdtype) for _ in range(op.num_primes)]
+        gp.fwd(lhs, *res)
+        for a, w in zip(res, op.fwd(lhs)):
+            assert (a == w).all(), (kind, n)
+        want_val, _ = op.inv([r.copy() for r in res])
+        got_val = op.value_array()
+        gp.inv(got_val, *[r.copy() for r in res])
+        assert (got_val == want_val).all(), (kind, n)
