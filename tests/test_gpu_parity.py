@@ -1151,3 +1151,53 @@ def test_native_plans_remaining_sizes(T, kind):
         got_val = op.value_array()
         gp.inv(got_val, *[r.copy() for r in res])
         assert (got_val == want_val).all(), (kind, n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,p", [(64, SOLINAS_P), (64, 4611686018427322369), (64, 18446744073707716609),
+                                    (32, 1073479681), (32, 4293918721)])
+def test_device_pointwise_lengths_alignments_and_periods(T, bits, p):
+    """normalize / mul_assign_normalize / mul_accumulate on device buffers: lengths that are not a multiple of the
+    128-bit vector width, pointers off the 16-byte grid (the scalar twins of the vector kernels), operands reused
+    cyclically with periods that do and do not divide the vector width; guard elements around the destination."""
+    import torch
+    dt = np.uint64 if bits == 64 else np.uint32
+    sdt = np.int64 if bits == 64 else np.int32
+    n = 64
+    gp, op = plan_pair(T, bits, n, p)
+    rng = np.random.default_rng(bits * 3 + (p & 7))
+    st = torch.cuda.current_stream()
+    n_inv = pow(n, -1, p)
+
+    def below(count):
+        hi = rng.integers(0, 1 << 32, size=count, dtype=np.uint64)
+        lo = rng.integers(0, 1 << 32, size=count, dtype=np.uint64)
+        return (((hi << np.uint64(32)) | lo) % np.uint64(p)).astype(dt)
+
+    def exact(fn, *cols):
+        return np.array([fn(*[int(v) for v in row]) % p for row in zip(*cols)], dtype=dt)
+
+    for length in (1, 3, 4, 5, 64, 67, 256, 1001, 4096 + 2):
+        for off in (0, 1, 3):
+            for period in sorted({length, 1, 2, 4, 64} & set(d for d in (length, 1, 2, 4, 64) if length % d == 0)):
+                acc0, lhs, rhs = below(length), below(length), below(period)
+                guard = np.full(8, 0x5A5A5A5A, dtype=dt)
+                buf = np.concatenate([guard[: 4 + off], acc0, guard])
+                d_buf = torch.from_numpy(buf.view(sdt)).cuda()
+                d_acc = d_buf[4 + off: 4 + off + length]
+                d_lhs = torch.from_numpy(np.concatenate([guard[:off], lhs]).view(sdt)).cuda()[off:]
+                d_rhs = torch.from_numpy(np.concatenate([guard[:off], rhs]).view(sdt)).cuda()[off:]
+                rhs_rows = np.tile(rhs, length // period)
+                gp.mul_accumulate_device(d_acc, d_lhs, d_rhs, length=length, lhs_len=length, rhs_len=period, stream=st)
+                got = d_buf.cpu().numpy().view(dt)
+                assert (got[: 4 + off] == guard[: 4 + off]).all() and (got[4 + off + length:] == guard).all()
+                assert (got[4 + off: 4 + off + length] == exact(lambda a, l, r: a + l * r, acc0, lhs, rhs_rows)).all(), \
+                    (length, off, period)
+                d_l2 = d_lhs.clone()
+                gp.mul_assign_normalize_device(d_l2, d_rhs, length=length, rhs_len=period, stream=st)
+                assert (d_l2.cpu().numpy().view(dt) == exact(lambda l, r: l * r * n_inv, lhs, rhs_rows)).all(), \
+                    (length, off, period)
+            d_v = torch.from_numpy(np.concatenate([guard[:off], lhs, guard]).view(sdt)).cuda()
+            gp.normalize_device(d_v[off: off + length], length=length, stream=st)
+            got = d_v.cpu().numpy().view(dt)
+            assert (got[off: off + length] == exact(lambda v: v * n_inv, lhs)).all() and (got[off + length:] == guard).all()
