@@ -281,3 +281,49 @@ def test_classic_pbs_rejects_more_decomposition_bits_than_the_modulus_has():
     out = np.zeros((gs - 1) * n + 1, dtype=np.uint64)
     with pytest.raises(NttB200Error):
         G.programmable_bootstrap_ntt64_lwe_ciphertext(lwe.reshape(-1), out, lut.reshape(-1), key)
+
+
+def _random_shapes(seed, count):
+    rng = np.random.default_rng(seed)
+    shapes = []
+    while len(shapes) < count:
+        k = int(rng.integers(1, 4))
+        N = int(rng.choice([256, 512, 1024, 2048]))
+        level = int(rng.integers(1, 7))
+        base_log = int(rng.integers(1, 63 // level + 1))  # the decomposers need base_log * level < 64
+        if k == 3 and N == 2048 and level > 2:
+            continue  # keep the oracle's share of the run time small
+        shapes.append((int(rng.integers(2, 5)), k, N, base_log, level))
+    # decomposition widths at the edges: one bit, 63 bits (the most the decomposers accept), many levels
+    shapes += [(3, 1, 512, 1, 1), (3, 1, 512, 62, 1), (3, 1, 256, 31, 2), (3, 1, 256, 1, 8), (2, 2, 256, 7, 9),
+               (3, 1, 1024, 63, 1), (3, 1, 2048, 21, 3), (2, 1, 4096, 15, 4)]
+    return shapes
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", _random_shapes(5, 16))
+def test_blind_rotate_random_decomposition_shapes(shape):
+    """Random (k, N, base_log, level) within what the decomposers accept, classic and bnf, every device path that
+    takes the shape (auto / composed; identical bits), against the oracle."""
+    n_lwe, k, N, base_log, level = shape
+    rng = np.random.default_rng(sum(shape))
+    G, key, opbs = _setup(rng, *shape)
+    batch = 2
+    lwe = _rand_mod(rng, (batch, n_lwe + 1), P)
+    lwe[0, 0] = 0
+    lut = _rand_mod(rng, (batch, (k + 1) * N), P)
+    want = np.stack([opbs.blind_rotate(lwe[b], lut[b]) for b in range(batch)])
+    for path in (0, 2):
+        got = lut.copy()
+        G.blind_rotate_ntt64_assign(lwe.reshape(-1), got.reshape(-1), key, path=path)
+        assert np.array_equal(got, want), (shape, path)
+    for width in (64, max(base_log * level, 33)):
+        if base_log * level > width:
+            continue
+        msed = rng.integers(0, 2 * N, (batch, n_lwe + 1), dtype=np.uint64)
+        lutb = _rand_u64(rng, (batch, (k + 1) * N), width)
+        wantb = np.stack([opbs.blind_rotate_bnf(msed[b], lutb[b], width) for b in range(batch)])
+        for path in (0, 2):
+            got = lutb.copy()
+            G.blind_rotate_ntt64_bnf_assign(msed.reshape(-1), got.reshape(-1), key, width, path=path)
+            assert np.array_equal(got, wantb), (shape, width, path)
