@@ -1201,3 +1201,73 @@ def test_device_pointwise_lengths_alignments_and_periods(T, bits, p):
             gp.normalize_device(d_v[off: off + length], length=length, stream=st)
             got = d_v.cpu().numpy().view(dt)
             assert (got[off: off + length] == exact(lambda v: v * n_inv, lhs)).all() and (got[off + length:] == guard).all()
+
+
+@pytest.mark.gpu
+def test_mixed_plans_from_many_host_threads(T):
+    """Eight host threads, each hammering a different mix of entry points (prime32 / prime64 single calls on the
+    mapped staging buffer, chunked batches, the fused host pipeline, CRT products, pointwise calls) on plans shared by
+    all of them -- per-thread staging buffers, cached streams and the stream-ordered pool must not interfere."""
+    import threading
+    rng = np.random.default_rng(99)
+    p64, op64 = plan_pair(T, 64, 2048, SOLINAS_P)
+    p32, op32 = plan_pair(T, 32, 1024, 1073479681)
+    big, opbig = plan_pair(T, 64, 16384, SOLINAS_P)
+    nat = T.native64.Plan32.try_new(1024)
+    onat = OracleNativePlan(O.NATIVE64_PLAN32, 1024)
+
+    def below(p, shape, dt):
+        hi = rng.integers(0, 1 << 32, size=shape, dtype=np.uint64)
+        lo = rng.integers(0, 1 << 32, size=shape, dtype=np.uint64)
+        return (((hi << np.uint64(32)) | lo) % np.uint64(p)).astype(dt)
+
+    jobs = []
+    for i in range(8):
+        x64 = below(SOLINAS_P, (5 + i, 2048), np.uint64)
+        x32 = below(1073479681, (3 + i, 1024), np.uint32)
+        xb = below(SOLINAS_P, (2, 16384), np.uint64)
+        l, r = rand_values(rng, 8, 1024), rand_values(rng, 8, 1024)
+        f64 = op64.fwd(x64)
+        jobs.append(dict(
+            x64=x64, f64=f64, i64=op64.inv(f64), x32=x32, f32=op32.fwd(x32), xb=xb, fb=opbig.fwd(xb), l=l, r=r,
+            prod=onat.negacyclic_polymul(l, r),
+            fused=op64.inv(op64.mul_accumulate(np.zeros_like(x64), f64, x64)),
+            mac=op64.mul_accumulate(x64[0].copy(), f64[0], f64[1])))
+    errors = []
+
+    def worker(i):
+        j = jobs[i]
+        try:
+            for rep in range(4):
+                y = j["x64"].copy()
+                p64.fwd_batch(y)
+                assert (y == j["f64"]).all()
+                one = j["x64"][rep % len(y)].copy()
+                p64.fwd(one)
+                assert (one == j["f64"][rep % len(y)]).all()
+                p64.inv_batch(y)
+                assert (y == j["i64"]).all()
+                z = j["x32"].copy()
+                p32.fwd_batch(z)
+                assert (z == j["f32"]).all()
+                w = j["xb"].copy()
+                big.fwd_batch(w)
+                assert (w == j["fb"]).all()
+                prod = np.zeros(1024, dtype=np.uint64)
+                nat.negacyclic_polymul(prod, j["l"], j["r"])
+                assert (prod == j["prod"]).all()
+                out = np.zeros_like(j["x64"])
+                p64.fwd_mac_inv_batch(out, j["x64"], j["x64"])
+                assert (out == j["fused"]).all()
+                acc = j["x64"][0].copy()
+                p64.mul_accumulate(acc, j["f64"][0], j["f64"][1])
+                assert (acc == j["mac"]).all()
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
