@@ -145,3 +145,42 @@ def test_rust_crate_build_lists_every_cuda_source():
     import re
     for name in re.findall(r"pub fn (ntt_b200_\w+)\(", ffi):
         assert re.search(r"\b%s\s*\(" % name, header), name
+
+
+def test_prime_helpers_agree_with_the_oracle_and_a_definition(T):
+    """is_prime64 / largest_prime_in_arithmetic_progression64 are host functions of the library (prime.rs:76-186): against
+    the oracle's restatement and, for small arguments, trial division; strong pseudoprimes and Carmichael numbers included."""
+    import ctypes as C
+    import random
+    import oracle_lib as O
+    L = O.lib()
+    rnd = random.Random(7)
+    hard = [2047, 1373653, 9080191, 25326001, 3215031751, 4759123141, 1122004669633, 2152302898747, 3474749660383,
+            341550071728321, 3825123056546413051, 318665857834031151167461 % (1 << 64), 561, 1105, 1729, 2465, 2821,
+            6601, 8911, 41041, 825265, 321197185, 5394826801, 232250619601, 9746347772161, (1 << 61) - 1, (1 << 64) - 59,
+            (1 << 64) - 1, (1 << 32) + 15, (1 << 32) - 5, 0, 1, 2, 3, 4]
+    values = hard + [rnd.getrandbits(rnd.randint(2, 64)) for _ in range(3000)] + [rnd.getrandbits(64) | 1 for _ in range(2000)]
+    for v in values:
+        assert bool(T.prime.is_prime64(v)) == bool(L.tfo_is_prime64(v)), v
+    for v in range(0, 3000):
+        want = v >= 2 and all(v % d for d in range(2, int(v ** 0.5) + 1))
+        assert bool(T.prime.is_prime64(v)) == want, v
+    import math
+    for _ in range(300):
+        factor = rnd.choice([1, 2, 6, 64, 1 << 12, 1 << 16, 2 * rnd.getrandbits(16) + 2])
+        offset = rnd.choice([1, 5, 7, 11])
+        if math.gcd(factor, offset) != 1:
+            continue  # no prime in the progression: the search walks the whole range
+        lo = rnd.getrandbits(rnd.randint(1, 62))
+        hi = lo + factor * rnd.randint(0, 3000)
+        got = T.prime.largest_prime_in_arithmetic_progression64(factor, offset, lo, hi)
+        first = offset if lo <= offset else lo + (offset - lo) % factor  # smallest term >= lo
+        if first > hi:
+            want = None  # (the reference walks below zero on a range without a term, prime.rs:165-178)
+        else:
+            out = C.c_uint64(0)
+            ok = L.tfo_largest_prime_in_arithmetic_progression64(factor, offset, lo, hi, C.byref(out))
+            want = int(out.value) if ok else None
+        assert got == want, (factor, offset, lo, hi, got, want)
+    assert T.prime.largest_prime_in_arithmetic_progression64(0, 7, 5, 9) == 7
+    assert T.prime.largest_prime_in_arithmetic_progression64(0, 8, 5, 9) is None
