@@ -37,6 +37,7 @@ extern "C" {
 #define NTT_B200_ERR_LEN 2   /* the reference's assert_eq!(buf.len(), ntt_size()) would panic */
 #define NTT_B200_ERR_CUDA 3  /* CUDA runtime failure; see ntt_b200_last_error() */
 #define NTT_B200_ERR_ARG 4   /* null pointer / unknown plan kind */
+#define NTT_B200_ERR_UNSUPPORTED 5 /* a valid call beyond a capacity limit of this implementation (custum_radix *_mut: n > 4096) */
 
 const char *ntt_b200_last_error(void); /* thread-local text of the last NTT_B200_ERR_CUDA */
 int ntt_b200_device_count(void);
@@ -407,8 +408,8 @@ int ntt_b200_largest_prime_in_arithmetic_progression64(uint64_t factor, uint64_t
  * below p -- and the inputs are below p.  For any other table the reference's radix-4 and split-radix
  * recursions (which read tw[(i + q n/4) % n], tw[2k], tw[3k] and J = tw[n/4] directly) and the GPU's
  * single schedule are different functions of the table and the results diverge.
- * The _mut entry points keep every level of one vector in shared memory: n <= 4096, NTT_B200_ERR_LEN
- * above that is a capacity limit of this implementation, not a length mismatch of the caller.
+ * The _mut entry points keep every level of one vector in shared memory: n <= 4096; a longer power-of-two vector
+ * answers NTT_B200_ERR_UNSUPPORTED (a capacity limit of this implementation, not a length mismatch of the caller).
  * ------------------------------------------------------------------------------------------ */
 #define NTT_B200_CR_RADIX2 0      /* fft_radix2_recursive fwd.rs:170-205 (= fwd_1.rs:190-230), ifft inv.rs:178-230 */
 #define NTT_B200_CR_RADIX4 1      /* fft_radix4_recursive fwd.rs:105-168 (= fwd_1.rs:102-188), ifft inv.rs:106-176 */
@@ -425,7 +426,7 @@ int ntt_b200_custum_radix_ifft(int kind, uint32_t *a, size_t n, const uint32_t *
  * and ifft_radix4_recursive_mut(a, inv_twiddles, p, n_inv, top, stats)                  fwd_1.rs:296-379:
  * the values of the routines above plus the fork's multiplication counters, ADDED onto stats[0]
  * (MultStats::nonzero_mults) and stats[1] (skipped_mults), fwd_1.rs:3-7, :28-37.  One vector per call,
- * n <= 4096 (all levels of the transform are kept in shared memory); NTT_B200_ERR_LEN above that. */
+ * n <= 4096 (all levels of the transform are kept in shared memory); NTT_B200_ERR_UNSUPPORTED above that. */
 int ntt_b200_custum_radix_fft_mut(int kind, uint32_t *a, size_t n, const uint32_t *twiddles,
                                   size_t tw_len, uint32_t p, uint64_t *stats);
 /* NEW: the same for `batch` contiguous vectors in one launch (one CTA per vector): the counters of vector v

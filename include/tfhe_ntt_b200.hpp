@@ -27,6 +27,8 @@ inline void check(int status, const char* what) {
     if (status == NTT_B200_OK) return;
     if (status == NTT_B200_ERR_LEN)
         throw std::logic_error(std::string("assertion failed: length mismatch in ") + what);
+    if (status == NTT_B200_ERR_UNSUPPORTED)
+        throw std::length_error(std::string(what) + ": size beyond a capacity limit of this implementation");
     throw std::runtime_error(std::string(what) + ": " + ntt_b200_last_error());
 }
 

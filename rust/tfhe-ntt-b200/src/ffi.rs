@@ -6,6 +6,8 @@ pub const OK: c_int = 0;
 pub const NONE: c_int = 1;
 pub const ERR_LEN: c_int = 2;
 pub const ERR_CUDA: c_int = 3;
+pub const ERR_ARG: c_int = 4;
+pub const ERR_UNSUPPORTED: c_int = 5;
 
 #[repr(C)] pub struct ntt_b200_plan64 { _p: [u8; 0] }
 #[repr(C)] pub struct ntt_b200_plan32 { _p: [u8; 0] }
@@ -124,6 +126,7 @@ pub fn check(status: c_int, what: &str) {
     match status {
         OK => {}
         ERR_LEN => panic!("assertion failed: length mismatch in {what}"),
+        ERR_UNSUPPORTED => panic!("{what}: size beyond a capacity limit of tfhe-ntt-b200 (custum_radix *_mut: n <= 4096)"),
         _ => {
             let msg = unsafe { core::ffi::CStr::from_ptr(ntt_b200_last_error()) };
             eprintln!("tfhe-ntt-b200: {what}: {}", msg.to_string_lossy());

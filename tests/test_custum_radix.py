@@ -415,7 +415,10 @@ def test_gpu_mult_stats_match_the_oracle(n, p):
 def test_mult_stats_rejections_need_no_gpu():
     import tfhe_ntt_b200.custum_radix as cr
     st = cr.MultStats()
-    with pytest.raises(AssertionError):  # the counting kernel keeps every level in shared memory: n <= 4096
+    from tfhe_ntt_b200 import NttB200Error
+    # the counting kernel keeps every level in shared memory: n <= 4096 -- a capacity limit (its own status code),
+    # not the length assertion of the reference
+    with pytest.raises(NttB200Error, match="capacity limit"):
         cr.fft_radix2_recursive_mut(np.zeros(8192, dtype=np.uint32), np.ones(8192, dtype=np.uint32), 17, st)
     with pytest.raises(AssertionError):
         cr.fft_split_radix_recursive_mut(np.zeros(12, dtype=np.uint32), np.ones(16, dtype=np.uint32), 17, st)

@@ -7,7 +7,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libtfhe_ntt_b200.so"
 
-OK, NONE, ERR_LEN, ERR_CUDA, ERR_ARG = 0, 1, 2, 3, 4
+OK, NONE, ERR_LEN, ERR_CUDA, ERR_ARG, ERR_UNSUPPORTED = 0, 1, 2, 3, 4, 5
 
 
 class NttB200Error(RuntimeError):
@@ -161,6 +161,8 @@ def check(status, what=""):
         raise AssertionError("length mismatch %s" % what)
     if status == ERR_CUDA:
         raise NttB200Error("CUDA failure %s: %s" % (what, last_error()))
+    if status == ERR_UNSUPPORTED:
+        raise NttB200Error("size beyond a capacity limit of this implementation %s" % what)
     raise NttB200Error("error %d %s" % (status, what))
 
 

@@ -561,7 +561,8 @@ int run_host(int kind, uint32_t* host, size_t n, size_t batch, const uint32_t* t
 int run_stats(int kind, uint32_t* host, size_t n, size_t batch, const uint32_t* tw, size_t tw_len, uint32_t p,
               uint32_t factor, uint64_t* stats) {
     if (kind < 0 || kind > NTT_B200_CR_STATS_IFFT_RADIX4 || p < 2 || (batch && !stats)) return NTT_B200_ERR_ARG;
-    if (n == 0 || (n & (n - 1)) || n > (size_t(1) << kStatsLogMax) || (n > 2 && tw_len < n)) return NTT_B200_ERR_LEN;
+    if (n == 0 || (n & (n - 1)) || (n > 2 && tw_len < n)) return NTT_B200_ERR_LEN;
+    if (n > (size_t(1) << kStatsLogMax)) return NTT_B200_ERR_UNSUPPORTED;  // capacity of the counting kernel, not a caller error
     if (batch && (!host || (n > 2 && !tw))) return NTT_B200_ERR_ARG;
     if (!batch) return NTT_B200_OK;
     return guarded([&] {
