@@ -17,6 +17,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "tfhe_ntt_b200.h"
@@ -87,6 +88,12 @@ struct Div64 {
         Plan clone() const {                                                                      \
             ntt_b200_plan##SFX* h = nullptr;                                                      \
             check(ntt_b200_plan##SFX##_clone(h_.get(), &h), "clone");                             \
+            return Plan(h);                                                                       \
+        }                                                                                         \
+        /* an owning handle on a plan borrowed from another object (shares its device tables) */ \
+        static Plan clone_of(const ntt_b200_plan##SFX* borrowed) {                                \
+            ntt_b200_plan##SFX* h = nullptr;                                                      \
+            check(ntt_b200_plan##SFX##_clone(borrowed, &h), "clone");                             \
             return Plan(h);                                                                       \
         }                                                                                         \
         size_t ntt_size() const { return ntt_b200_plan##SFX##_ntt_size(h_.get()); }               \
@@ -206,6 +213,27 @@ class NativePlan {
         return NativePlan(h);
     }
     size_t ntt_size() const { return ntt_b200_native_ntt_size(h_.get()); }
+    // ntt_0() .. ntt_9(): the per-prime plans (native64.rs:950-968, :1095-1103).  The reference returns `&Plan`; here a
+    // cheap clone that shares the device tables of the CRT plan.
+    using prime_plan = std::conditional_t<sizeof(R) == 4, prime32::Plan, prime64::Plan>;
+    prime_plan ntt_i(int i) const {
+        const void* b = (i >= 0 && i < NP) ? ntt_b200_native_ntt_i(h_.get(), i) : nullptr;
+        if (!b) throw std::out_of_range("ntt_i: this plan has no such prime");
+        if constexpr (sizeof(R) == 4)
+            return prime32::Plan::clone_of(static_cast<const ntt_b200_plan32*>(b));
+        else
+            return prime64::Plan::clone_of(static_cast<const ntt_b200_plan64*>(b));
+    }
+    prime_plan ntt_0() const { return ntt_i(0); }
+    prime_plan ntt_1() const { return ntt_i(1); }
+    prime_plan ntt_2() const { return ntt_i(2); }
+    prime_plan ntt_3() const { return ntt_i(3); }
+    prime_plan ntt_4() const { return ntt_i(4); }
+    prime_plan ntt_5() const { return ntt_i(5); }
+    prime_plan ntt_6() const { return ntt_i(6); }
+    prime_plan ntt_7() const { return ntt_i(7); }
+    prime_plan ntt_8() const { return ntt_i(8); }
+    prime_plan ntt_9() const { return ntt_i(9); }
     // fwd(value, mod_p0, .., mod_p{NP-1})   e.g. native64.rs:970
     void fwd(const V* value, size_t len, const std::array<R*, NP>& mod_p) const {
         void* r[NP];

@@ -67,11 +67,28 @@ static int check_plan(size_t n, bool binary_rhs, uint64_t seed) {
         return 6;
     } catch (const std::logic_error&) {
     }
+    // ntt_0() .. : the per-prime plans; the residues of fwd are their transforms of value mod p_i
+    for (int i = 0; i < NP; ++i)
+        if (plan->ntt_i(i).ntt_size() != n || plan->ntt_i(i).modulus() < 2) return 8;
+    if (plan->ntt_0().modulus() == (NP > 1 ? plan->ntt_i(NP - 1).modulus() : 0)) return 9;
+    try {
+        plan->ntt_i(NP);
+        return 10;
+    } catch (const std::out_of_range&) {
+    }
     // fwd writes NP residue polynomials below their primes; on the binary plans fwd_binary agrees with fwd
     std::vector<std::vector<R>> res(NP, std::vector<R>(n)), res_b(NP, std::vector<R>(n));
     std::array<R*, NP> ptr, ptr_b;
     for (int i = 0; i < NP; ++i) ptr[i] = res[i].data(), ptr_b[i] = res_b[i].data();
     plan->fwd(r.data(), n, ptr);
+    {
+        // residue 0 is ntt_0().fwd of the value reduced modulo its prime (native64.rs:970-998)
+        auto p0 = plan->ntt_0();
+        std::vector<R> direct(n);
+        for (size_t i = 0; i < n; ++i) direct[i] = (R)((unsigned __int128)r[i] % (unsigned __int128)p0.modulus());
+        p0.fwd(direct);
+        if (direct != res[0]) return 11;
+    }
     if constexpr (Plan::is_binary) {
         if (binary_rhs) {
             plan->fwd_binary(r.data(), n, ptr_b);
